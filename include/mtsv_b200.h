@@ -1,0 +1,173 @@
+/*
+ * mtsv_b200.h — C ABI of the B200 (sm_100a) implementation of mtsv-binner's
+ * read-assignment hot path.
+ *
+ * Boundary replaced (reference = FofanovLab/mtsv_tools v2.1.0):
+ *   MGIndex::matching_tax_ids                       src/index.rs:258-432
+ *   the per-read worker closure that calls it 2x    src/binner.rs:77-131
+ *   from_file::<MGIndex>                            src/io.rs:115-122
+ * FFI precedent this header follows (callee allocates, paired free function,
+ * plain pointers and sizes, reentrant per handle): ssw/src/lib.rs:132-154,
+ * ssw/build.rs:3-7.  INTEGRATION.md shows the Rust `extern "C"` block a
+ * maintainer would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative MTSVGPU_E* code;
+ *     mtsvgpu_last_error() gives a thread-local message for the last failure;
+ *   - one mtsvgpu_index per GPU; calls on one handle must be serialised by the
+ *     caller, distinct handles are independent;
+ *   - buffers returned through `**` are allocated by the library and released
+ *     with mtsvgpu_free();
+ *   - there is NO CPU fallback: without a CUDA device every entry point that
+ *     computes fails with MTSVGPU_ENODEVICE.
+ */
+#ifndef MTSV_B200_H
+#define MTSV_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define MTSVGPU_API __attribute__((visibility("default")))
+#else
+#define MTSVGPU_API
+#endif
+
+#define MTSVGPU_OK 0
+#define MTSVGPU_EINVAL -1    /* bad argument */
+#define MTSVGPU_EIO -2       /* cannot open / short read */
+#define MTSVGPU_EFORMAT -3   /* .index does not parse as a bincode MGIndex or fails validation */
+#define MTSVGPU_ENODEVICE -4 /* no usable CUDA device */
+#define MTSVGPU_ECUDA -5     /* CUDA runtime error */
+#define MTSVGPU_ENOMEM -6    /* host or device allocation failed */
+#define MTSVGPU_ELIMIT -7    /* input exceeds a documented limit (index >= 2^32 symbols, read too long, hit explosion) */
+
+typedef struct mtsvgpu_index mtsvgpu_index;
+
+/* `Hit` — src/index.rs:30-40.  offset = window start - bin start (src/index.rs:416). */
+typedef struct {
+  uint32_t tax_id;
+  uint32_t gi;
+  uint64_t offset;
+  uint32_t edit;
+  uint32_t reserved;
+} mtsvgpu_hit;
+
+/* `Bin` — src/index.rs:44-54 (same field order as the bincode record). */
+typedef struct {
+  uint32_t gi;
+  uint32_t tax_id;
+  uint64_t start;
+  uint64_t end;
+} mtsvgpu_bin;
+
+/* Arguments of matching_tax_ids — src/index.rs:258-269; CLI defaults src/bin/mtsv-binner.rs:68-94. */
+typedef struct {
+  double edit_rate;        /* edit_freq            (--edit-rate, 0.13)   */
+  uint32_t seed_size;      /* seed_length          (--seed-size, 18)     */
+  uint32_t seed_gap;       /* seed_gap             (--seed-interval, 15) */
+  double min_seed;         /* min_seeds_percent    (--min-seed, 0.015)   */
+  uint64_t max_hits;       /* max_hits             (--max-hits, 2000)    */
+  uint64_t tune_max_hits;  /* tune_max_hits        (--tune-max-hits, 200)*/
+  int64_t max_candidates;  /* max_candidates_checked, -1 = None          */
+  int64_t max_assignments; /* max_hits_found,         -1 = None          */
+  uint32_t strands;        /* 2 (or 0) = forward then reverse complement, as src/binner.rs:102-128;
+                              1 = the given strand only, i.e. one matching_tax_ids call */
+  uint32_t reserved;
+} mtsvgpu_params;
+
+/* Device-side re-layout options (all optional; pass NULL for defaults). */
+typedef struct {
+  uint32_t sa_rate;       /* suffix-array sample rate kept on the device: 0 = auto (1 = full SA when it
+                             fits the memory budget), otherwise a divisor of the file's rate          */
+  uint32_t ktab_k;        /* k-mer interval table order: 0 = auto, 1..16; 0xFFFFFFFF = none           */
+  uint64_t max_batch_hits;/* cap on seed hits in flight per device sub-batch (0 = default 1<<27)      */
+  uint32_t batch_reads;   /* reads per device sub-batch (0 = default 1<<20)                            */
+  uint32_t reserved;
+} mtsvgpu_index_opts;
+
+typedef struct {
+  uint64_t text_len;       /* n, including the '$' terminator */
+  uint64_t n_bins;
+  uint64_t file_sa_rate;   /* s of the .index file */
+  uint32_t device_sa_rate; /* s' kept on the device */
+  uint32_t ktab_k;
+  uint64_t device_bytes;   /* bytes of HBM held by the index */
+  uint64_t dollar_row;
+  double load_seconds;     /* parse + upload + re-layout */
+  double relayout_seconds; /* device re-layout only */
+} mtsvgpu_index_info;
+
+/* Per-stage device time of the last mtsvgpu_bin_batch*(), CUDA events on the launch stream (ms). */
+#define MTSVGPU_N_STAGES 12
+typedef struct {
+  float ms[MTSVGPU_N_STAGES];
+  uint64_t launches[MTSVGPU_N_STAGES];
+  /* work actually performed, for the roofline */
+  uint64_t n_queries;      /* read-strands */
+  uint64_t n_seed_slots;   /* seeds searched */
+  uint64_t n_seed_hits;    /* SA rows located */
+  uint64_t n_candidates;   /* windows verified */
+  uint64_t n_hits;         /* hits returned */
+  uint64_t window_bytes;   /* reference bytes read by the verifier */
+  uint64_t rank_queries;   /* occurrence-rank queries executed by seed search (0 unless profiling) */
+} mtsvgpu_batch_stats;
+
+/* ---- index lifetime: replaces from_file::<MGIndex> (src/io.rs:115-122, src/binner.rs:63-67) ---- */
+MTSVGPU_API int mtsvgpu_index_open(const char* index_path, int device, const mtsvgpu_index_opts* opts,
+                       mtsvgpu_index** out);
+/* Same, from the in-memory fields of an MGIndex (src/index.rs:60-68): text incl. '$', bins, the
+ * byte BWT and the row-sampled suffix array (rows 0,s,2s,..). */
+MTSVGPU_API int mtsvgpu_index_from_parts(const uint8_t* text, uint64_t n, const mtsvgpu_bin* bins,
+                             uint64_t n_bins, const uint8_t* bwt, const uint64_t* sa_sample,
+                             uint64_t sa_sample_len, uint64_t sa_rate, int device,
+                             const mtsvgpu_index_opts* opts, mtsvgpu_index** out);
+MTSVGPU_API void mtsvgpu_index_close(mtsvgpu_index* ix);
+MTSVGPU_API int mtsvgpu_index_get_info(const mtsvgpu_index* ix, mtsvgpu_index_info* info);
+
+/* ---- the hot path: replaces the worker closure of run_fastx_pipeline (src/binner.rs:77-131) ----
+ * seqs: concatenated raw read bytes exactly as parsed from FASTA/FASTQ (normalisation of
+ * src/binner.rs:88-100 happens on the device); seq_off: n_reads+1 offsets into seqs.
+ * Output is CSR by read: hits of read i are (*hits)[(*hit_off)[i] .. (*hit_off)[i+1]), forward-strand
+ * hits first then reverse-complement hits, each in the reference's acceptance order. */
+MTSVGPU_API int mtsvgpu_bin_batch(mtsvgpu_index* ix, const uint8_t* seqs, const uint64_t* seq_off,
+                      uint64_t n_reads, const mtsvgpu_params* params, mtsvgpu_hit** hits,
+                      uint64_t** hit_off);
+/* Same with inputs already resident in device memory and results left there.  The returned device
+ * pointers are owned by the handle and stay valid until its next batch call or close. */
+MTSVGPU_API int mtsvgpu_bin_batch_device(mtsvgpu_index* ix, const uint8_t* d_seqs, const uint64_t* d_seq_off,
+                             uint64_t n_reads, const mtsvgpu_params* params,
+                             const mtsvgpu_hit** d_hits, const uint64_t** d_hit_off,
+                             uint64_t* n_hits);
+MTSVGPU_API int mtsvgpu_last_batch_stats(const mtsvgpu_index* ix, mtsvgpu_batch_stats* stats);
+/* Launch on a caller-provided cudaStream_t (e.g. torch's current stream); NULL = the handle's own. */
+MTSVGPU_API int mtsvgpu_set_stream(mtsvgpu_index* ix, void* cuda_stream);
+/* Collect per-stage CUDA-event timings (costs a few event records per stage); 0 = off (default). */
+MTSVGPU_API int mtsvgpu_set_profiling(mtsvgpu_index* ix, int on);
+
+/* ---- stage-level entry points (parity tests of the individual kernels) ---- */
+/* FMIndex::backward_search (bio 3.0.0; call site src/index.rs:305) for n_pats patterns of equal
+ * length over {A,C,G,T,N}: lower/upper = half-open SA interval when the result is Complete, else 0,0. */
+MTSVGPU_API int mtsvgpu_backward_search(mtsvgpu_index* ix, const uint8_t* pats, uint32_t pat_len,
+                            uint64_t n_pats, uint64_t* lower, uint64_t* upper);
+/* SampledSuffixArray::get (bio 3.0.0; call site src/index.rs:347): text position of each SA row. */
+MTSVGPU_API int mtsvgpu_locate(mtsvgpu_index* ix, const uint64_t* rows, uint64_t n_rows, uint64_t* pos);
+/* Aligner::min_edit_distance (src/align.rs:28-85) for n pairs; pattern i = pats[pat_off[i]..pat_off[i+1]),
+ * text i likewise.  Bytes are compared as-is except that, as at src/index.rs:272-279, callers wanting
+ * the binner's rule replace 'N' by '.' in the pattern beforehand; any byte outside ACGT never matches. */
+MTSVGPU_API int mtsvgpu_edit_distance(int device, const uint8_t* pats, const uint64_t* pat_off,
+                          const uint8_t* texts, const uint64_t* text_off, uint64_t n_pairs,
+                          uint32_t* edits);
+
+MTSVGPU_API void mtsvgpu_free(void* p);
+MTSVGPU_API const char* mtsvgpu_last_error(void);
+/* Number of kernels this library has launched in this process (all handles). */
+MTSVGPU_API uint64_t mtsvgpu_launch_count(void);
+MTSVGPU_API const char* mtsvgpu_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MTSV_B200_H */

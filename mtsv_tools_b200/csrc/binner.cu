@@ -1,0 +1,970 @@
+// binner.cu — the read-assignment hot path as a chain of sm_100a kernels.
+//
+// Replaces the worker closure of run_fastx_pipeline (src/binner.rs:77-131) and
+// MGIndex::matching_tax_ids (src/index.rs:258-432) for a whole batch of reads:
+//
+//   count/scan      seed slots per read-strand ("query")
+//   seed_search     one thread per seed slot: k-mer table lookup + rank steps     [HBM random sectors]
+//   seed_select     one thread per query: replay the max-hits / tune-max-hits rule
+//   locate          SA lookups (or LF walks when the SA is kept sampled)           [HBM random sectors]
+//   sort            segmented sort of (ref_pos, q_off) keys per query
+//   coalesce        one thread per query: windows + merge                          (src/index.rs:435-487)
+//   rank            segmented sort by num_seeds, compaction to a dense candidate list
+//   verify          one thread per candidate: Myers bit-vector edit distance       [SM integer issue]
+//   select/emit     one thread per query: per-TaxID first pass, limits, CSR output
+//
+// All per-item arithmetic lives in core.cuh (shared with the CPU emulation tests).
+#include <algorithm>
+
+#include "ctx.h"
+
+namespace mtsv {
+
+// ------------------------------------------------------------------------------------------
+// small kernels
+// ------------------------------------------------------------------------------------------
+struct BatchCounters {  // device-side scalars of one sub-batch
+  unsigned long long total_slots, total_hits, total_cands, total_out;
+  unsigned int max_len, overflow, n_medium, n_large, medium_cursor, large_cursor;
+  unsigned long long rank_steps, window_bytes;
+};
+
+__global__ void count_slots_kernel(ReadsView rv, Params p, uint32_t nq, uint32_t* __restrict__ q_nslots,
+                                   BatchCounters* __restrict__ ctr) {
+  uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t L = 0;
+  if (q < nq) {
+    L = query_len(rv, p.ns, q);
+    q_nslots[q] = seed_slots(L, p.S, p.G);
+  }
+  // block max of L -> one atomic per block
+  __shared__ unsigned int smax;
+  if (threadIdx.x == 0) smax = 0;
+  __syncthreads();
+  unsigned int wmax = __reduce_max_sync(0xffffffffu, L);
+  if ((threadIdx.x & 31) == 0) atomicMax(&smax, wmax);
+  __syncthreads();
+  if (threadIdx.x == 0) atomicMax(&ctr->max_len, smax);
+}
+
+__global__ void expand_slots_kernel(const uint32_t* __restrict__ slot_off, uint32_t nq,
+                                    uint32_t* __restrict__ slot_q) {
+  uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= nq) return;
+  uint32_t b = slot_off[q], e = slot_off[q + 1];
+  for (uint32_t s = b; s < e; ++s) slot_q[s] = q;
+}
+
+// seed search: one thread per slot.  Each thread owns one dependent chain of sector fetches;
+// ~2048 chains per SM keep the HBM random-access pipeline full.
+__global__ void __launch_bounds__(256) seed_search_kernel(FmView fm, KtabView kt, ReadsView rv, Params p,
+                                                          const uint32_t* __restrict__ slot_off,
+                                                          const uint32_t* __restrict__ slot_q,
+                                                          uint32_t n_slots,
+                                                          uint32_t* __restrict__ slot_lo,
+                                                          uint32_t* __restrict__ slot_cnt,
+                                                          BatchCounters* __restrict__ ctr, int count_ranks) {
+  uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t steps = 0;
+  if (s < n_slots) {
+    uint32_t q = slot_q[s];
+    uint32_t j = s - slot_off[q];
+    uint32_t L = query_len(rv, p.ns, q);
+    uint32_t lo, cnt;
+    seed_search_item(fm, kt, query_seq(rv, p.ns, q), q % p.ns, L, p.S, j * p.G, &lo, &cnt, &steps);
+    slot_lo[s] = lo;
+    slot_cnt[s] = cnt;
+  }
+  if (count_ranks) {
+    unsigned int w = __reduce_add_sync(0xffffffffu, steps);
+    if ((threadIdx.x & 31) == 0 && w) atomicAdd(&ctr->rank_steps, (unsigned long long)w);
+  }
+}
+
+__global__ void seed_select_kernel(Params p, const uint32_t* __restrict__ slot_off, uint32_t nq,
+                                   const uint32_t* __restrict__ slot_cnt, uint32_t* __restrict__ slot_hoff,
+                                   uint32_t* __restrict__ q_nseeds, uint32_t* __restrict__ q_nhits,
+                                   BatchCounters* __restrict__ ctr) {
+  uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= nq) return;
+  uint32_t b = slot_off[q], e = slot_off[q + 1];
+  uint32_t ns = 0, nh = 0, ovf = 0;
+  seed_select_item(p, e - b, slot_cnt + b, slot_hoff + b, &ns, &nh, &ovf);
+  q_nseeds[q] = ns;
+  q_nhits[q] = nh;
+  if (ovf) atomicExch(&ctr->overflow, 1u);
+}
+
+// locate: one lane per slot; intervals with more than a few rows are spread over the warp so that
+// consecutive SA entries are read coalesced and long LF walks are shared.
+__global__ void __launch_bounds__(256) locate_kernel(FmView fm, SaView sv, Params p,
+                                                     const uint32_t* __restrict__ slot_off,
+                                                     const uint32_t* __restrict__ slot_q, uint32_t n_slots,
+                                                     const uint32_t* __restrict__ slot_lo,
+                                                     const uint32_t* __restrict__ slot_cnt,
+                                                     const uint32_t* __restrict__ slot_hoff,
+                                                     const uint32_t* __restrict__ hit_off,
+                                                     uint64_t* __restrict__ hit_keys) {
+  uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned lane = threadIdx.x & 31;
+  uint32_t cnt = 0, lo = 0, dst = 0, qoff = 0;
+  if (s < n_slots) {
+    uint32_t ho = slot_hoff[s];
+    if (ho != kUnused) {
+      uint32_t q = slot_q[s];
+      cnt = slot_cnt[s];
+      lo = slot_lo[s];
+      dst = hit_off[q] + ho;
+      qoff = (s - slot_off[q]) * p.G;
+    }
+  }
+  constexpr uint32_t kSolo = 4;
+  if (cnt <= kSolo) {
+    for (uint32_t j = 0; j < cnt; ++j)
+      hit_keys[dst + j] = make_hit_key(fm_locate(fm, sv, lo + j, nullptr), qoff);
+  }
+  unsigned big = __ballot_sync(0xffffffffu, cnt > kSolo);
+  while (big) {
+    int src = __ffs(big) - 1;
+    big &= big - 1;
+    uint32_t c = __shfl_sync(0xffffffffu, cnt, src);
+    uint32_t l = __shfl_sync(0xffffffffu, lo, src);
+    uint32_t d = __shfl_sync(0xffffffffu, dst, src);
+    uint32_t o = __shfl_sync(0xffffffffu, qoff, src);
+    for (uint32_t j = lane; j < c; j += 32)
+      hit_keys[d + j] = make_hit_key(fm_locate(fm, sv, l + j, nullptr), o);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// segmented sort of u64 keys: bitonic network in its "all ascending" form (first step of each
+// merge compares i with its mirror i ^ (k-1)), which tolerates virtual +inf padding, so segment
+// lengths need not be powers of two.  Segment q = keys[seg_off[q] .. + seg_cnt[q]).
+//   <= 32 keys : one warp, registers + shuffles
+//   <= 4096    : one CTA, shared memory
+//   larger     : one CTA, in place in global memory (rare: > 4096 seed hits for one read-strand)
+// ------------------------------------------------------------------------------------------
+constexpr uint32_t kSortMedium = 4096;
+
+__device__ __forceinline__ uint64_t warp_sort_u64(uint64_t v, unsigned lane) {
+#pragma unroll
+  for (int k = 2; k <= 32; k <<= 1) {
+    {
+      uint64_t o = __shfl_xor_sync(0xffffffffu, v, k - 1);
+      bool low = (lane & (k - 1)) < ((lane ^ (k - 1)) & (k - 1));
+      v = low ? (v < o ? v : o) : (v > o ? v : o);
+    }
+#pragma unroll
+    for (int j = k >> 2; j > 0; j >>= 1) {
+      uint64_t o = __shfl_xor_sync(0xffffffffu, v, j);
+      bool low = (lane & j) == 0;
+      v = low ? (v < o ? v : o) : (v > o ? v : o);
+    }
+  }
+  return v;
+}
+
+__global__ void __launch_bounds__(256) sort_small_kernel(uint64_t* __restrict__ keys,
+                                                         const uint32_t* __restrict__ seg_off,
+                                                         const uint32_t* __restrict__ seg_cnt, uint32_t nq,
+                                                         uint32_t* __restrict__ medium_list,
+                                                         uint32_t* __restrict__ large_list,
+                                                         BatchCounters* __restrict__ ctr) {
+  uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const unsigned lane = threadIdx.x & 31;
+  if (q >= nq) return;
+  uint32_t n = seg_cnt[q];
+  if (n < 2) return;
+  if (n <= 32) {
+    uint64_t* base = keys + seg_off[q];
+    uint64_t v = lane < n ? base[lane] : ~0ull;
+    v = warp_sort_u64(v, lane);
+    if (lane < n) base[lane] = v;
+  } else if (lane == 0) {
+    if (n <= kSortMedium) medium_list[atomicAdd(&ctr->n_medium, 1u)] = q;
+    else large_list[atomicAdd(&ctr->n_large, 1u)] = q;
+  }
+}
+
+__global__ void __launch_bounds__(512) sort_medium_kernel(uint64_t* __restrict__ keys,
+                                                          const uint32_t* __restrict__ seg_off,
+                                                          const uint32_t* __restrict__ seg_cnt,
+                                                          const uint32_t* __restrict__ list,
+                                                          const BatchCounters* __restrict__ ctr) {
+  __shared__ uint64_t sk[kSortMedium];
+  const uint32_t n_list = ctr->n_medium;
+  for (uint32_t it = blockIdx.x; it < n_list; it += gridDim.x) {
+    uint32_t q = list[it];
+    uint32_t n = seg_cnt[q];
+    uint64_t* base = keys + seg_off[q];
+    uint32_t N = 64;
+    while (N < n) N <<= 1;
+    for (uint32_t i = threadIdx.x; i < N; i += blockDim.x) sk[i] = i < n ? base[i] : ~0ull;
+    __syncthreads();
+    for (uint32_t k = 2; k <= N; k <<= 1) {
+      for (uint32_t i = threadIdx.x; i < N; i += blockDim.x) {
+        uint32_t l = i ^ (k - 1);
+        if (l > i) {
+          uint64_t a = sk[i], b = sk[l];
+          if (a > b) {
+            sk[i] = b;
+            sk[l] = a;
+          }
+        }
+      }
+      __syncthreads();
+      for (uint32_t j = k >> 2; j > 0; j >>= 1) {
+        for (uint32_t i = threadIdx.x; i < N; i += blockDim.x) {
+          uint32_t l = i ^ j;
+          if (l > i) {
+            uint64_t a = sk[i], b = sk[l];
+            if (a > b) {
+              sk[i] = b;
+              sk[l] = a;
+            }
+          }
+        }
+        __syncthreads();
+      }
+    }
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) base[i] = sk[i];
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(1024) sort_large_kernel(uint64_t* __restrict__ keys,
+                                                          const uint32_t* __restrict__ seg_off,
+                                                          const uint32_t* __restrict__ seg_cnt,
+                                                          const uint32_t* __restrict__ list,
+                                                          const BatchCounters* __restrict__ ctr) {
+  const uint32_t n_list = ctr->n_large;
+  for (uint32_t it = blockIdx.x; it < n_list; it += gridDim.x) {
+    uint32_t q = list[it];
+    uint32_t n = seg_cnt[q];
+    uint64_t* base = keys + seg_off[q];
+    uint64_t N = 64;
+    while (N < n) N <<= 1;
+    for (uint64_t k = 2; k <= N; k <<= 1) {
+      for (uint64_t i = threadIdx.x; i < n; i += blockDim.x) {
+        uint64_t l = i ^ (k - 1);
+        if (l > i && l < n) {
+          uint64_t a = base[i], b = base[l];
+          if (a > b) {
+            base[i] = b;
+            base[l] = a;
+          }
+        }
+      }
+      __syncthreads();
+      for (uint64_t j = k >> 2; j > 0; j >>= 1) {
+        for (uint64_t i = threadIdx.x; i < n; i += blockDim.x) {
+          uint64_t l = i ^ j;
+          if (l > i && l < n) {
+            uint64_t a = base[i], b = base[l];
+            if (a > b) {
+              base[i] = b;
+              base[l] = a;
+            }
+          }
+        }
+        __syncthreads();
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// coalesce / rank
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) coalesce_kernel(BinsView bv, ReadsView rv, Params p, uint32_t nq,
+                                                       const uint32_t* __restrict__ hit_off,
+                                                       const uint32_t* __restrict__ q_nhits,
+                                                       const uint32_t* __restrict__ q_nseeds,
+                                                       const uint64_t* __restrict__ hit_keys,
+                                                       CandRec* __restrict__ cand_sparse,
+                                                       uint64_t* __restrict__ rank_keys,
+                                                       uint32_t* __restrict__ q_ncand) {
+  uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= nq) return;
+  uint32_t nh = q_nhits[q];
+  uint32_t nc = 0;
+  if (nh) {
+    uint32_t L = query_len(rv, p.ns, q);
+    uint32_t k = edit_budget(L, p.edit_rate);
+    uint32_t ms = min_seeds_of(q_nseeds[q], p.min_seed);
+    uint32_t base = hit_off[q];
+    nc = coalesce_item(bv, hit_keys + base, nh, ms, L, k, cand_sparse + base, rank_keys + base);
+  }
+  q_ncand[q] = nc;
+}
+
+__global__ void rank_emit_kernel(uint32_t nq, const uint32_t* __restrict__ hit_off,
+                                 const uint32_t* __restrict__ q_ncand, const uint32_t* __restrict__ cand_off,
+                                 const uint64_t* __restrict__ rank_keys,
+                                 const CandRec* __restrict__ cand_sparse, CandRec* __restrict__ cand_dense,
+                                 uint32_t* __restrict__ cand_q) {
+  uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= nq) return;
+  uint32_t nc = q_ncand[q];
+  uint32_t src = hit_off[q], dst = cand_off[q];
+  for (uint32_t i = 0; i < nc; ++i) {
+    uint32_t idx = (uint32_t)(rank_keys[src + i] & 0xffffffffu);
+    cand_dense[dst + i] = cand_sparse[src + idx];
+    cand_q[dst + i] = q;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// verification: one thread per (pattern, text window) job, Myers/Hyyrö bit-vector recurrence with
+// the pattern-match masks of the thread staged in shared memory ([class][word][thread], conflict
+// free).  W = 64-bit words per pattern (compile time), NCLS = match classes (4: A,C,G,T for the
+// binner where any N is a mismatch, src/index.rs:272-279; 5: N equals N, the raw
+// Aligner::min_edit_distance semantics used by the stage-level entry point).
+// ------------------------------------------------------------------------------------------
+constexpr int kVerifyThreads = 128;
+
+struct VerifyJob {
+  const uint8_t* pat;   // pattern bytes (raw read bytes for the binner)
+  uint32_t L;           // pattern length
+  uint32_t rc;          // 1 = use the reverse complement of the normalised pattern
+  const uint8_t* txt;   // text window
+  uint32_t T;           // window length
+  uint32_t limit;       // edit budget k; result > limit is reported as kNoEdit
+  uint32_t skip;        // 1 = do not verify (result kNoEdit)
+};
+
+// binner jobs: dense candidate list
+struct BinnerJobs {
+  ReadsView rv;
+  Params p;
+  const CandRec* cand;
+  const uint32_t* cand_q;
+  const uint32_t* cand_off;
+  const uint8_t* text;
+  uint32_t n;
+  __device__ __forceinline__ VerifyJob get(uint32_t i) const {
+    VerifyJob j;
+    CandRec c = cand[i];
+    uint32_t q = cand_q[i];
+    uint64_t r = rv.read0 + q / p.ns;
+    uint64_t so = rv.seq_off[r];
+    j.pat = rv.seqs + so;
+    j.L = (uint32_t)(rv.seq_off[r + 1] - so);
+    j.rc = q % p.ns;
+    j.txt = text + c.start;
+    j.T = c.end - c.start;
+    j.limit = edit_budget(j.L, p.edit_rate);
+    uint32_t rank = i - cand_off[q];
+    // src/index.rs:385-389 (prefix of the ranked list) and :406 (L - 2k wraps when 2k > L)
+    j.skip = (p.max_candidates >= 0 && (uint64_t)rank >= (uint64_t)p.max_candidates) ||
+             (2ull * j.limit > (uint64_t)j.L) || j.L == 0;
+    return j;
+  }
+};
+
+// stage-level jobs: explicit pairs
+struct PairJobs {
+  const uint8_t* pats;
+  const uint64_t* pat_off;
+  const uint8_t* texts;
+  const uint64_t* text_off;
+  uint32_t n;
+  __device__ __forceinline__ VerifyJob get(uint32_t i) const {
+    VerifyJob j;
+    j.pat = pats + pat_off[i];
+    j.L = (uint32_t)(pat_off[i + 1] - pat_off[i]);
+    j.rc = 0;
+    j.txt = texts + text_off[i];
+    j.T = (uint32_t)(text_off[i + 1] - text_off[i]);
+    j.limit = 0xfffffffeu;
+    j.skip = 0;
+    return j;
+  }
+};
+
+template <int NCLS>
+__device__ __forceinline__ uint32_t pattern_class(uint8_t b, uint32_t rc) {
+  if (NCLS == 4) {  // binner: normalise (src/binner.rs:88-100), N never matches
+    uint32_t c = read_code(b);
+    if (rc) c = comp_code(c);
+    return c;  // 0..3 or 4 (= none)
+  } else {  // raw bytes: A,C,G,T,N are classes, anything else matches nothing
+    uint32_t c = text_code(b);
+    return c <= SYM_N ? c : 7u;
+  }
+}
+
+template <int W, int NCLS, typename Jobs>
+__global__ void __launch_bounds__(kVerifyThreads) verify_kernel(Jobs jobs, uint32_t* __restrict__ out,
+                                                                BatchCounters* __restrict__ ctr) {
+  extern __shared__ uint64_t peq[];  // [NCLS][W][kVerifyThreads]
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= jobs.n) return;
+  VerifyJob job = jobs.get(i);
+  if (job.skip) {
+    out[i] = kNoEdit;
+    return;
+  }
+  const uint32_t L = job.L;
+  if (L == 0) {  // empty needle aligns anywhere with 0 edits (src/align.rs test_empty)
+    out[i] = 0;
+    return;
+  }
+  const int last = (int)((L - 1) >> 6);
+  // pattern masks
+#pragma unroll
+  for (int w = 0; w < W; ++w) {
+    uint64_t m[NCLS];
+#pragma unroll
+    for (int c = 0; c < NCLS; ++c) m[c] = 0;
+    if (w <= last) {
+      uint32_t lim = L - (uint32_t)w * 64 < 64 ? L - (uint32_t)w * 64 : 64;
+      for (uint32_t b = 0; b < lim; ++b) {
+        uint32_t pi = (uint32_t)w * 64 + b;
+        uint8_t byte = job.rc ? job.pat[L - 1 - pi] : job.pat[pi];
+        uint32_t c = pattern_class<NCLS>(byte, job.rc);
+#pragma unroll
+        for (int cc = 0; cc < NCLS; ++cc) m[cc] |= (uint64_t)(c == (uint32_t)cc) << b;
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < NCLS; ++c) peq[(c * W + w) * kVerifyThreads + threadIdx.x] = m[c];
+  }
+  uint64_t Pv[W], Mv[W];
+#pragma unroll
+  for (int w = 0; w < W; ++w) {
+    Pv[w] = ~0ull;
+    Mv[w] = 0;
+  }
+  const uint32_t sbit = (L - 1) & 63;
+  uint32_t score = L, best = L;
+  const uint8_t* t = job.txt;
+  const uint32_t T = job.T;
+  // text is read through 8-byte aligned words (the device text has 16 bytes of slack at the end)
+  uint64_t addr = (uint64_t)t;
+  const uint64_t* wp = reinterpret_cast<const uint64_t*>(addr & ~7ull);
+  uint32_t sh = (uint32_t)(addr & 7ull);
+  uint64_t word = 0;
+  for (uint32_t j = 0; j < T; ++j) {
+    uint32_t bi = (j + sh) & 7;
+    if (j == 0 || bi == 0) word = __ldg(wp + ((j + sh) >> 3));
+    uint8_t byte = (uint8_t)(word >> (bi * 8));
+    uint32_t c = text_code(byte);
+    bool none = c >= (uint32_t)NCLS;
+    uint32_t phin = 0, mhin = 0;
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+      if (w <= last) {
+        uint64_t Eq = none ? 0ull : peq[(c * W + w) * kVerifyThreads + threadIdx.x];
+        uint64_t Ph, Mh;
+        myers_block(Eq, Pv[w], Mv[w], phin, mhin, Ph, Mh);
+        if (w == last) {
+          score += (uint32_t)((Ph >> sbit) & 1);
+          score -= (uint32_t)((Mh >> sbit) & 1);
+        }
+      }
+    }
+    best = score < best ? score : best;
+  }
+  out[i] = best <= job.limit ? best : kNoEdit;
+  if (ctr) atomicAdd(&ctr->window_bytes, (unsigned long long)T);
+}
+
+template <int NCLS, typename Jobs>
+static int launch_verify(const Jobs& jobs, uint32_t max_len, uint32_t* out, BatchCounters* ctr,
+                         cudaStream_t st) {
+  if (jobs.n == 0) return 0;
+  uint32_t words = (max_len + 63) / 64;
+  unsigned grid = (jobs.n + kVerifyThreads - 1) / kVerifyThreads;
+#define MTSV_VERIFY_CASE(WW)                                                                      \
+  {                                                                                               \
+    size_t smem = (size_t)NCLS * WW * kVerifyThreads * sizeof(uint64_t);                          \
+    auto kfn = verify_kernel<WW, NCLS, Jobs>;                                                     \
+    if (smem > 48 * 1024)                                                                         \
+      MTSV_CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    MTSV_LAUNCH(kfn, grid, kVerifyThreads, smem, st, jobs, out, ctr);                             \
+  }
+  if (words <= 1) MTSV_VERIFY_CASE(1)
+  else if (words <= 2) MTSV_VERIFY_CASE(2)
+  else if (words <= 3) MTSV_VERIFY_CASE(3)
+  else if (words <= 4) MTSV_VERIFY_CASE(4)
+  else if (words <= 8) MTSV_VERIFY_CASE(8)
+  else if (words <= 16) MTSV_VERIFY_CASE(16)
+  else return set_error(MTSVGPU_ELIMIT, "pattern of %u bases exceeds the verifier limit of 1024", max_len);
+#undef MTSV_VERIFY_CASE
+  MTSV_CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+constexpr uint32_t kMaxReadLen = 1024;
+
+// ------------------------------------------------------------------------------------------
+// select / emit
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) select_kernel(BinsView bv, ReadsView rv, Params p, uint32_t nq,
+                                                     const uint32_t* __restrict__ cand_off,
+                                                     const CandRec* __restrict__ cand_dense,
+                                                     const uint32_t* __restrict__ cand_edit,
+                                                     HitRec* __restrict__ hit_tmp,
+                                                     uint32_t* __restrict__ q_nout) {
+  uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= nq) return;
+  uint32_t b = cand_off[q], e = cand_off[q + 1];
+  uint32_t n = 0;
+  if (e > b) {
+    uint32_t L = query_len(rv, p.ns, q);
+    uint32_t k = edit_budget(L, p.edit_rate);
+    n = select_item(bv, p, cand_dense + b, cand_edit + b, e - b, k, hit_tmp + b);
+  }
+  q_nout[q] = n;
+}
+
+__global__ void gather_hits_kernel(uint32_t nq, uint32_t ns, const uint32_t* __restrict__ cand_off,
+                                   const uint32_t* __restrict__ out_off, const HitRec* __restrict__ hit_tmp,
+                                   HitRec* __restrict__ out_hits, uint64_t out_base,
+                                   uint64_t* __restrict__ out_hit_off /*indexed by read within batch*/,
+                                   uint64_t read_base) {
+  uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q > nq) return;
+  if (q % ns == 0) out_hit_off[read_base + q / ns] = out_base + out_off[q];  // also q == nq: the end
+  if (q == nq) return;
+  uint32_t n = out_off[q + 1] - out_off[q];
+  const HitRec* src = hit_tmp + cand_off[q];
+  HitRec* dst = out_hits + out_base + out_off[q];
+  for (uint32_t i = 0; i < n; ++i) dst[i] = src[i];
+}
+
+// ------------------------------------------------------------------------------------------
+// host orchestration
+// ------------------------------------------------------------------------------------------
+static int validate_params(const mtsvgpu_params* in, Params* p) {
+  if (!in) return set_error(MTSVGPU_EINVAL, "params is NULL");
+  if (!(in->edit_rate >= 0.0 && in->edit_rate <= 1.0))  // src/bin/mtsv-binner.rs:151
+    return set_error(MTSVGPU_EINVAL, "edit_rate must be in [0,1]");
+  if (!(in->min_seed > 0.0 && in->min_seed <= 1.0))  // src/bin/mtsv-binner.rs:195
+    return set_error(MTSVGPU_EINVAL, "min_seed must be in (0,1]");
+  if (in->seed_size == 0 || in->seed_size > 4096)
+    return set_error(MTSVGPU_EINVAL, "seed_size must be in [1,4096]");
+  if (in->seed_gap == 0)  // itertools .step(0) panics in the reference (src/index.rs:285)
+    return set_error(MTSVGPU_EINVAL, "seed_gap must be > 0");
+  p->edit_rate = in->edit_rate;
+  p->min_seed = in->min_seed;
+  p->S = in->seed_size;
+  p->G = in->seed_gap;
+  p->max_hits = in->max_hits;
+  p->tune_max_hits = in->tune_max_hits;
+  p->max_candidates = in->max_candidates < 0 ? -1 : in->max_candidates;
+  p->max_assignments = in->max_assignments < 0 ? -1 : in->max_assignments;
+  p->ns = in->strands == 1 ? 1 : 2;
+  return 0;
+}
+
+struct StageClock {
+  mtsvgpu_index* h;
+  explicit StageClock(mtsvgpu_index* hh) : h(hh) {}
+  cudaEvent_t next_event() {
+    if (h->ev_next == h->ev_pool.size()) {
+      cudaEvent_t e;
+      cudaEventCreate(&e);
+      h->ev_pool.push_back(e);
+    }
+    return h->ev_pool[h->ev_next++];
+  }
+  void begin(int stage) {
+    if (!h->profiling) return;
+    cudaEvent_t a = next_event(), b = next_event();
+    cudaEventRecord(a, h->stream);
+    h->ev_used.push_back({stage, {a, b}});
+  }
+  void end() {
+    if (!h->profiling) return;
+    cudaEventRecord(h->ev_used.back().second.second, h->stream);
+  }
+  void resolve() {
+    if (!h->profiling) return;
+    cudaStreamSynchronize(h->stream);
+    for (auto& e : h->ev_used) {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, e.second.first, e.second.second);
+      h->stats.ms[e.first] += ms;
+    }
+    h->ev_used.clear();
+    h->ev_next = 0;
+  }
+};
+
+static int run_segmented_sort(mtsvgpu_index* h, uint64_t* keys, const uint32_t* seg_off,
+                              const uint32_t* seg_cnt, uint32_t nq, BatchCounters* d_ctr) {
+  cudaStream_t st = h->stream;
+  uint32_t* lists = h->ws.worklist.as<uint32_t>();
+  MTSV_CUDA_TRY(cudaMemsetAsync(&d_ctr->n_medium, 0, 2 * sizeof(unsigned int), st));
+  unsigned grid = (unsigned)(((uint64_t)nq * 32 + 255) / 256);
+  MTSV_LAUNCH(sort_small_kernel, grid, 256, 0, st, keys, seg_off, seg_cnt, nq, lists, lists + nq, d_ctr);
+  MTSV_LAUNCH(sort_medium_kernel, 148 * 4, 512, 0, st, keys, seg_off, seg_cnt, lists, d_ctr);
+  MTSV_LAUNCH(sort_large_kernel, 148, 1024, 0, st, keys, seg_off, seg_cnt, lists + nq, d_ctr);
+  MTSV_CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+// grow-with-preserve for the whole-batch output
+static int grow_preserve(DevBuf& buf, size_t used_bytes, size_t need_bytes, cudaStream_t st) {
+  if (need_bytes <= buf.cap && buf.p) return 0;
+  size_t want = std::max(need_bytes + need_bytes / 2, (size_t)1 << 20);
+  void* np = nullptr;
+  cudaError_t e = cudaMalloc(&np, want);
+  if (e != cudaSuccess) {
+    (void)cudaGetLastError();
+    return set_error(MTSVGPU_ENOMEM, "cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+  }
+  if (buf.p && used_bytes) {
+    MTSV_CUDA_TRY(cudaMemcpyAsync(np, buf.p, used_bytes, cudaMemcpyDeviceToDevice, st));
+    MTSV_CUDA_TRY(cudaStreamSynchronize(st));
+  }
+  if (buf.p) cudaFree(buf.p);
+  buf.p = np;
+  buf.cap = want;
+  return 0;
+}
+
+// One device sub-batch: reads [read0, read0 + n_reads).  Returns 1 when the seed hits exceed the
+// in-flight cap and the caller must split the range (nothing was emitted in that case).
+static int run_sub_batch(mtsvgpu_index* h, const Params& p, const uint8_t* d_seqs,
+                         const uint64_t* d_seq_off, uint64_t read0, uint32_t n_reads,
+                         uint64_t slot_bound, uint64_t batch_read0, uint64_t* out_total) {
+  DeviceIndex& ix = h->ix;
+  BatchWorkspace& ws = h->ws;
+  cudaStream_t st = h->stream;
+  StageClock clk(h);
+  const uint32_t nq = n_reads * p.ns;
+  ReadsView rv{d_seqs, d_seq_off, read0, n_reads};
+  const uint64_t hit_cap = h->opts.max_batch_hits ? h->opts.max_batch_hits : (1ull << 27);
+
+  MTSV_TRY(ws.counters.reserve(sizeof(BatchCounters)));
+  BatchCounters* d_ctr = ws.counters.as<BatchCounters>();
+  MTSV_CUDA_TRY(cudaMemsetAsync(d_ctr, 0, sizeof(BatchCounters), st));
+  const size_t qn = (size_t)nq + 1;
+  MTSV_TRY(ws.slot_off.reserve(qn * 4));
+  MTSV_TRY(ws.q_nseeds.reserve(qn * 4));
+  MTSV_TRY(ws.q_nhits.reserve(qn * 4));
+  MTSV_TRY(ws.hit_off.reserve(qn * 4));
+  MTSV_TRY(ws.q_ncand.reserve(qn * 4));
+  MTSV_TRY(ws.cand_off.reserve(qn * 4));
+  MTSV_TRY(ws.q_nout.reserve(qn * 4));
+  MTSV_TRY(ws.out_off.reserve(qn * 4));
+  MTSV_TRY(ws.worklist.reserve(2 * qn * 4));
+  MTSV_TRY(ws.slot_q.reserve((slot_bound + 1) * 4));
+  MTSV_TRY(ws.slot_lo.reserve((slot_bound + 1) * 4));
+  MTSV_TRY(ws.slot_cnt.reserve((slot_bound + 1) * 4));
+  MTSV_TRY(ws.slot_hoff.reserve((slot_bound + 1) * 4));
+  MTSV_TRY(ws.scan_tmp.reserve(((qn + 2047) / 2048 + 1) * 8));
+
+  BatchCounters hc;
+  const unsigned qgrid = (nq + 255) / 256;
+
+  // ---- seed slots ----
+  clk.begin(ST_PREP);
+  uint32_t* slot_off = ws.slot_off.as<uint32_t>();
+  MTSV_LAUNCH(count_slots_kernel, qgrid, 256, 0, st, rv, p, nq, slot_off, d_ctr);
+  MTSV_TRY(exclusive_scan_u32(slot_off, slot_off, nq, ws.scan_tmp, (uint64_t*)&d_ctr->total_slots, st));
+  MTSV_LAUNCH(expand_slots_kernel, qgrid, 256, 0, st, slot_off, nq, ws.slot_q.as<uint32_t>());
+  clk.end();
+  MTSV_CUDA_TRY(cudaMemcpyAsync(&hc, d_ctr, sizeof hc, cudaMemcpyDeviceToHost, st));
+  MTSV_CUDA_TRY(cudaStreamSynchronize(st));
+  if (hc.max_len > kMaxReadLen)
+    return set_error(MTSVGPU_ELIMIT, "a read of %u bases exceeds this build's limit of %u", hc.max_len,
+                     kMaxReadLen);
+  if (hc.total_slots > slot_bound)
+    return set_error(MTSVGPU_ECUDA, "internal: seed slots %llu exceed bound %llu", hc.total_slots,
+                     (unsigned long long)slot_bound);
+  const uint32_t n_slots = (uint32_t)hc.total_slots;
+  h->stats.n_seed_slots += n_slots;
+
+  // ---- seed search ----
+  clk.begin(ST_SEARCH);
+  if (n_slots)
+    MTSV_LAUNCH(seed_search_kernel, (n_slots + 255) / 256, 256, 0, st, ix.fm_view(), ix.ktab_view(), rv, p,
+                slot_off, ws.slot_q.as<uint32_t>(), n_slots, ws.slot_lo.as<uint32_t>(),
+                ws.slot_cnt.as<uint32_t>(), d_ctr, h->profiling ? 1 : 0);
+  clk.end();
+
+  // ---- replay the seed rule, hit offsets ----
+  clk.begin(ST_SELECT);
+  MTSV_LAUNCH(seed_select_kernel, qgrid, 256, 0, st, p, slot_off, nq, ws.slot_cnt.as<uint32_t>(),
+              ws.slot_hoff.as<uint32_t>(), ws.q_nseeds.as<uint32_t>(), ws.q_nhits.as<uint32_t>(), d_ctr);
+  MTSV_TRY(exclusive_scan_u32(ws.q_nhits.as<uint32_t>(), ws.hit_off.as<uint32_t>(), nq, ws.scan_tmp,
+                              (uint64_t*)&d_ctr->total_hits, st));
+  clk.end();
+  MTSV_CUDA_TRY(cudaMemcpyAsync(&hc, d_ctr, sizeof hc, cudaMemcpyDeviceToHost, st));
+  MTSV_CUDA_TRY(cudaStreamSynchronize(st));
+  if (hc.overflow)
+    return set_error(MTSVGPU_ELIMIT, "a single read-strand produced more than %u seed hits; lower max_hits",
+                     kMaxQueryHits);
+  if (hc.total_hits > hit_cap || hc.total_hits > 0xfffffff0ull) {
+    if (n_reads == 1)
+      return set_error(MTSVGPU_ELIMIT, "one read produced %llu seed hits (cap %llu)", hc.total_hits,
+                       (unsigned long long)hit_cap);
+    return 1;  // caller splits
+  }
+  const uint32_t n_hits = (uint32_t)hc.total_hits;
+  h->stats.n_seed_hits += n_hits;
+  h->stats.rank_queries += 2 * hc.rank_steps;
+
+  uint64_t sub_out = 0;
+  uint32_t n_cand = 0;
+  if (n_hits) {
+    MTSV_TRY(ws.hit_keys.reserve((size_t)n_hits * 8));
+    MTSV_TRY(ws.cand_sparse.reserve((size_t)n_hits * sizeof(CandRec)));
+    MTSV_TRY(ws.rank_keys.reserve((size_t)n_hits * 8));
+    // ---- locate ----
+    clk.begin(ST_LOCATE);
+    MTSV_LAUNCH(locate_kernel, (n_slots + 255) / 256, 256, 0, st, ix.fm_view(), ix.sa_view(), p, slot_off,
+                ws.slot_q.as<uint32_t>(), n_slots, ws.slot_lo.as<uint32_t>(), ws.slot_cnt.as<uint32_t>(),
+                ws.slot_hoff.as<uint32_t>(), ws.hit_off.as<uint32_t>(), ws.hit_keys.as<uint64_t>());
+    clk.end();
+    // ---- sort hits per query ----
+    clk.begin(ST_SORT);
+    MTSV_TRY(run_segmented_sort(h, ws.hit_keys.as<uint64_t>(), ws.hit_off.as<uint32_t>(),
+                                ws.q_nhits.as<uint32_t>(), nq, d_ctr));
+    clk.end();
+    // ---- coalesce ----
+    clk.begin(ST_COALESCE);
+    MTSV_LAUNCH(coalesce_kernel, (nq + 127) / 128, 128, 0, st, ix.bins_view(), rv, p, nq,
+                ws.hit_off.as<uint32_t>(), ws.q_nhits.as<uint32_t>(), ws.q_nseeds.as<uint32_t>(),
+                ws.hit_keys.as<uint64_t>(), ws.cand_sparse.as<CandRec>(), ws.rank_keys.as<uint64_t>(),
+                ws.q_ncand.as<uint32_t>());
+    MTSV_TRY(exclusive_scan_u32(ws.q_ncand.as<uint32_t>(), ws.cand_off.as<uint32_t>(), nq, ws.scan_tmp,
+                                (uint64_t*)&d_ctr->total_cands, st));
+    clk.end();
+    MTSV_CUDA_TRY(cudaMemcpyAsync(&hc, d_ctr, sizeof hc, cudaMemcpyDeviceToHost, st));
+    MTSV_CUDA_TRY(cudaStreamSynchronize(st));
+    n_cand = (uint32_t)hc.total_cands;
+    h->stats.n_candidates += n_cand;
+  }
+  if (n_cand) {
+    MTSV_TRY(ws.cand_dense.reserve((size_t)n_cand * sizeof(CandRec)));
+    MTSV_TRY(ws.cand_q.reserve((size_t)n_cand * 4));
+    MTSV_TRY(ws.cand_edit.reserve((size_t)n_cand * 4));
+    MTSV_TRY(ws.hit_tmp.reserve((size_t)n_cand * sizeof(HitRec)));
+    // ---- rank ----
+    clk.begin(ST_RANK);
+    MTSV_TRY(run_segmented_sort(h, ws.rank_keys.as<uint64_t>(), ws.hit_off.as<uint32_t>(),
+                                ws.q_ncand.as<uint32_t>(), nq, d_ctr));
+    MTSV_LAUNCH(rank_emit_kernel, qgrid, 256, 0, st, nq, ws.hit_off.as<uint32_t>(),
+                ws.q_ncand.as<uint32_t>(), ws.cand_off.as<uint32_t>(), ws.rank_keys.as<uint64_t>(),
+                ws.cand_sparse.as<CandRec>(), ws.cand_dense.as<CandRec>(), ws.cand_q.as<uint32_t>());
+    clk.end();
+    // ---- verify ----
+    clk.begin(ST_VERIFY);
+    BinnerJobs jobs{rv, p, ws.cand_dense.as<CandRec>(), ws.cand_q.as<uint32_t>(),
+                    ws.cand_off.as<uint32_t>(), ix.text, n_cand};
+    MTSV_TRY(launch_verify<4>(jobs, hc.max_len, ws.cand_edit.as<uint32_t>(),
+                              h->profiling ? d_ctr : nullptr, st));
+    clk.end();
+    // ---- select ----
+    clk.begin(ST_EMIT);
+    MTSV_LAUNCH(select_kernel, (nq + 127) / 128, 128, 0, st, ix.bins_view(), rv, p, nq,
+                ws.cand_off.as<uint32_t>(), ws.cand_dense.as<CandRec>(), ws.cand_edit.as<uint32_t>(),
+                ws.hit_tmp.as<HitRec>(), ws.q_nout.as<uint32_t>());
+    MTSV_TRY(exclusive_scan_u32(ws.q_nout.as<uint32_t>(), ws.out_off.as<uint32_t>(), nq, ws.scan_tmp,
+                                (uint64_t*)&d_ctr->total_out, st));
+    clk.end();
+    MTSV_CUDA_TRY(cudaMemcpyAsync(&hc, d_ctr, sizeof hc, cudaMemcpyDeviceToHost, st));
+    MTSV_CUDA_TRY(cudaStreamSynchronize(st));
+    sub_out = hc.total_out;
+    h->stats.window_bytes += hc.window_bytes;
+  } else {
+    MTSV_CUDA_TRY(cudaMemsetAsync(ws.out_off.p, 0, qn * 4, st));
+    MTSV_CUDA_TRY(cudaMemsetAsync(ws.cand_off.p, 0, qn * 4, st));
+  }
+  // ---- append to the batch output ----
+  MTSV_TRY(grow_preserve(ws.out_hits, *out_total * sizeof(HitRec), (*out_total + sub_out + 1) * sizeof(HitRec),
+                         st));
+  clk.begin(ST_EMIT);
+  MTSV_LAUNCH(gather_hits_kernel, (nq + 1 + 255) / 256, 256, 0, st, nq, p.ns, ws.cand_off.as<uint32_t>(),
+              ws.out_off.as<uint32_t>(), ws.hit_tmp.as<HitRec>(), ws.out_hits.as<HitRec>(), *out_total,
+              ws.out_hit_off.as<uint64_t>(), read0 - batch_read0);
+  clk.end();
+  MTSV_CUDA_TRY(cudaGetLastError());
+  clk.resolve();
+  *out_total += sub_out;
+  h->stats.n_hits += sub_out;
+  h->stats.n_queries += nq;
+  return 0;
+}
+
+static int run_range(mtsvgpu_index* h, const Params& p, const uint8_t* d_seqs, const uint64_t* d_seq_off,
+                     const uint64_t* h_seq_off, uint64_t read0, uint64_t n_reads, uint64_t batch_read0,
+                     uint64_t* out_total) {
+  // bound on seed slots from the byte count: slots(L) <= L/G + 1 per strand
+  uint64_t bytes = h_seq_off[read0 + n_reads - batch_read0] - h_seq_off[read0 - batch_read0];
+  uint64_t slot_bound = (bytes / p.G + n_reads) * p.ns + 1;
+  if (slot_bound > 0xfffffff0ull || n_reads * p.ns > 0x7ffffff0ull) {
+    if (n_reads == 1) return set_error(MTSVGPU_ELIMIT, "read too long");
+    uint64_t half = n_reads / 2;
+    MTSV_TRY(run_range(h, p, d_seqs, d_seq_off, h_seq_off, read0, half, batch_read0, out_total));
+    return run_range(h, p, d_seqs, d_seq_off, h_seq_off, read0 + half, n_reads - half, batch_read0, out_total);
+  }
+  int rc = run_sub_batch(h, p, d_seqs, d_seq_off, read0, (uint32_t)n_reads, slot_bound, batch_read0, out_total);
+  if (rc == 1) {
+    uint64_t half = n_reads / 2;
+    MTSV_TRY(run_range(h, p, d_seqs, d_seq_off, h_seq_off, read0, half, batch_read0, out_total));
+    return run_range(h, p, d_seqs, d_seq_off, h_seq_off, read0 + half, n_reads - half, batch_read0, out_total);
+  }
+  return rc;
+}
+
+int bin_batch_device(mtsvgpu_index* h, const uint8_t* d_seqs, const uint64_t* d_seq_off, uint64_t n_reads,
+                     const uint64_t* h_seq_off_or_null, const mtsvgpu_params* params,
+                     const mtsvgpu_hit** d_hits, const uint64_t** d_hit_off, uint64_t* n_hits) {
+  if (!h) return set_error(MTSVGPU_EINVAL, "index is NULL");
+  Params p;
+  MTSV_TRY(validate_params(params, &p));
+  if (!d_seq_off) return set_error(MTSVGPU_EINVAL, "seq_off is NULL");
+  MTSV_CUDA_TRY(cudaSetDevice(h->ix.device));
+  cudaStream_t st = h->stream;
+  memset(&h->stats, 0, sizeof h->stats);
+  BatchWorkspace& ws = h->ws;
+  MTSV_TRY(ws.out_hit_off.reserve((n_reads + 1) * 8));
+  std::vector<uint64_t> off_copy;
+  const uint64_t* h_off = h_seq_off_or_null;
+  if (!h_off) {  // device-resident caller: fetch the offsets once (8 B/read)
+    off_copy.resize(n_reads + 1);
+    MTSV_CUDA_TRY(cudaMemcpyAsync(off_copy.data(), d_seq_off, (n_reads + 1) * 8, cudaMemcpyDeviceToHost, st));
+    MTSV_CUDA_TRY(cudaStreamSynchronize(st));
+    h_off = off_copy.data();
+  }
+  for (uint64_t i = 0; i < n_reads; ++i)
+    if (h_off[i + 1] < h_off[i]) return set_error(MTSVGPU_EINVAL, "seq_off is not monotone at read %llu", (unsigned long long)i);
+  uint64_t total = 0;
+  const uint64_t step = h->opts.batch_reads ? h->opts.batch_reads : (1u << 20);
+  if (n_reads == 0) {
+    MTSV_CUDA_TRY(cudaMemsetAsync(ws.out_hit_off.p, 0, 8, st));
+    MTSV_TRY(grow_preserve(ws.out_hits, 0, sizeof(HitRec), st));
+  }
+  for (uint64_t r0 = 0; r0 < n_reads; r0 += step) {
+    uint64_t nr = std::min(step, n_reads - r0);
+    MTSV_TRY(run_range(h, p, d_seqs, d_seq_off, h_off, r0, nr, 0, &total));
+  }
+  MTSV_CUDA_TRY(cudaStreamSynchronize(st));
+  if (d_hits) *d_hits = reinterpret_cast<const mtsvgpu_hit*>(ws.out_hits.p);
+  if (d_hit_off) *d_hit_off = ws.out_hit_off.as<uint64_t>();
+  if (n_hits) *n_hits = total;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// stage-level entry points
+// ------------------------------------------------------------------------------------------
+__global__ void bs_patterns_kernel(FmView fm, KtabView kt, const uint8_t* __restrict__ pats, uint32_t len,
+                                   uint64_t n, uint64_t* __restrict__ lower, uint64_t* __restrict__ upper) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  // a pattern is a forward-strand "read" whose single seed covers it entirely
+  uint32_t lo, cnt;
+  seed_search_item(fm, kt, pats + i * len, 0, len, len, 0, &lo, &cnt, nullptr);
+  lower[i] = cnt ? lo : 0;
+  upper[i] = cnt ? (uint64_t)lo + cnt : 0;
+}
+
+int backward_search_batch(mtsvgpu_index* h, const uint8_t* pats, uint32_t pat_len, uint64_t n_pats,
+                          uint64_t* lower, uint64_t* upper) {
+  if (!h || !pats || !lower || !upper) return set_error(MTSVGPU_EINVAL, "null argument");
+  if (pat_len == 0) return set_error(MTSVGPU_EINVAL, "pattern length must be > 0");
+  if (n_pats == 0) return 0;
+  MTSV_CUDA_TRY(cudaSetDevice(h->ix.device));
+  cudaStream_t st = h->stream;
+  DevBuf dp, dl, du;
+  int rc = 0;
+  do {
+    if ((rc = dp.reserve(n_pats * pat_len))) break;
+    if ((rc = dl.reserve(n_pats * 8))) break;
+    if ((rc = du.reserve(n_pats * 8))) break;
+    cudaMemcpyAsync(dp.p, pats, n_pats * pat_len, cudaMemcpyHostToDevice, st);
+    MTSV_LAUNCH(bs_patterns_kernel, (unsigned)((n_pats + 127) / 128), 128, 0, st, h->ix.fm_view(),
+                h->ix.ktab_view(), dp.as<uint8_t>(), pat_len, n_pats, dl.as<uint64_t>(), du.as<uint64_t>());
+    cudaMemcpyAsync(lower, dl.p, n_pats * 8, cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(upper, du.p, n_pats * 8, cudaMemcpyDeviceToHost, st);
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) rc = set_error(MTSVGPU_ECUDA, "backward_search: %s", cudaGetErrorString(e));
+  } while (0);
+  dp.release();
+  dl.release();
+  du.release();
+  return rc;
+}
+
+__global__ void locate_rows_kernel(FmView fm, SaView sv, const uint64_t* __restrict__ rows, uint64_t n,
+                                   uint64_t* __restrict__ pos) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint64_t r = rows[i];
+  pos[i] = r < fm.n ? (uint64_t)fm_locate(fm, sv, (uint32_t)r, nullptr) : ~0ull;
+}
+
+int locate_batch(mtsvgpu_index* h, const uint64_t* rows, uint64_t n_rows, uint64_t* pos) {
+  if (!h || !rows || !pos) return set_error(MTSVGPU_EINVAL, "null argument");
+  if (n_rows == 0) return 0;
+  MTSV_CUDA_TRY(cudaSetDevice(h->ix.device));
+  cudaStream_t st = h->stream;
+  DevBuf dr, dp;
+  int rc = 0;
+  do {
+    if ((rc = dr.reserve(n_rows * 8))) break;
+    if ((rc = dp.reserve(n_rows * 8))) break;
+    cudaMemcpyAsync(dr.p, rows, n_rows * 8, cudaMemcpyHostToDevice, st);
+    MTSV_LAUNCH(locate_rows_kernel, (unsigned)((n_rows + 127) / 128), 128, 0, st, h->ix.fm_view(),
+                h->ix.sa_view(), dr.as<uint64_t>(), n_rows, dp.as<uint64_t>());
+    cudaMemcpyAsync(pos, dp.p, n_rows * 8, cudaMemcpyDeviceToHost, st);
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) rc = set_error(MTSVGPU_ECUDA, "locate: %s", cudaGetErrorString(e));
+  } while (0);
+  dr.release();
+  dp.release();
+  return rc;
+}
+
+int edit_distance_batch(int device, const uint8_t* pats, const uint64_t* pat_off, const uint8_t* texts,
+                        const uint64_t* text_off, uint64_t n_pairs, uint32_t* edits) {
+  if (!pat_off || !text_off || !edits) return set_error(MTSVGPU_EINVAL, "null argument");
+  if (n_pairs == 0) return 0;
+  if (n_pairs > 0x7fffffffull) return set_error(MTSVGPU_ELIMIT, "too many pairs");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    (void)cudaGetLastError();
+    return set_error(MTSVGPU_ENODEVICE, "no CUDA device available (this library has no CPU path)");
+  }
+  MTSV_CUDA_TRY(cudaSetDevice(device));
+  uint32_t max_len = 0;
+  for (uint64_t i = 0; i < n_pairs; ++i) {
+    if (pat_off[i + 1] < pat_off[i] || text_off[i + 1] < text_off[i])
+      return set_error(MTSVGPU_EINVAL, "offsets not monotone");
+    max_len = std::max<uint64_t>(max_len, pat_off[i + 1] - pat_off[i]);
+  }
+  if (max_len > kMaxReadLen) return set_error(MTSVGPU_ELIMIT, "pattern longer than %u", kMaxReadLen);
+  uint64_t pb = pat_off[n_pairs], tb = text_off[n_pairs];
+  DevBuf dp, dpo, dt, dto, de;
+  int rc = 0;
+  do {
+    if ((rc = dp.reserve(pb + 16))) break;
+    if ((rc = dt.reserve(tb + 16))) break;
+    if ((rc = dpo.reserve((n_pairs + 1) * 8))) break;
+    if ((rc = dto.reserve((n_pairs + 1) * 8))) break;
+    if ((rc = de.reserve(n_pairs * 4))) break;
+    if (pb) cudaMemcpy(dp.p, pats, pb, cudaMemcpyHostToDevice);
+    if (tb) cudaMemcpy(dt.p, texts, tb, cudaMemcpyHostToDevice);
+    cudaMemcpy(dpo.p, pat_off, (n_pairs + 1) * 8, cudaMemcpyHostToDevice);
+    cudaMemcpy(dto.p, text_off, (n_pairs + 1) * 8, cudaMemcpyHostToDevice);
+    PairJobs jobs{dp.as<uint8_t>(), dpo.as<uint64_t>(), dt.as<uint8_t>(), dto.as<uint64_t>(), (uint32_t)n_pairs};
+    if ((rc = launch_verify<5>(jobs, std::max(max_len, 1u), de.as<uint32_t>(), nullptr, 0))) break;
+    cudaError_t e = cudaMemcpy(edits, de.p, n_pairs * 4, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) rc = set_error(MTSVGPU_ECUDA, "edit_distance: %s", cudaGetErrorString(e));
+  } while (0);
+  dp.release();
+  dpo.release();
+  dt.release();
+  dto.release();
+  de.release();
+  return rc;
+}
+
+}  // namespace mtsv

@@ -1,0 +1,554 @@
+// core.cuh — device data layout and the per-work-item logic of every hot-path stage.
+//
+// Everything here is `__host__ __device__` so that tests/emul/ can compile the very same
+// arithmetic with g++ and diff it against the oracle without a GPU (test-only; the product
+// library has no CPU path).  Kernels in binner.cu / index.cu are thin grids over these items.
+//
+// Reference (FofanovLab/mtsv_tools v2.1.0) lines restated by each item are cited inline.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define MTSV_HD __host__ __device__ __forceinline__
+#else
+#define MTSV_HD inline
+struct uint2 {  // CUDA vector type, for the g++ build of tests/emul/
+  uint32_t x, y;
+};
+#endif
+
+namespace mtsv {
+
+// ---------------------------------------------------------------------------------------------
+// small helpers
+// ---------------------------------------------------------------------------------------------
+MTSV_HD int popc64(uint64_t x) {
+#ifdef __CUDA_ARCH__
+  return __popcll(x);
+#else
+  return __builtin_popcountll(x);
+#endif
+}
+
+template <typename T>
+MTSV_HD T ldg(const T* p) {
+#ifdef __CUDA_ARCH__
+  return __ldg(p);
+#else
+  return *p;
+#endif
+}
+
+// symbol codes used on the device: A C G T in 2 bits, N and '$' are "exceptions"
+enum : uint32_t { SYM_A = 0, SYM_C = 1, SYM_G = 2, SYM_T = 3, SYM_N = 4, SYM_DOLLAR = 5, SYM_OTHER = 6 };
+
+// read normalisation of src/binner.rs:88-100 fused with the 0..4 encoding
+MTSV_HD uint32_t read_code(uint8_t b) {
+  switch (b) {
+    case 'A': case 'a': return SYM_A;
+    case 'C': case 'c': return SYM_C;
+    case 'G': case 'g': return SYM_G;
+    case 'T': case 't': return SYM_T;
+    default: return SYM_N;
+  }
+}
+// reference text bytes are already upper-case ACGTN (src/index.rs:543-553)
+MTSV_HD uint32_t text_code(uint8_t b) {
+  switch (b) {
+    case 'A': return SYM_A;
+    case 'C': return SYM_C;
+    case 'G': return SYM_G;
+    case 'T': return SYM_T;
+    case 'N': return SYM_N;
+    case '$': return SYM_DOLLAR;
+    default: return SYM_OTHER;
+  }
+}
+// bio::alphabets::dna::revcomp on the normalised alphabet (src/binner.rs:115): A<->T C<->G N->N
+MTSV_HD uint32_t comp_code(uint32_t c) { return c < 4 ? 3u - c : c; }
+
+// ---------------------------------------------------------------------------------------------
+// FM-index layout in HBM
+//
+// One 32-byte sector per 64 BWT rows: relative A/C/G/T counts (u16, relative to the enclosing
+// 32768-row superblock), a 64-bit exception plane (rows holding N or '$'), and the two bit
+// planes of the 2-bit symbol code.  A rank query = one sector from here + 16 bytes from the tiny
+// (n/2048 bytes) superblock table that lives in L2.  Replaces rust-bio's byte BWT + 11 separate
+// u64 checkpoint arrays (Occ::get) — same counts, different bytes.
+// ---------------------------------------------------------------------------------------------
+struct __attribute__((aligned(32))) FmBlock {
+  uint16_t rel[4];
+  uint64_t exc;
+  uint64_t lo;
+  uint64_t hi;
+};
+static_assert(sizeof(FmBlock) == 32, "FmBlock must be one 32-byte sector");
+
+constexpr uint32_t kRowsPerBlock = 64;
+constexpr uint32_t kBlocksPerSuper = 512;  // 32768 rows: relative counts fit u16
+
+struct SuperCounts {  // absolute counts of A,C,G,T before the superblock
+  uint32_t c[4];
+};
+
+struct FmView {
+  const FmBlock* blocks;      // n/64 + 1
+  const SuperCounts* super;   // per 512 blocks
+  const uint32_t* n_before;   // per block: number of N in bwt[0 .. 64*blk)
+  uint32_t C[5];              // `less` for A,C,G,T,N (byte order $ < A < C < G < N < T)
+  uint32_t n;                 // rows (= text length incl. '$')
+  uint32_t dollar_row;        // the single row whose BWT symbol is '$'
+};
+
+MTSV_HD FmBlock load_block(const FmBlock* p) {
+#ifdef __CUDA_ARCH__
+  FmBlock b;
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+  uint4 v0 = __ldg(q), v1 = __ldg(q + 1);
+  b.rel[0] = (uint16_t)(v0.x & 0xffff);
+  b.rel[1] = (uint16_t)(v0.x >> 16);
+  b.rel[2] = (uint16_t)(v0.y & 0xffff);
+  b.rel[3] = (uint16_t)(v0.y >> 16);
+  b.exc = (uint64_t)v0.z | ((uint64_t)v0.w << 32);
+  b.lo = (uint64_t)v1.x | ((uint64_t)v1.y << 32);
+  b.hi = (uint64_t)v1.z | ((uint64_t)v1.w << 32);
+  return b;
+#else
+  return *p;
+#endif
+}
+
+// occurrences of symbol a (0..3) among the first j (0..63) rows of the block, plus its rel count
+MTSV_HD uint32_t block_occ(const FmBlock& b, uint32_t a, uint32_t j) {
+  uint64_t m = ~b.exc & ((a & 1) ? b.lo : ~b.lo) & ((a & 2) ? b.hi : ~b.hi);
+  return (uint32_t)b.rel[a] + (uint32_t)popc64(m & ((1ull << j) - 1));
+}
+
+// occ(a, i) = number of `a` in bwt[0 .. i)   (== bio Occ::get(bwt, i-1, a) for i > 0)
+MTSV_HD uint32_t fm_occ(const FmView& fm, uint32_t a, uint32_t i) {
+  uint32_t blk = i >> 6, j = i & 63;
+  if (a < 4) {
+    uint32_t sup = ldg(&fm.super[blk >> 9].c[a]);
+    FmBlock b = load_block(fm.blocks + blk);
+    return sup + block_occ(b, a, j);
+  }
+  // N: absolute per-block count (side array, touched only by N queries) + exception plane
+  FmBlock b = load_block(fm.blocks + blk);
+  uint32_t c = ldg(&fm.n_before[blk]) + (uint32_t)popc64(b.exc & ((1ull << j) - 1));
+  uint32_t base = blk << 6;
+  if (fm.dollar_row >= base && fm.dollar_row < i) c -= 1;
+  return c;
+}
+
+// BWT symbol at a row
+MTSV_HD uint32_t fm_symbol(const FmView& fm, const FmBlock& b, uint32_t row) {
+  uint32_t j = row & 63;
+  if ((b.exc >> j) & 1) return row == fm.dollar_row ? SYM_DOLLAR : SYM_N;
+  return (uint32_t)((b.lo >> j) & 1) | ((uint32_t)((b.hi >> j) & 1) << 1);
+}
+
+// One backward-search step on the half-open interval [l,u) — bio FMIndexable::backward_search
+// body: l = less[a] + occ(l-1,a) ; r = less[a] + occ(r,a) - 1  with u = r + 1.
+MTSV_HD void fm_step(const FmView& fm, uint32_t a, uint32_t& l, uint32_t& u) {
+  if (a < 4) {
+    uint32_t bl = l >> 6, bu = u >> 6;
+    uint32_t sup_l = ldg(&fm.super[bl >> 9].c[a]);
+    FmBlock b1 = load_block(fm.blocks + bl);
+    uint32_t ol = sup_l + block_occ(b1, a, l & 63);
+    uint32_t ou;
+    if (bu == bl) {
+      ou = sup_l + block_occ(b1, a, u & 63);
+    } else {
+      FmBlock b2 = load_block(fm.blocks + bu);
+      ou = ldg(&fm.super[bu >> 9].c[a]) + block_occ(b2, a, u & 63);
+    }
+    l = fm.C[a] + ol;
+    u = fm.C[a] + ou;
+  } else {
+    uint32_t ol = fm_occ(fm, SYM_N, l), ou = fm_occ(fm, SYM_N, u);
+    l = fm.C[SYM_N] + ol;
+    u = fm.C[SYM_N] + ou;
+  }
+}
+
+// LF mapping used by locate — bio SampledSuffixArray::get: pos = less[c] + occ(pos-1, c)
+MTSV_HD uint32_t fm_lf(const FmView& fm, uint32_t c, const FmBlock& b, uint32_t row) {
+  uint32_t blk = row >> 6, j = row & 63;
+  if (c < 4) return fm.C[c] + ldg(&fm.super[blk >> 9].c[c]) + block_occ(b, c, j);
+  uint32_t cnt = ldg(&fm.n_before[blk]) + (uint32_t)popc64(b.exc & ((1ull << j) - 1));
+  uint32_t base = blk << 6;
+  if (fm.dollar_row >= base && fm.dollar_row < row) cnt -= 1;
+  return fm.C[SYM_N] + cnt;
+}
+
+// Suffix array as kept on the device: rows 0, s', 2s', ... (s' = 1 means the full array).
+struct SaView {
+  const uint32_t* sa;
+  uint32_t rate;  // s'
+};
+
+// SampledSuffixArray::get (bio 3.0.0) on the device layout.  The '$' row needs no
+// extra_rows entry here: its suffix is text position 0.
+MTSV_HD uint32_t fm_locate(const FmView& fm, const SaView& sv, uint32_t row, uint32_t* lf_steps) {
+  uint32_t off = 0;
+  for (;;) {
+    if (sv.rate == 1) break;
+    if (row % sv.rate == 0) break;
+    FmBlock b = load_block(fm.blocks + (row >> 6));
+    uint32_t c = fm_symbol(fm, b, row);
+    if (c == SYM_DOLLAR) {
+      if (lf_steps) *lf_steps += off;
+      return off;  // SA[dollar_row] = 0
+    }
+    row = fm_lf(fm, c, b, row);
+    ++off;
+  }
+  if (lf_steps) *lf_steps += off;
+  return ldg(&sv.sa[row / sv.rate]) + off;
+}
+
+// k-mer interval table: entry for a k-mer w (lexicographic index, first base most significant)
+// = SA interval [l,u) of w, or l == u when absent.  Legal shortcut 5 of SURVEY app. A.
+struct KtabView {
+  const uint2* tab;
+  uint32_t k;  // 0 = no table
+};
+
+// ---------------------------------------------------------------------------------------------
+// batch description
+// ---------------------------------------------------------------------------------------------
+struct Params {  // mtsvgpu_params, validated
+  double edit_rate, min_seed;
+  uint32_t S, G;
+  uint64_t max_hits, tune_max_hits;
+  int64_t max_candidates, max_assignments;
+  uint32_t ns;  // strands per read: 1 or 2
+};
+
+struct ReadsView {
+  const uint8_t* seqs;
+  const uint64_t* seq_off;  // indexed by absolute read id
+  uint64_t read0;           // first read of this sub-batch
+  uint32_t n_reads;
+};
+
+MTSV_HD uint32_t query_len(const ReadsView& rv, uint32_t ns, uint32_t q) {
+  uint64_t r = rv.read0 + q / ns;
+  return (uint32_t)(ldg(&rv.seq_off[r + 1]) - ldg(&rv.seq_off[r]));
+}
+
+// base i of a read in the strand's own orientation (rc = 1: reverse complement), as a code 0..4
+MTSV_HD uint32_t strand_base(const uint8_t* seq, uint32_t rc, uint32_t L, uint32_t i) {
+  if (!rc) return read_code(ldg(seq + i));
+  return comp_code(read_code(ldg(seq + (L - 1 - i))));
+}
+
+MTSV_HD const uint8_t* query_seq(const ReadsView& rv, uint32_t ns, uint32_t q) {
+  return rv.seqs + ldg(&rv.seq_off[rv.read0 + q / ns]);
+}
+
+// k = ceil(len * edit_freq) in f64 — src/index.rs:281-282
+MTSV_HD uint32_t edit_budget(uint32_t L, double edit_rate) {
+  double v = (double)L * edit_rate;
+  double c = (double)(int64_t)v;
+  if (c < v) c += 1.0;
+  if (c < 0) c = 0;
+  if (c > 4294967295.0) c = 4294967295.0;
+  return (uint32_t)c;
+}
+
+// number of seed start offsets: (0..len+1-S).step(G) — src/index.rs:284-286.  len < S-1 makes the
+// reference panic (usize wrap + out-of-range slice); defined here as no seeds.
+MTSV_HD uint32_t seed_slots(uint32_t L, uint32_t S, uint32_t G) {
+  if (L + 1 < S || L + 1 == S) return 0;
+  uint32_t starts = L + 1 - S;
+  return (starts + G - 1) / G;
+}
+
+// ---------------------------------------------------------------------------------------------
+// stage: seed search (one item per seed slot) — src/index.rs:305 + bio backward_search
+// Only `Complete` results matter to the caller (src/index.rs:312-332): cnt = 0 otherwise.
+// ---------------------------------------------------------------------------------------------
+MTSV_HD void seed_search_item(const FmView& fm, const KtabView& kt, const uint8_t* seq, uint32_t rc,
+                              uint32_t L, uint32_t S, uint32_t seed_off, uint32_t* out_lo,
+                              uint32_t* out_cnt, uint32_t* rank_steps) {
+  uint32_t l = 0, u = fm.n;
+  int i = (int)S - 1;
+  uint32_t steps = 0;
+  if (kt.k && kt.k <= S) {
+    // the table replaces the first k steps (the last k bases of the seed) when none is N
+    uint32_t idx = 0;
+    bool has_n = false;
+    for (uint32_t t = 0; t < kt.k; ++t) {
+      uint32_t c = strand_base(seq, rc, L, seed_off + S - kt.k + t);
+      has_n |= c > 3;
+      idx = (idx << 2) | (c & 3);
+    }
+    if (!has_n) {
+      uint2 e = ldg(&kt.tab[idx]);
+      l = e.x;
+      u = e.y;
+      i -= (int)kt.k;
+    }
+  }
+  for (; i >= 0 && l < u; --i) {
+    uint32_t a = strand_base(seq, rc, L, seed_off + (uint32_t)i);
+    fm_step(fm, a, l, u);
+    ++steps;
+  }
+  if (rank_steps) *rank_steps = steps;
+  if (l < u) {
+    *out_lo = l;
+    *out_cnt = u - l;
+  } else {
+    *out_lo = 0;
+    *out_cnt = 0;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// stage: seed selection (one item per query) — replays src/index.rs:293-355 over the
+// speculatively searched slots.  slot_hoff[slot] = offset of the slot's hits inside the query's
+// hit list, or kUnused.
+// ---------------------------------------------------------------------------------------------
+constexpr uint32_t kUnused = 0xffffffffu;
+constexpr uint32_t kMaxQueryHits = 1u << 26;  // per query; beyond this the batch fails loudly
+
+MTSV_HD void seed_select_item(const Params& p, uint32_t nslots, const uint32_t* slot_cnt,
+                              uint32_t* slot_hoff, uint32_t* n_seeds, uint32_t* n_hits,
+                              uint32_t* overflow) {
+  uint64_t next_offset = 0, seed_interval = p.G;
+  uint32_t seeds = 0;
+  uint64_t total = 0;
+  for (uint32_t j = 0; j < nslots; ++j) {
+    uint64_t offset = (uint64_t)j * p.G;
+    uint32_t cnt = slot_cnt[j];
+    uint32_t ho = kUnused;
+    if (offset >= next_offset && cnt != 0 && (uint64_t)cnt <= p.max_hits) {  // :300-302,:330,:335
+      if ((uint64_t)cnt > p.tune_max_hits) {                                 // :338-344
+        seed_interval *= 2;
+        next_offset = offset + seed_interval;
+      }
+      if (total + cnt > kMaxQueryHits) {
+        *overflow = 1;
+      } else {
+        ho = (uint32_t)total;
+        total += cnt;
+      }
+      seeds += 1;  // :354
+    }
+    slot_hoff[j] = ho;
+  }
+  *n_seeds = seeds;
+  *n_hits = (uint32_t)total;
+}
+
+// hit key: (reference_offset << 16) | query_offset — sorts as the derived Ord of SeedHit
+// (src/index.rs:109-113, :443)
+MTSV_HD uint64_t make_hit_key(uint32_t pos, uint32_t q_off) { return ((uint64_t)pos << 16) | q_off; }
+
+// ---------------------------------------------------------------------------------------------
+// stage: candidate windows
+// ---------------------------------------------------------------------------------------------
+struct BinsView {
+  const uint32_t* start;  // nbins
+  const uint32_t* end;    // nbins
+  const uint32_t* tax;
+  const uint32_t* gi;
+  uint32_t n;
+};
+
+// SeedHit::candidate_indices — src/index.rs:118-153 (u64 wrapping arithmetic of a release build)
+MTSV_HD bool candidate_window(uint64_t site, uint64_t seed_offset, uint64_t bin_start,
+                              uint64_t bin_end, uint64_t read_len, uint64_t k, uint32_t* ws,
+                              uint32_t* we) {
+  uint64_t start_offset = seed_offset + k;
+  uint64_t cand_start =
+      ((uint64_t)(site - start_offset) < bin_start || start_offset > site) ? bin_start
+                                                                           : site - start_offset;
+  uint64_t cand_end = site + (read_len - seed_offset) + k;
+  if (cand_end > bin_end) cand_end = bin_end;
+  if (cand_start > cand_end || cand_start < bin_start || cand_end > bin_end ||
+      cand_end - cand_start < read_len - k)
+    return false;
+  *ws = (uint32_t)cand_start;
+  *we = (uint32_t)cand_end;
+  return true;
+}
+
+// first bin with end > site — the `while curr_bin.end <= site` walk of src/index.rs:455-458
+MTSV_HD uint32_t find_bin(const BinsView& bv, uint32_t site) {
+  uint32_t lo = 0, hi = bv.n;  // answer in [lo, hi)
+  while (lo < hi) {
+    uint32_t mid = (lo + hi) >> 1;
+    if (ldg(&bv.end[mid]) <= site) lo = mid + 1;
+    else hi = mid;
+  }
+  return lo;
+}
+
+// min_seeds = max(floor(n_seeds * pct), 1) — src/index.rs:358
+MTSV_HD uint32_t min_seeds_of(uint32_t n_seeds, double pct) {
+  double v = (double)n_seeds * pct;
+  double f = (double)(int64_t)v;  // v >= 0: truncation == floor
+  if (f < 1.0) f = 1.0;
+  if (f > 4294967295.0) f = 4294967295.0;
+  return (uint32_t)f;
+}
+
+struct CandRec {  // ReferenceCandidate (src/index.rs:158-165), 16 bytes
+  uint32_t start, end, bin, num_seeds;
+};
+
+// rank key: ascending sort == `refs.sort_by(|a,b| b.num_seeds.cmp(&a.num_seeds))` (stable)
+MTSV_HD uint64_t make_rank_key(uint32_t num_seeds, uint32_t idx) {
+  return ((uint64_t)(~num_seeds) << 32) | idx;
+}
+
+// coalesce_seed_sites (src/index.rs:435-487) over the query's sorted hit keys.
+// Writes candidates (in discovery order) to cand[0..), their rank keys to rkey[0..); returns count.
+MTSV_HD uint32_t coalesce_item(const BinsView& bv, const uint64_t* keys, uint32_t n_hits,
+                               uint32_t min_seeds, uint32_t L, uint32_t k, CandRec* cand,
+                               uint64_t* rkey) {
+  uint32_t nc = 0;
+  bool have = false;
+  CandRec cur{0, 0, 0, 0};
+  uint32_t b = 0, b_start = 0, b_end = 0;
+  bool b_valid = false;
+  for (uint32_t h = 0; h < n_hits; ++h) {
+    uint64_t key = keys[h];
+    uint32_t site = (uint32_t)(key >> 16), q_off = (uint32_t)(key & 0xffff);
+    if (!b_valid || site >= b_end) {  // hits are sorted by site, bins only move forward
+      b = find_bin(bv, site);
+      b_start = ldg(&bv.start[b]);
+      b_end = ldg(&bv.end[b]);
+      b_valid = true;
+    }
+    uint32_t ws = 0, we = 0;
+    bool some = candidate_window(site, q_off, b_start, b_end, L, k, &ws, &we);
+    bool merged = false;
+    if (have && some && b == cur.bin &&
+        ((cur.start <= ws && ws < cur.end) || (cur.start < we && we <= cur.end))) {  // :216-221
+      cur.start = ws < cur.start ? ws : cur.start;
+      cur.end = we > cur.end ? we : cur.end;
+      cur.num_seeds += 1;
+      merged = true;
+    }
+    if (!merged) {
+      if (have && cur.num_seeds >= min_seeds) {  // :467-469
+        cand[nc] = cur;
+        rkey[nc] = make_rank_key(cur.num_seeds, nc);
+        ++nc;
+      }
+      have = some;  // :472 / :475
+      if (some) cur = CandRec{ws, we, b, 1};
+    }
+  }
+  if (have && cur.num_seeds >= min_seeds) {  // :481-485
+    cand[nc] = cur;
+    rkey[nc] = make_rank_key(cur.num_seeds, nc);
+    ++nc;
+  }
+  return nc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// stage: verification — Aligner::min_edit_distance (src/align.rs:28-85) as a Myers/Hyyrö
+// bit-vector recurrence (semi-global: free start in the text, min over the last row).
+// By SURVEY §8 a-7 the SSW pre-filter of src/index.rs:402-406 is implied for reads <= 253 bp.
+// ---------------------------------------------------------------------------------------------
+constexpr uint32_t kNoEdit = 0xffffffffu;
+
+// One 64-row block of the recurrence for one text column.  phin/mhin: horizontal delta entering
+// from the block above (+1 / -1 as separate bits); returns the pre-shift Ph/Mh for score tracking.
+MTSV_HD void myers_block(uint64_t Eq, uint64_t& Pv, uint64_t& Mv, uint32_t& phin, uint32_t& mhin,
+                         uint64_t& Ph_out, uint64_t& Mh_out) {
+  uint64_t Xv = Eq | Mv;
+  Eq |= (uint64_t)mhin;
+  uint64_t Xh = (((Eq & Pv) + Pv) ^ Pv) | Eq;
+  uint64_t Ph = Mv | ~(Xh | Pv);
+  uint64_t Mh = Pv & Xh;
+  Ph_out = Ph;
+  Mh_out = Mh;
+  uint32_t pho = (uint32_t)(Ph >> 63), mho = (uint32_t)(Mh >> 63);
+  Ph = (Ph << 1) | (uint64_t)phin;
+  Mh = (Mh << 1) | (uint64_t)mhin;
+  Pv = Mh | ~(Xv | Ph);
+  Mv = Ph & Xv;
+  phin = pho;
+  mhin = mho;
+}
+
+// Reference implementation of the multi-word recurrence with the pattern masks supplied by a
+// functor peq(sym, word) -> u64 and the text by text(j) -> class (0..4 match classes, >4 = none).
+// Used directly by the CPU emulation and by the generic device path; the tuned kernel in
+// binner.cu specialises the same recurrence.
+template <int W, typename PeqF, typename TextF>
+MTSV_HD uint32_t myers_semiglobal(uint32_t L, uint32_t T, PeqF peq, TextF text) {
+  if (L == 0) return 0;
+  uint64_t Pv[W], Mv[W];
+#pragma unroll
+  for (int w = 0; w < W; ++w) {
+    Pv[w] = ~0ull;
+    Mv[w] = 0;
+  }
+  const int last = (int)((L - 1) >> 6);
+  const uint32_t sbit = (L - 1) & 63;
+  uint32_t score = L, best = L;
+  for (uint32_t j = 0; j < T; ++j) {
+    uint32_t c = text(j);
+    uint32_t phin = 0, mhin = 0;
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+      if (w <= last) {
+        uint64_t Eq = c <= 4 ? peq(c, w) : 0ull;
+        uint64_t Ph, Mh;
+        myers_block(Eq, Pv[w], Mv[w], phin, mhin, Ph, Mh);
+        if (w == last) {
+          score += (uint32_t)((Ph >> sbit) & 1);
+          score -= (uint32_t)((Mh >> sbit) & 1);
+        }
+      }
+    }
+    best = score < best ? score : best;
+  }
+  return best;
+}
+
+// ---------------------------------------------------------------------------------------------
+// stage: selection (one item per query) — the verification loop control of src/index.rs:375-431
+// over already computed edit distances, in rank order.
+// ---------------------------------------------------------------------------------------------
+struct HitRec {  // mtsvgpu_hit layout
+  uint32_t tax_id, gi;
+  uint64_t offset;
+  uint32_t edit, reserved;
+};
+static_assert(sizeof(HitRec) == 24, "HitRec must match mtsvgpu_hit");
+
+MTSV_HD uint32_t select_item(const BinsView& bv, const Params& p, const CandRec* cand,
+                             const uint32_t* edits, uint32_t n_cand, uint32_t k, HitRec* out) {
+  uint32_t n_out = 0;
+  for (uint32_t c = 0; c < n_cand; ++c) {
+    if (p.max_candidates >= 0 && (uint64_t)c >= (uint64_t)p.max_candidates) break;  // :385-389
+    uint32_t bin = cand[c].bin;
+    uint32_t tax = ldg(&bv.tax[bin]);
+    bool seen = false;
+    for (uint32_t m = 0; m < n_out; ++m) seen |= out[m].tax_id == tax;  // :393-396
+    if (seen) continue;
+    uint32_t e = edits[c];
+    if (e == kNoEdit || e > k) continue;  // :406,:410
+    HitRec h;
+    h.tax_id = tax;
+    h.gi = ldg(&bv.gi[bin]);
+    uint32_t bs = ldg(&bv.start[bin]);
+    h.offset = cand[c].start >= bs ? cand[c].start - bs : 0;  // saturating_sub, :416
+    h.edit = e;
+    h.reserved = 0;
+    out[n_out++] = h;
+    if (p.max_assignments >= 0 && (uint64_t)n_out >= (uint64_t)p.max_assignments) break;  // :421-425
+  }
+  return n_out;
+}
+
+}  // namespace mtsv

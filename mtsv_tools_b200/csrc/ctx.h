@@ -1,0 +1,173 @@
+// ctx.h — host-side handle, error plumbing and device-buffer helpers shared by index.cu,
+// binner.cu and capi.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <string>
+#include <vector>
+
+#include "../../include/mtsv_b200.h"
+#include "core.cuh"
+
+namespace mtsv {
+
+int set_error(int code, const char* fmt, ...);
+extern std::atomic<uint64_t> g_launches;
+
+#define MTSV_CUDA_TRY(expr)                                                                  \
+  do {                                                                                       \
+    cudaError_t e_ = (expr);                                                                 \
+    if (e_ != cudaSuccess)                                                                   \
+      return ::mtsv::set_error(MTSVGPU_ECUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(e_), \
+                               __FILE__, __LINE__);                                          \
+  } while (0)
+
+#define MTSV_TRY(expr)          \
+  do {                          \
+    int rc_ = (expr);           \
+    if (rc_ != 0) return rc_;   \
+  } while (0)
+
+// every kernel launch of the library goes through this so gpu_launches can be reported
+#define MTSV_LAUNCH(kernel, grid, block, smem, stream, ...)       \
+  do {                                                            \
+    kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);   \
+    ::mtsv::g_launches.fetch_add(1, std::memory_order_relaxed);   \
+  } while (0)
+
+// growable device allocation
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int reserve(size_t bytes);  // contents are NOT preserved
+  void release();
+  template <typename T>
+  T* as() const {
+    return reinterpret_cast<T*>(p);
+  }
+};
+
+// device-resident index (one per GPU)
+struct DeviceIndex {
+  int device = 0;
+  uint64_t n = 0;  // rows / text length incl. '$'
+  // FM-index
+  FmBlock* blocks = nullptr;
+  SuperCounts* super = nullptr;
+  uint32_t* n_before = nullptr;
+  uint64_t n_blocks = 0, n_super = 0;
+  uint32_t C[5] = {0, 0, 0, 0, 0};
+  uint32_t dollar_row = 0;
+  // suffix array at the device rate
+  uint32_t* sa = nullptr;
+  uint32_t sa_rate = 1;
+  uint64_t sa_len = 0;
+  uint64_t file_sa_rate = 0;
+  // k-mer interval table
+  uint2* ktab = nullptr;
+  uint32_t ktab_k = 0;
+  // reference text (bytes, as in the file) and bins (SoA)
+  uint8_t* text = nullptr;
+  uint32_t *bin_start = nullptr, *bin_end = nullptr, *bin_tax = nullptr, *bin_gi = nullptr;
+  uint64_t n_bins = 0;
+  uint64_t device_bytes = 0;
+  double load_seconds = 0, relayout_seconds = 0;
+
+  FmView fm_view() const {
+    FmView v;
+    v.blocks = blocks;
+    v.super = super;
+    v.n_before = n_before;
+    for (int i = 0; i < 5; ++i) v.C[i] = C[i];
+    v.n = (uint32_t)n;
+    v.dollar_row = dollar_row;
+    return v;
+  }
+  SaView sa_view() const { return SaView{sa, sa_rate}; }
+  KtabView ktab_view() const { return KtabView{ktab, ktab_k}; }
+  BinsView bins_view() const { return BinsView{bin_start, bin_end, bin_tax, bin_gi, (uint32_t)n_bins}; }
+};
+
+enum Stage {
+  ST_PREP = 0,    // slot counting + scans
+  ST_SEARCH = 1,  // backward search of all seed slots
+  ST_SELECT = 2,  // tune/max-hits replay + hit offsets
+  ST_LOCATE = 3,  // SA lookup / LF walks
+  ST_SORT = 4,    // segmented sort of seed hits
+  ST_COALESCE = 5,
+  ST_RANK = 6,    // candidate ranking + compaction
+  ST_VERIFY = 7,  // bit-vector edit distance
+  ST_EMIT = 8,    // selection, compaction of hits
+  ST_COPY = 9,    // H2D / D2H inside bin_batch
+  ST_N = 10
+};
+static_assert(ST_N <= MTSVGPU_N_STAGES, "stage table too small");
+
+struct BatchWorkspace {
+  // per query (nq+1 where a scan is involved)
+  DevBuf slot_off, q_nseeds, q_nhits, hit_off, q_ncand, cand_off, q_nout, out_off;
+  // per slot
+  DevBuf slot_q, slot_lo, slot_cnt, slot_hoff;
+  // per seed hit
+  DevBuf hit_keys, cand_sparse, rank_keys;
+  // per candidate (dense)
+  DevBuf cand_dense, cand_q, cand_edit, hit_tmp;
+  // scan scratch, counters, worklists
+  DevBuf scan_tmp, counters, worklist;
+  // per sub-batch results before concatenation
+  DevBuf sub_hits, sub_hit_off;
+  // whole-batch results (device-resident API)
+  DevBuf out_hits, out_hit_off;
+  // staged inputs for the host API
+  DevBuf d_seqs, d_seq_off;
+  void release_all();
+};
+
+}  // namespace mtsv
+
+struct mtsvgpu_index {
+  mtsv::DeviceIndex ix;
+  mtsvgpu_index_opts opts{};
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t stream = nullptr;
+  bool profiling = false;
+  mtsv::BatchWorkspace ws;
+  mtsvgpu_batch_stats stats{};
+  // pinned staging for the host API
+  void* pin_in = nullptr;
+  size_t pin_in_cap = 0;
+  void* pin_out = nullptr;
+  size_t pin_out_cap = 0;
+  // event pool for profiling
+  std::vector<cudaEvent_t> ev_pool;
+  std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> ev_used;
+  size_t ev_next = 0;
+};
+
+namespace mtsv {
+// index.cu
+int index_from_host_parts(const uint8_t* text, uint64_t n, const mtsvgpu_bin* bins, uint64_t n_bins,
+                          const uint8_t* bwt, const uint64_t* sa_sample, uint64_t sa_sample_len,
+                          uint64_t sa_rate, int device, const mtsvgpu_index_opts* opts,
+                          mtsvgpu_index** out);
+int index_open_file(const char* path, int device, const mtsvgpu_index_opts* opts,
+                    mtsvgpu_index** out);
+void index_destroy(mtsvgpu_index* h);
+// binner.cu
+int bin_batch_device(mtsvgpu_index* h, const uint8_t* d_seqs, const uint64_t* d_seq_off,
+                     uint64_t n_reads, const uint64_t* h_seq_off_or_null,
+                     const mtsvgpu_params* params, const mtsvgpu_hit** d_hits,
+                     const uint64_t** d_hit_off, uint64_t* n_hits);
+int backward_search_batch(mtsvgpu_index* h, const uint8_t* pats, uint32_t pat_len, uint64_t n_pats,
+                          uint64_t* lower, uint64_t* upper);
+int locate_batch(mtsvgpu_index* h, const uint64_t* rows, uint64_t n_rows, uint64_t* pos);
+int edit_distance_batch(int device, const uint8_t* pats, const uint64_t* pat_off,
+                        const uint8_t* texts, const uint64_t* text_off, uint64_t n_pairs,
+                        uint32_t* edits);
+// scan.cuh users
+int exclusive_scan_u32(const uint32_t* d_in, uint32_t* d_out, uint64_t n, DevBuf& tmp,
+                       uint64_t* d_total, cudaStream_t stream);
+}  // namespace mtsv

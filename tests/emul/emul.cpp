@@ -1,0 +1,261 @@
+// emul.cpp — TEST-ONLY host harness that runs the per-item device logic of
+// mtsv_tools_b200/csrc/core.cuh serially on the CPU (compiled with g++, no CUDA), so the
+// arithmetic of every stage can be diffed against the oracle without a GPU.  It is not part of
+// the product: libmtsv_b200.so never contains or calls this code and has no CPU path.
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "../../mtsv_tools_b200/csrc/core.cuh"
+
+using namespace mtsv;
+
+namespace {
+
+struct EmulIndex {
+  std::vector<FmBlock> blocks;
+  std::vector<SuperCounts> super;
+  std::vector<uint32_t> n_before;
+  std::vector<uint32_t> sa;
+  std::vector<uint2> ktab;
+  std::vector<uint8_t> text;
+  std::vector<uint32_t> bin_start, bin_end, bin_tax, bin_gi;
+  FmView fm{};
+  SaView sv{};
+  KtabView kt{};
+  BinsView bv{};
+};
+
+}  // namespace
+
+extern "C" {
+
+struct emul_bin {
+  uint32_t gi, tax_id;
+  uint64_t start, end;
+};
+
+struct emul_params {
+  double edit_rate;
+  uint32_t seed_size, seed_gap;
+  double min_seed;
+  uint64_t max_hits, tune_max_hits;
+  int64_t max_candidates, max_assignments;
+  uint32_t strands, reserved;
+};
+
+void* emul_index_build(const uint8_t* text, uint64_t n, const emul_bin* bins, uint64_t n_bins,
+                       const uint8_t* bwt, const uint64_t* sample, uint64_t n_sample, uint64_t s_file,
+                       uint32_t sa_rate, uint32_t ktab_k) {
+  EmulIndex* e = new EmulIndex;
+  e->text.assign(text, text + n);
+  e->text.resize(n + 16, 0);
+  for (uint64_t i = 0; i < n_bins; ++i) {
+    e->bin_start.push_back((uint32_t)bins[i].start);
+    e->bin_end.push_back((uint32_t)bins[i].end);
+    e->bin_tax.push_back(bins[i].tax_id);
+    e->bin_gi.push_back(bins[i].gi);
+  }
+  uint64_t n_blocks = n / 64 + 1;
+  uint64_t n_super = (n_blocks + kBlocksPerSuper - 1) / kBlocksPerSuper;
+  e->blocks.assign(n_super * kBlocksPerSuper, FmBlock{{0, 0, 0, 0}, 0, 0, 0});
+  e->super.resize(n_super);
+  e->n_before.assign(n_super * kBlocksPerSuper, 0);
+  uint32_t run[5] = {0, 0, 0, 0, 0};
+  uint32_t sup[4] = {0, 0, 0, 0};
+  uint32_t dollar = 0;
+  for (uint64_t blk = 0; blk < n_blocks; ++blk) {
+    if (blk % kBlocksPerSuper == 0) {
+      for (int a = 0; a < 4; ++a) {
+        sup[a] = run[a];
+        e->super[blk / kBlocksPerSuper].c[a] = run[a];
+      }
+    }
+    FmBlock b{{0, 0, 0, 0}, 0, 0, 0};
+    for (int a = 0; a < 4; ++a) b.rel[a] = (uint16_t)(run[a] - sup[a]);
+    e->n_before[blk] = run[4];
+    for (uint32_t j = 0; j < 64; ++j) {
+      uint64_t r = blk * 64 + j;
+      if (r >= n) break;
+      uint32_t c = text_code(bwt[r]);
+      if (c < 4) {
+        b.lo |= (uint64_t)(c & 1) << j;
+        b.hi |= (uint64_t)(c >> 1) << j;
+        run[c]++;
+      } else {
+        b.exc |= 1ull << j;
+        if (c == SYM_N) run[4]++;
+        else dollar = (uint32_t)r;
+      }
+    }
+    e->blocks[blk] = b;
+  }
+  e->fm.blocks = e->blocks.data();
+  e->fm.super = e->super.data();
+  e->fm.n_before = e->n_before.data();
+  e->fm.n = (uint32_t)n;
+  e->fm.dollar_row = dollar;
+  e->fm.C[SYM_A] = 1;
+  e->fm.C[SYM_C] = 1 + run[0];
+  e->fm.C[SYM_G] = 1 + run[0] + run[1];
+  e->fm.C[SYM_N] = 1 + run[0] + run[1] + run[2];
+  e->fm.C[SYM_T] = 1 + run[0] + run[1] + run[2] + run[4];
+  // suffix array at the requested rate: same walk as sa_densify_kernel
+  if (sa_rate == 0) sa_rate = 1;
+  e->sa.assign((n + sa_rate - 1) / sa_rate, 0xffffffffu);
+  for (uint64_t i = 0; i < n_sample; ++i) {
+    uint32_t row = (uint32_t)(i * s_file), pos = (uint32_t)sample[i];
+    if (row % sa_rate == 0) e->sa[row / sa_rate] = pos;
+    for (;;) {
+      FmBlock b = e->blocks[row >> 6];
+      uint32_t c = fm_symbol(e->fm, b, row);
+      if (c == SYM_DOLLAR) break;
+      row = fm_lf(e->fm, c, b, row);
+      pos -= 1;
+      if (row % s_file == 0) break;
+      if (row % sa_rate == 0) e->sa[row / sa_rate] = pos;
+    }
+  }
+  e->sv.sa = e->sa.data();
+  e->sv.rate = sa_rate;
+  // k-mer table, level by level like ktab_level_kernel
+  if (ktab_k) {
+    std::vector<uint2> cur(1), next;
+    cur[0].x = 0;
+    cur[0].y = (uint32_t)n;
+    for (uint32_t lev = 1; lev <= ktab_k; ++lev) {
+      next.resize(cur.size() * 4);
+      for (uint64_t t = 0; t < next.size(); ++t) {
+        uint32_t c = (uint32_t)(t / cur.size());
+        uint32_t l = cur[t % cur.size()].x, u = cur[t % cur.size()].y;
+        if (l < u) fm_step(e->fm, c, l, u);
+        if (l >= u) l = u = 0;
+        next[t].x = l;
+        next[t].y = u;
+      }
+      cur.swap(next);
+    }
+    e->ktab = cur;
+  }
+  e->kt.tab = e->ktab.data();
+  e->kt.k = ktab_k;
+  e->bv = BinsView{e->bin_start.data(), e->bin_end.data(), e->bin_tax.data(), e->bin_gi.data(),
+                   (uint32_t)n_bins};
+  return e;
+}
+
+void emul_index_free(void* p) { delete (EmulIndex*)p; }
+
+// rank, symbol, locate, backward search as the kernels compute them
+uint32_t emul_occ(void* p, uint32_t a, uint32_t i) { return fm_occ(((EmulIndex*)p)->fm, a, i); }
+uint32_t emul_locate(void* p, uint32_t row) {
+  EmulIndex* e = (EmulIndex*)p;
+  return fm_locate(e->fm, e->sv, row, nullptr);
+}
+void emul_backward_search(void* p, const uint8_t* pat, uint32_t len, uint32_t* lo, uint32_t* cnt) {
+  EmulIndex* e = (EmulIndex*)p;
+  seed_search_item(e->fm, e->kt, pat, 0, len, len, 0, lo, cnt, nullptr);
+}
+
+// Myers recurrence exactly as verify_kernel evaluates it (ncls = 4: binner rule, 5: raw bytes)
+uint32_t emul_edit_distance(const uint8_t* pat, uint32_t L, uint32_t rc, const uint8_t* txt, uint32_t T,
+                            int ncls) {
+  if (L == 0) return 0;
+  if (L > 1024) return 0xffffffffu;
+  uint64_t peq[5][16];
+  memset(peq, 0, sizeof peq);
+  for (uint32_t i = 0; i < L; ++i) {
+    uint8_t byte = rc ? pat[L - 1 - i] : pat[i];
+    uint32_t c;
+    if (ncls == 4) {
+      c = read_code(byte);
+      if (rc) c = comp_code(c);
+      if (c > 3) continue;
+    } else {
+      c = text_code(byte);
+      if (c > SYM_N) continue;
+    }
+    peq[c][i >> 6] |= 1ull << (i & 63);
+  }
+  auto pf = [&](uint32_t c, int w) { return peq[c][w]; };
+  auto tf = [&](uint32_t j) {
+    uint32_t c = text_code(txt[j]);
+    return c < (uint32_t)ncls ? c : 7u;
+  };
+  return myers_semiglobal<16>(L, T, pf, tf);
+}
+
+// the whole pipeline, one query at a time, in the stage order of binner.cu
+int emul_bin_reads(void* p, const uint8_t* seqs, const uint64_t* seq_off, uint64_t n_reads,
+                   const emul_params* ep, HitRec** hits_out, uint64_t** off_out) {
+  EmulIndex* e = (EmulIndex*)p;
+  Params prm;
+  prm.edit_rate = ep->edit_rate;
+  prm.min_seed = ep->min_seed;
+  prm.S = ep->seed_size;
+  prm.G = ep->seed_gap;
+  prm.max_hits = ep->max_hits;
+  prm.tune_max_hits = ep->tune_max_hits;
+  prm.max_candidates = ep->max_candidates < 0 ? -1 : ep->max_candidates;
+  prm.max_assignments = ep->max_assignments < 0 ? -1 : ep->max_assignments;
+  prm.ns = ep->strands == 1 ? 1 : 2;
+  ReadsView rv{seqs, seq_off, 0, (uint32_t)n_reads};
+  std::vector<HitRec> all;
+  std::vector<uint64_t> offs(n_reads + 1, 0);
+  const uint32_t nq = (uint32_t)n_reads * prm.ns;
+  for (uint32_t q = 0; q < nq; ++q) {
+    if (q % prm.ns == 0) offs[q / prm.ns] = all.size();
+    uint32_t L = query_len(rv, prm.ns, q);
+    const uint8_t* seq = query_seq(rv, prm.ns, q);
+    uint32_t rc = q % prm.ns;
+    uint32_t nslots = seed_slots(L, prm.S, prm.G);
+    std::vector<uint32_t> lo(nslots), cnt(nslots), hoff(nslots);
+    for (uint32_t j = 0; j < nslots; ++j)
+      seed_search_item(e->fm, e->kt, seq, rc, L, prm.S, j * prm.G, &lo[j], &cnt[j], nullptr);
+    uint32_t nseeds = 0, nhits = 0, ovf = 0;
+    seed_select_item(prm, nslots, cnt.data(), hoff.data(), &nseeds, &nhits, &ovf);
+    if (ovf) return -7;
+    std::vector<uint64_t> keys(nhits);
+    for (uint32_t j = 0; j < nslots; ++j)
+      if (hoff[j] != kUnused)
+        for (uint32_t r = 0; r < cnt[j]; ++r)
+          keys[hoff[j] + r] = make_hit_key(fm_locate(e->fm, e->sv, lo[j] + r, nullptr), j * prm.G);
+    std::sort(keys.begin(), keys.end());
+    uint32_t k = edit_budget(L, prm.edit_rate);
+    std::vector<CandRec> cand(nhits ? nhits : 1);
+    std::vector<uint64_t> rkeys(nhits ? nhits : 1);
+    uint32_t nc = nhits ? coalesce_item(e->bv, keys.data(), nhits, min_seeds_of(nseeds, prm.min_seed), L, k,
+                                        cand.data(), rkeys.data())
+                        : 0;
+    std::sort(rkeys.begin(), rkeys.begin() + nc);
+    std::vector<CandRec> dense(nc ? nc : 1);
+    std::vector<uint32_t> edits(nc ? nc : 1);
+    for (uint32_t i = 0; i < nc; ++i) {
+      dense[i] = cand[(uint32_t)(rkeys[i] & 0xffffffffu)];
+      bool skip = (prm.max_candidates >= 0 && (uint64_t)i >= (uint64_t)prm.max_candidates) ||
+                  2ull * k > (uint64_t)L || L == 0;
+      uint32_t ed = kNoEdit;
+      if (!skip) {
+        ed = emul_edit_distance(seq, L, rc, e->text.data() + dense[i].start, dense[i].end - dense[i].start, 4);
+        if (ed > k) ed = kNoEdit;
+      }
+      edits[i] = ed;
+    }
+    std::vector<HitRec> out(nc ? nc : 1);
+    uint32_t no = select_item(e->bv, prm, dense.data(), edits.data(), nc, k, out.data());
+    all.insert(all.end(), out.begin(), out.begin() + no);
+  }
+  offs[n_reads] = all.size();
+  *hits_out = (HitRec*)malloc((all.size() ? all.size() : 1) * sizeof(HitRec));
+  if (!all.empty()) memcpy(*hits_out, all.data(), all.size() * sizeof(HitRec));
+  *off_out = (uint64_t*)malloc((n_reads + 1) * 8);
+  memcpy(*off_out, offs.data(), (n_reads + 1) * 8);
+  return 0;
+}
+
+void emul_free(void* p) { free(p); }
+
+}  // extern "C"
