@@ -1,0 +1,474 @@
+#!/usr/bin/env python
+"""bench.py — reads/sec of the mtsv-binner read-assignment hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # CPU arm: the oracle on all host cores
+
+Workload (BASELINE.json configs[1]): one ~1 Gbp MG-index chunk (200 synthetic genomes x 5 Mbp, 10 % of
+each genome shared with an earlier genome at 1 % divergence, 0.1 % N), default binner flags, 150 bp
+reads (90 % from the reference with 2 % substitutions and 0.5 % indels, half reverse-complemented; 10 %
+random).  The index is replicated on every GPU and each GPU bins its own 10 M reads per step (weak
+scaling, no data-path collective: reads are independent units).  One step = one pass of the hot path
+over one such batch.  `value` = reads/s with the reads already resident in HBM (mtsvgpu_bin_batch_device);
+`e2e` = the same through mtsvgpu_bin_batch with pinned HOST buffers, H2D of the reads and D2H of the
+hits inside the timed region.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CONFIGS = {
+    # name: (n_genomes, genome_len, shared_frac, divergence, reads, read_len, flags)
+    "cfg2": dict(n_seqs=200, seq_len=5_000_000, shared=0.10, div=0.01, reads=10_000_000, read_len=150,
+                 flags={}, label="cfg2: 1 Gbp chunk (200 x 5 Mbp), 150 bp reads, default flags"),
+    "cfg1": dict(n_seqs=52, seq_len=192_308, shared=0.0, div=0.0, reads=100_000, read_len=150,
+                 flags={}, label="cfg1: 10 Mbp reference, 100k x 150 bp reads, default flags"),
+    "cfg2s": dict(n_seqs=40, seq_len=5_000_000, shared=0.10, div=0.01, reads=2_000_000, read_len=150,
+                  flags={}, label="cfg2s: 200 Mbp chunk (40 x 5 Mbp), 150 bp reads, default flags"),
+}
+CACHE_DIR = os.environ.get("MTSV_B200_CACHE", "/tmp/mtsv_b200_cache")
+
+
+def log(*a):
+    print("[bench]", *a, file=sys.stderr, flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# data
+# ------------------------------------------------------------------------------------------------
+def make_reference_torch(cfg, seed, device):
+    """i.i.d. ACGT genomes + shared diverged segments + N runs, generated on `device`."""
+    import torch
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    n_seqs, seq_len = cfg["n_seqs"], cfg["seq_len"]
+    total = n_seqs * seq_len
+    acgt = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device=device)
+    cat = torch.empty(total, dtype=torch.uint8, device=device)
+    step = 1 << 28
+    for b in range(0, total, step):
+        e = min(total, b + step)
+        cat[b:e] = acgt[torch.randint(0, 4, (e - b,), generator=g, device=device)]
+    rng = np.random.default_rng(seed)
+    if cfg["shared"] > 0:
+        seg = int(seq_len * cfg["shared"])
+        for i in range(1, n_seqs):
+            src = int(rng.integers(0, i))
+            so = int(rng.integers(0, seq_len - seg + 1))
+            do = int(rng.integers(0, seq_len - seg + 1))
+            piece = cat[src * seq_len + so: src * seq_len + so + seg].clone()
+            nmut = int(seg * cfg["div"])
+            if nmut:
+                pos = torch.randint(0, seg, (nmut,), generator=g, device=device)
+                piece[pos] = acgt[torch.randint(0, 4, (nmut,), generator=g, device=device)]
+            cat[i * seq_len + do: i * seq_len + do + seg] = piece
+    # N runs: 0.1 % of the bases in runs of 10-50
+    n_runs = int(total * 0.001 / 30)
+    if n_runs:
+        pos = torch.randint(0, total - 64, (n_runs,), generator=g, device=device)
+        ln = torch.randint(10, 51, (n_runs,), generator=g, device=device)
+        idx = pos[:, None] + torch.arange(50, device=device)[None, :]
+        m = torch.arange(50, device=device)[None, :] < ln[:, None]
+        cat[idx[m]] = ord("N")
+    off = np.arange(n_seqs + 1, dtype=np.uint64) * np.uint64(seq_len)
+    gi = np.arange(1, n_seqs + 1, dtype=np.uint32)
+    tax = (1000 + np.arange(n_seqs)).astype(np.uint32)
+    return cat, off, gi, tax
+
+
+def get_index_parts(name, cfg, device, rank, world, barrier):
+    """Build (GPU suffix sort) or load the cached MGIndex fields for the workload."""
+    import torch
+    from mtsv_tools_b200.build_index import build_index_parts
+    d = os.path.join(CACHE_DIR, "%s_seed3" % name)
+    done = os.path.join(d, "DONE")
+    if rank == 0 and not os.path.exists(done):
+        t0 = time.time()
+        os.makedirs(d, exist_ok=True)
+        dev = device if torch.cuda.is_available() else "cpu"
+        cat, off, gi, tax = make_reference_torch(cfg, 3, dev)
+        cat_np = cat.cpu().numpy()
+        del cat
+        if torch.cuda.is_available():
+            torch.cuda.empty_cache()
+        log("reference generated: %.1f Mbp in %.1fs" % (len(cat_np) / 1e6, time.time() - t0))
+        t1 = time.time()
+        parts = build_index_parts(cat_np, off, gi, tax, 32, device=dev, verbose=True)
+        log("index built (suffix array, BWT, samples) in %.1fs" % (time.time() - t1))
+        np.save(os.path.join(d, "text.npy"), parts["text"])
+        np.save(os.path.join(d, "bwt.npy"), parts["bwt"])
+        np.save(os.path.join(d, "sa_sample.npy"), parts["sa_sample"])
+        np.savez(os.path.join(d, "bins.npz"), gi=parts["bins"][0], tax=parts["bins"][1], start=parts["bins"][2],
+                 end=parts["bins"][3], off=off)
+        open(done, "w").write("ok")
+        del parts
+    barrier()
+    t0 = time.time()
+    b = np.load(os.path.join(d, "bins.npz"))
+    parts = dict(text=np.load(os.path.join(d, "text.npy")), bwt=np.load(os.path.join(d, "bwt.npy")),
+                 sa_sample=np.load(os.path.join(d, "sa_sample.npy")),
+                 bins=(b["gi"], b["tax"], b["start"], b["end"]), sa_rate=32, ref_off=b["off"])
+    log("rank %d: index parts loaded from %s in %.1fs" % (rank, d, time.time() - t0))
+    return parts
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "200"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f:
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1]))
+                mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for nme, v in zip(names, c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        if sm:
+            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                   "samples": len(sm)}
+        return out
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)), "measured"
+        except Exception:
+            pass
+    return {"hbm_gbs": 6650.0}, "fallback"
+
+
+# ------------------------------------------------------------------------------------------------
+# arms
+# ------------------------------------------------------------------------------------------------
+def run_reference_arm(args, cfg, rank, world):
+    """The reference's CPU implementation of the path = the oracle (the Rust binary cannot be built in
+    this image: no cargo/rustc), with the reference's own ssw.c, on all host cores."""
+    if rank != 0:
+        return
+    import torch
+    from oracle import pyoracle
+    from mtsv_tools_b200 import synth
+    cores = os.cpu_count() or 1
+    parts = get_index_parts(args.config, cfg, "cuda:0", 0, 1, lambda: None)
+    t0 = time.time()
+    oix = pyoracle.Index.from_parts(parts["text"], parts["bins"], parts["bwt"], parts["sa_sample"], 32)
+    log("oracle index assembled in %.1fs" % (time.time() - t0))
+    L = cfg["read_len"]
+    dev = "cuda:0" if torch.cuda.is_available() else "cpu"
+    # bounded sample per step: calibrate on 20k reads, aim at ~10 s per step
+    ref_t = torch.from_numpy(parts["text"][:-1]).to(dev)
+    calib = synth.make_reads_torch(ref_t, parts["ref_off"], 20000, L, 4, dev).cpu().numpy()
+    off = np.arange(20001, dtype=np.uint64) * np.uint64(L)
+    params = pyoracle.default_params(**cfg["flags"])
+    t0 = time.time()
+    oix.bin_reads((calib, off), params, threads=cores)
+    rate = 20000 / (time.time() - t0)
+    n_sample = int(min(cfg["reads"], max(20000, rate * args.ref_seconds)))
+    reads = synth.make_reads_torch(ref_t, parts["ref_off"], n_sample, L, 4, dev).cpu().numpy()
+    del ref_t
+    off = np.arange(n_sample + 1, dtype=np.uint64) * np.uint64(L)
+    for _ in range(min(args.warmup, 1)):
+        oix.bin_reads((reads[:20000 * L], off[:20001]), params, threads=cores)
+    t0 = time.time()
+    n_hits = 0
+    for _ in range(args.steps):
+        h, o = oix.bin_reads((reads, off), params, threads=cores)
+        n_hits = len(h)
+    dt = time.time() - t0
+    value = n_sample * args.steps / dt
+    sample = "%d of the workload's %d reads per step (same generator, same index)" % (n_sample, cfg["reads"])
+    line = {
+        "impl": "reference", "metric": "reads/sec binned (150 bp)", "value": value, "unit": "reads/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8/u32 integer", "data": "synthetic",
+        "config": {"workload": cfg["label"], "reads_per_step": n_sample, "threads": cores,
+                   "index_mbp": len(parts["text"]) / 1e6, "hits_per_step": n_hits},
+        "cpu_baseline": {"value": value, "unit": "reads/s", "cores": cores, "kind": "port", "sample": sample,
+                         "note": "C++ restatement of src/index.rs:258-432 + reference ssw.c (oracle/); "
+                                 "the Rust mtsv-binner cannot be built here"},
+        "e2e": {"value": value, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_gpu_arm(args, cfg, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from mtsv_tools_b200 import MGIndex, Params, synth, load_library
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — this implementation has no CPU path "
+                         "(use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = "cuda:%d" % local_rank
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    lib = load_library()
+    parts = get_index_parts(args.config, cfg, dev, rank, world, barrier)
+    t0 = time.time()
+    gix = MGIndex.from_parts(parts["text"], parts["bins"], parts["bwt"], parts["sa_sample"], 32,
+                             device=local_rank, sa_rate=args.sa_rate, ktab_k=args.ktab_k,
+                             batch_reads=args.batch_reads)
+    info = gix.info()
+    log("rank %d: index on device in %.1fs (relayout %.2fs), %.2f GB HBM, sa_rate %d, ktab k=%d" %
+        (rank, time.time() - t0, info["relayout_seconds"], info["device_bytes"] / 1e9,
+         info["device_sa_rate"], info["ktab_k"]))
+    L = cfg["read_len"]
+    n_reads = args.reads or cfg["reads"]
+    ref_t = torch.from_numpy(parts["text"][:-1]).to(dev)
+    t0 = time.time()
+    d_reads = synth.make_reads_torch(ref_t, parts["ref_off"], n_reads, L, 4 + 17 * rank, dev)
+    del ref_t
+    d_off = (torch.arange(n_reads + 1, dtype=torch.int64, device=dev) * L)
+    torch.cuda.synchronize()
+    log("rank %d: %d reads generated on device in %.1fs" % (rank, n_reads, time.time() - t0))
+    # pinned host copies for the end-to-end leg
+    h_reads = torch.empty(d_reads.numel(), dtype=torch.uint8, pin_memory=True)
+    h_reads.copy_(d_reads)
+    h_off = torch.empty(n_reads + 1, dtype=torch.int64, pin_memory=True)
+    h_off.copy_(d_off)
+    torch.cuda.synchronize()
+    params = Params(**cfg["flags"])
+    stream = torch.cuda.current_stream()
+    gix.set_stream(stream.cuda_stream)
+
+    # ---- parity gate on a sample before any timing (rank 0): GPU vs oracle, bit-exact ----
+    parity = None
+    if rank == 0 and not args.no_parity:
+        from oracle import pyoracle
+        ns = min(args.parity_reads, n_reads)
+        t0 = time.time()
+        oix = pyoracle.Index.from_parts(parts["text"], parts["bins"], parts["bwt"], parts["sa_sample"], 32)
+        sub = (h_reads.numpy()[:ns * L], h_off.numpy()[:ns + 1].astype(np.uint64))
+        want_h, want_o = oix.bin_reads(sub, pyoracle.default_params(**cfg["flags"]), threads=os.cpu_count())
+        got_h, got_o = gix.bin_reads(sub, params)
+        ok = np.array_equal(want_o, got_o) and all(np.array_equal(want_h[f], got_h[f])
+                                                   for f in ("tax_id", "gi", "offset", "edit"))
+        parity = {"reads": ns, "hits": int(len(want_h)), "bit_exact": bool(ok)}
+        log("parity gate: %s (%.1fs)" % (parity, time.time() - t0))
+        if not ok:
+            raise SystemExit("bench.py: GPU results differ from the oracle — refusing to report a number")
+    else:
+        oix = None
+    barrier()
+
+    def step_device():
+        return gix.bin_reads_device(d_reads.data_ptr(), d_off.data_ptr(), n_reads, params)
+
+    # ---- device-resident timing ----
+    for _ in range(max(3, args.warmup)):
+        step_device()
+    gix.set_profiling(not args.no_profile)
+    launches0 = lib.mtsvgpu_launch_count()
+    clocks = ClockSampler(local_rank)
+    torch.cuda.synchronize()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    stage_ms = {}
+    stats = None
+    e0.record(stream)
+    for _ in range(args.steps):
+        _, _, n_hits = step_device()
+        if not args.no_profile:
+            stats = gix.last_batch_stats()
+            for k, v in stats["ms"].items():
+                stage_ms[k] = stage_ms.get(k, 0.0) + v
+    e1.record(stream)
+    torch.cuda.synchronize()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clk = clocks.stop()
+    launches = lib.mtsvgpu_launch_count() - launches0
+    gix.set_profiling(False)
+    if stats is None:
+        gix.set_profiling(True)
+        step_device()
+        stats = gix.last_batch_stats()
+        stage_ms = {k: v * args.steps for k, v in stats["ms"].items()}
+        gix.set_profiling(False)
+
+    # ---- end-to-end timing: host buffers in, host results out ----
+    hr, ho = h_reads.numpy(), h_off.numpy().astype(np.uint64)
+    for _ in range(2):
+        gix.bin_reads((hr, ho), params)
+    torch.cuda.synchronize()
+    barrier()
+    t0 = time.perf_counter()
+    d2h = 0
+    for _ in range(args.steps):
+        hits, offs = gix.bin_reads((hr, ho), params)
+        d2h = hits.nbytes + offs.nbytes
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    barrier()
+
+    # ---- reduce over ranks: max time ----
+    if world > 1:
+        t = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_ms = float(t[0]), float(t[1])
+    else:
+        e2e_ms = e2e_s * 1e3
+    if rank != 0:
+        return
+    total_reads = n_reads * world * args.steps
+    value = total_reads / (ms * 1e-3)
+    e2e_value = total_reads / (e2e_ms * 1e-3)
+
+    # ---- roofline of the dominant kernel ----
+    peaks, peak_kind = measured_peaks()
+    S = params.seed_size
+    per_step = {k: v / args.steps for k, v in stage_ms.items()}
+    alg_bytes = {
+        # index sectors actually needed (counted in-kernel) + seed bases read + 8 B interval out per slot
+        "seed_search": 32.0 * stats["rank_queries"] + (S + 8.0) * stats["n_seed_slots"],
+        # one SA sector per located row + 8 B key out
+        "locate": (32.0 + 8.0) * stats["n_seed_hits"],
+        # reference window bytes + the read + 4 B result
+        "verify": stats["window_bytes"] + (L + 4.0) * stats["n_candidates"],
+    }
+    dom = max(alg_bytes, key=lambda k: per_step.get(k, 0.0))
+    dom_ms = per_step.get(dom, 0.0)
+    achieved = alg_bytes[dom] / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": dom + "_kernel", "achieved": achieved, "peak": peaks["hbm_gbs"],
+                "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": None,
+                "peak_source": "%s MEASURED_PEAKS.json hbm_gbs (streaming copy)" % peak_kind,
+                "algorithmic_bytes_per_launch": alg_bytes[dom] / max(1, -(-n_reads // (args.batch_reads or (1 << 20)))),
+                "kernel_ms_per_step": dom_ms, "share_of_step": dom_ms / (ms / args.steps),
+                "random_sector_ceiling_gbs": 1290.0,
+                "note": "random 32-B sector gathers; tools/randbench.cu measured 4.0e10 sectors/s (1.29 TB/s) "
+                        "on this pool for tables beyond L2 (profiles/r01_randbench.jsonl)"}
+
+    # ---- CPU baseline on a bounded sample (rank 0, N=1 only) ----
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import pyoracle
+        if oix is None:
+            oix = pyoracle.Index.from_parts(parts["text"], parts["bins"], parts["bwt"], parts["sa_sample"], 32)
+        cores = os.cpu_count() or 1
+        op = pyoracle.default_params(**cfg["flags"])
+        t0 = time.time()
+        oix.bin_reads((hr[:20000 * L], ho[:20001]), op, threads=cores)
+        rate = 20000 / (time.time() - t0)
+        ns = int(min(n_reads, max(20000, rate * args.cpu_seconds)))
+        ctr = pyoracle.Counters()
+        t0 = time.time()
+        oix.bin_reads((hr[:ns * L], ho[:ns + 1]), op, threads=cores, counters=ctr)
+        dt = time.time() - t0
+        c = ctr.as_dict()
+        cpu = {"value": ns / dt, "unit": "reads/s", "cores": cores, "kind": "port",
+               "sample": "first %d of the step's %d reads, %.1f s" % (ns, n_reads, dt),
+               "reference_algorithm_sectors_per_read":
+                   (2 * c["bs_steps"] + c["lf_steps"] + c["rows_located"] + c["window_bytes"] / 128.0) / ns}
+
+    line = {
+        "metric": "reads/sec binned (150 bp)", "value": value, "unit": "reads/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/u32 integer",
+        "data": "synthetic",
+        "config": {"workload": cfg["label"], "reads_per_gpu_per_step": n_reads, "index_mbp": info["text_len"] / 1e6,
+                   "index_replicated": True, "device_sa_rate": info["device_sa_rate"], "ktab_k": info["ktab_k"],
+                   "index_hbm_gb": info["device_bytes"] / 1e9, "batch_reads": args.batch_reads or (1 << 20),
+                   "l2_note": "index (>= 1 GB at cfg2) and per-step read batch exceed the 126 MB L2",
+                   "hits_per_step": int(stats["n_hits"]), "profiling_events": not args.no_profile},
+        "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": int(hr.nbytes + ho.nbytes),
+                "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms / args.steps},
+        "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "cpu_baseline": cpu,
+        "stages_ms_per_step": per_step,
+        "work_per_step": {k: stats[k] for k in ("n_queries", "n_seed_slots", "n_seed_hits", "n_candidates",
+                                                 "n_hits", "window_bytes", "rank_queries")},
+        "parity": parity, "index_load_seconds": info["load_seconds"],
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS))
+    ap.add_argument("--reads", type=int, default=0, help="reads per GPU per step (default: the config's)")
+    ap.add_argument("--sa-rate", type=int, default=0)
+    ap.add_argument("--ktab-k", type=int, default=0)
+    ap.add_argument("--batch-reads", type=int, default=0)
+    ap.add_argument("--parity-reads", type=int, default=50000)
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--ref-seconds", type=float, default=10.0)
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-profile", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    cfg = CONFIGS[args.config]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference_arm(args, cfg, rank, world)
+        return
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_gpu_arm(args, cfg, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

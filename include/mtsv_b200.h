@@ -112,7 +112,7 @@ typedef struct {
   uint64_t n_candidates;   /* windows verified */
   uint64_t n_hits;         /* hits returned */
   uint64_t window_bytes;   /* reference bytes read by the verifier */
-  uint64_t rank_queries;   /* occurrence-rank queries executed by seed search (0 unless profiling) */
+  uint64_t rank_queries;   /* 32-byte index sectors touched by seed search: FM blocks + k-mer table (0 unless profiling) */
 } mtsvgpu_batch_stats;
 
 /* ---- index lifetime: replaces from_file::<MGIndex> (src/io.rs:115-122, src/binner.rs:63-67) ---- */

@@ -707,7 +707,7 @@ static int run_sub_batch(mtsvgpu_index* h, const Params& p, const uint8_t* d_seq
   }
   const uint32_t n_hits = (uint32_t)hc.total_hits;
   h->stats.n_seed_hits += n_hits;
-  h->stats.rank_queries += 2 * hc.rank_steps;
+  h->stats.rank_queries += hc.rank_steps;  // sectors touched by seed search (profiling only)
 
   uint64_t sub_out = 0;
   uint32_t n_cand = 0;

@@ -149,7 +149,8 @@ MTSV_HD uint32_t fm_symbol(const FmView& fm, const FmBlock& b, uint32_t row) {
 
 // One backward-search step on the half-open interval [l,u) — bio FMIndexable::backward_search
 // body: l = less[a] + occ(l-1,a) ; r = less[a] + occ(r,a) - 1  with u = r + 1.
-MTSV_HD void fm_step(const FmView& fm, uint32_t a, uint32_t& l, uint32_t& u) {
+MTSV_HD uint32_t fm_step(const FmView& fm, uint32_t a, uint32_t& l, uint32_t& u) {
+  uint32_t sectors = 1;  // FmBlock sectors touched (the roofline's unit of work)
   if (a < 4) {
     uint32_t bl = l >> 6, bu = u >> 6;
     uint32_t sup_l = ldg(&fm.super[bl >> 9].c[a]);
@@ -161,6 +162,7 @@ MTSV_HD void fm_step(const FmView& fm, uint32_t a, uint32_t& l, uint32_t& u) {
     } else {
       FmBlock b2 = load_block(fm.blocks + bu);
       ou = ldg(&fm.super[bu >> 9].c[a]) + block_occ(b2, a, u & 63);
+      sectors = 2;
     }
     l = fm.C[a] + ol;
     u = fm.C[a] + ou;
@@ -168,7 +170,9 @@ MTSV_HD void fm_step(const FmView& fm, uint32_t a, uint32_t& l, uint32_t& u) {
     uint32_t ol = fm_occ(fm, SYM_N, l), ou = fm_occ(fm, SYM_N, u);
     l = fm.C[SYM_N] + ol;
     u = fm.C[SYM_N] + ou;
+    sectors = 4;  // two FmBlock sectors + two n_before sectors
   }
+  return sectors;
 }
 
 // LF mapping used by locate — bio SampledSuffixArray::get: pos = less[c] + occ(pos-1, c)
@@ -289,12 +293,12 @@ MTSV_HD void seed_search_item(const FmView& fm, const KtabView& kt, const uint8_
       l = e.x;
       u = e.y;
       i -= (int)kt.k;
+      steps = 1;  // one table sector
     }
   }
   for (; i >= 0 && l < u; --i) {
     uint32_t a = strand_base(seq, rc, L, seed_off + (uint32_t)i);
-    fm_step(fm, a, l, u);
-    ++steps;
+    steps += fm_step(fm, a, l, u);
   }
   if (rank_steps) *rank_steps = steps;
   if (l < u) {

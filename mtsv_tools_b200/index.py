@@ -72,7 +72,7 @@ class MGIndex:
         return cls(h.value)
 
     @classmethod
-    def from_parts(cls, text, bins, bwt, sa_sample, sa_rate, device=0, **opts):
+    def from_parts(cls, text, bins, bwt, sa_sample, file_sa_rate, device=0, **opts):
         """text/bwt: uint8 arrays incl. '$'; bins: (gi, tax, start, end) arrays; sa_sample: uint64."""
         L = _lib.load_library()
         text = np.ascontiguousarray(text, dtype=np.uint8)
@@ -85,7 +85,7 @@ class MGIndex:
         h = C.c_void_p()
         o = cls._opts(**opts)
         check(L.mtsvgpu_index_from_parts(_ptr(text), len(text), barr, len(gi), _ptr(bwt), _ptr(sa_sample),
-                                         len(sa_sample), sa_rate, device, C.byref(o), C.byref(h)))
+                                         len(sa_sample), file_sa_rate, device, C.byref(o), C.byref(h)))
         return cls(h.value)
 
     def close(self):

@@ -117,7 +117,8 @@ inline uint64_t locate(const orc_index& ix, uint64_t row, uint64_t* lf_steps) {
 uint32_t min_edit_distance(std::vector<uint32_t>& d, const uint8_t* p, size_t plen,
                            const uint8_t* t, size_t tlen) {
   size_t row_mult = tlen + 1;
-  d.assign((plen + 1) * row_mult, 0);
+  d.resize((plen + 1) * row_mult, 0);
+  for (size_t i = 0; i < row_mult; ++i) d[i] = 0;
   for (size_t row = 1; row <= plen; ++row) d[row * row_mult] = (uint32_t)row;
   for (size_t row = 1; row <= plen; ++row) {
     uint8_t pc = p[row - 1];
@@ -164,6 +165,8 @@ const SswApi& ssw_api() {
   }();
   return api;
 }
+
+int g_ssw_kind = 0;  // 0 auto (reference ssw.c when built), 1 force reference, 2 force restated
 
 // ssw/src/lib.rs:11-16 (note the last entry is +1: N-N scores as a match)
 const int8_t kIdentMatrix[25] = {1, -1, -1, -1, -1, -1, 1, -1, -1, -1, -1, -1, 1,
@@ -375,7 +378,7 @@ void matching_tax_ids(const orc_index& ix, const uint8_t* seq, uint64_t len, con
     if (std::find(matches.begin(), matches.end(), tax) != matches.end()) continue;  // :393-396
     const uint8_t* cand_seq = ix.text.data() + c.start;  // :401
     size_t cand_len = c.end - c.start;
-    if (!profile) profile = new Profile(seq, len, 0);
+    if (!profile) profile = new Profile(seq, len, g_ssw_kind);
     int score = profile->align_score(cand_seq, cand_len);  // :402
     if (ctr) {
       ctr->sw_calls++;
@@ -467,6 +470,38 @@ struct Reader {
 
 }  // namespace
 
+
+namespace {
+// less (src/index.rs:570) and Occ::new (src/index.rs:571) from the BWT
+void build_less_occ(orc_index* ix, uint32_t occ_interval) {
+  const uint64_t n = ix->bwt.size();
+  ix->k = occ_interval;
+  // :570 less over n_alphabet() = "ACGTNacgtn": max symbol 't' (116) -> 118 entries
+  const size_t m_less = 118, m_occ = 117;
+  ix->less.assign(m_less, 0);
+  {
+    std::vector<uint64_t> count(256, 0);
+    for (uint8_t c : ix->bwt) count[c]++;
+    uint64_t sum = 0;
+    for (size_t c = 0; c < m_less; ++c) {
+      ix->less[c] = sum;
+      sum += count[c];
+    }
+  }
+  // :571 Occ::new — entry j of symbol a = count of a in bwt[0..=j*k]; alphabet symbols + '$'
+  ix->occ.assign(m_occ, {});
+  {
+    const uint8_t alpha[] = {'A', 'C', 'G', 'T', 'N', 'a', 'c', 'g', 't', 'n', '$'};
+    std::vector<uint64_t> cur(256, 0);
+    for (uint64_t i = 0; i < n; ++i) {
+      cur[ix->bwt[i]]++;
+      if (i % occ_interval == 0)
+        for (uint8_t a : alpha) ix->occ[a].push_back(cur[a]);
+    }
+  }
+}
+}  // namespace
+
 // =================================================================== C API
 
 extern "C" {
@@ -541,29 +576,29 @@ orc_index* orc_index_build(const uint8_t* seqs, const uint64_t* seq_off, const u
     orc::sais<int64_t, uint8_t>(ix->text.data(), sa.data(), (int64_t)n, 256);
     finish(sa.data());
   }
-  // :570 less over n_alphabet() = "ACGTNacgtn": max symbol 't' (116) -> 118 entries
-  const size_t m_less = 118, m_occ = 117;
-  ix->less.assign(m_less, 0);
-  {
-    std::vector<uint64_t> count(256, 0);
-    for (uint8_t c : ix->bwt) count[c]++;
-    uint64_t sum = 0;
-    for (size_t c = 0; c < m_less; ++c) {
-      ix->less[c] = sum;
-      sum += count[c];
-    }
-  }
-  // :571 Occ::new — entry j of symbol a = count of a in bwt[0..=j*k]; alphabet symbols + '$'
-  ix->occ.assign(m_occ, {});
-  {
-    const uint8_t alpha[] = {'A', 'C', 'G', 'T', 'N', 'a', 'c', 'g', 't', 'n', '$'};
-    std::vector<uint64_t> cur(256, 0);
-    for (uint64_t i = 0; i < n; ++i) {
-      cur[ix->bwt[i]]++;
-      if (i % occ_interval == 0)
-        for (uint8_t a : alpha) ix->occ[a].push_back(cur[a]);
-    }
-  }
+  build_less_occ(ix, occ_interval);
+  return ix;
+}
+
+// An MGIndex assembled from already computed parts (text incl. '$', bins, BWT, row-sampled SA):
+// used when the suffix array was built elsewhere (e.g. on the GPU for the 1 Gbp benchmark index).
+orc_index* orc_index_from_parts(const uint8_t* text, uint64_t n, const uint32_t* gi,
+                                const uint32_t* tax_id, const uint64_t* start, const uint64_t* end,
+                                uint64_t n_bins, const uint8_t* bwt, const uint64_t* sample,
+                                uint64_t n_sample, uint64_t sa_sample, uint32_t occ_interval) {
+  if (occ_interval == 0 || sa_sample == 0 || n == 0) return nullptr;
+  if (n_sample != (n + sa_sample - 1) / sa_sample) return nullptr;
+  orc_index* ix = new orc_index;
+  ix->text.assign(text, text + n);
+  ix->bwt.assign(bwt, bwt + n);
+  for (uint64_t i = 0; i < n_bins; ++i) ix->bins.push_back(Bin{gi[i], tax_id[i], start[i], end[i]});
+  ix->sample.assign(sample, sample + n_sample);
+  ix->s = sa_sample;
+  ix->sentinel = '$';
+  // extra_rows: the row whose BWT symbol is the sentinel holds suffix 0 (bio SuffixArray::sample)
+  for (uint64_t r = 0; r < n; ++r)
+    if (bwt[r] == '$' && r % sa_sample != 0) ix->extra_rows[r] = 0;
+  build_less_occ(ix, occ_interval);
   return ix;
 }
 
@@ -707,6 +742,7 @@ uint32_t orc_min_edit_distance(const uint8_t* p, uint64_t plen, const uint8_t* t
 }
 
 int orc_ssw_ref_available(void) { return ssw_api().ok ? 1 : 0; }
+void orc_set_ssw_kind(int kind) { g_ssw_kind = kind; }
 
 int orc_ssw_score(const uint8_t* read, uint64_t rlen, const uint8_t* ref, uint64_t reflen,
                   int kind) {

@@ -65,6 +65,10 @@ typedef struct {
 orc_index* orc_index_build(const uint8_t* seqs, const uint64_t* seq_off, const uint32_t* gi,
                            const uint32_t* tax_id, uint64_t n_seqs, uint32_t occ_interval,
                            uint64_t sa_sample);
+orc_index* orc_index_from_parts(const uint8_t* text, uint64_t n, const uint32_t* gi,
+                                const uint32_t* tax_id, const uint64_t* start, const uint64_t* end,
+                                uint64_t n_bins, const uint8_t* bwt, const uint64_t* sample,
+                                uint64_t n_sample, uint64_t sa_sample, uint32_t occ_interval);
 int orc_index_write(const orc_index* ix, const char* path);
 orc_index* orc_index_read(const char* path);
 void orc_index_free(orc_index* ix);
@@ -97,6 +101,7 @@ uint32_t orc_min_edit_distance(const uint8_t* p, uint64_t plen, const uint8_t* t
 /* Profile::new + align_score(.,1,1) (ssw/src/lib.rs:36-86). kind: 0 auto, 1 force _ref, 2 force restated */
 int orc_ssw_score(const uint8_t* read, uint64_t rlen, const uint8_t* ref, uint64_t reflen, int kind);
 int orc_ssw_ref_available(void);
+void orc_set_ssw_kind(int kind); /* SW used by the hot path: 0 auto, 1 reference ssw.c, 2 restated */
 
 /* SeedHit::candidate_indices (src/index.rs:118-153); returns 1 and fills out if Some */
 int orc_candidate_indices(uint64_t site, uint64_t q_off, uint64_t bin_start, uint64_t bin_end,

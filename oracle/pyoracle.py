@@ -66,6 +66,9 @@ def lib():
     vp = C.c_void_p
     L.orc_index_build.restype = vp
     L.orc_index_build.argtypes = [vp, vp, vp, vp, C.c_uint64, C.c_uint32, C.c_uint64]
+    L.orc_index_from_parts.restype = vp
+    L.orc_index_from_parts.argtypes = [vp, C.c_uint64, vp, vp, vp, vp, C.c_uint64, vp, vp, C.c_uint64,
+                                       C.c_uint64, C.c_uint32]
     L.orc_index_write.argtypes = [vp, C.c_char_p]
     L.orc_index_read.restype = vp
     L.orc_index_read.argtypes = [C.c_char_p]
@@ -146,6 +149,17 @@ class Index:
                                          occ_interval, sa_sample))
 
     @classmethod
+    def from_parts(cls, text, bins, bwt, sa_sample, sa_rate, occ_interval=64):
+        text = np.ascontiguousarray(text, dtype=np.uint8)
+        bwt = np.ascontiguousarray(bwt, dtype=np.uint8)
+        sa_sample = np.ascontiguousarray(sa_sample, dtype=np.uint64)
+        gi, tx, st, en = [np.ascontiguousarray(a, dtype=d) for a, d in
+                          zip(bins, (np.uint32, np.uint32, np.uint64, np.uint64))]
+        return cls(lib().orc_index_from_parts(_ptr(text), len(text), _ptr(gi), _ptr(tx), _ptr(st), _ptr(en),
+                                              len(gi), _ptr(bwt), _ptr(sa_sample), len(sa_sample), sa_rate,
+                                              occ_interval))
+
+    @classmethod
     def read(cls, path):
         return cls(lib().orc_index_read(os.fsencode(path)))
 
@@ -155,8 +169,8 @@ class Index:
             raise IOError("orc_index_write failed: %d" % rc)
 
     def __del__(self):
-        if getattr(self, "h", None):
-            lib().orc_index_free(self.h)
+        if getattr(self, "h", None) and _LIB is not None:
+            _LIB.orc_index_free(self.h)
             self.h = None
 
     def __len__(self):

@@ -143,7 +143,7 @@ CASES = [
     ("edit 0", dict(edit_rate=0.0), {}),
     ("min_seed 0.5", dict(min_seed=0.5), {}),
     ("tiny sub-batches", {}, dict(batch_reads=97)),
-    ("hit cap forces splitting", {}, dict(max_batch_hits=500)),
+    ("hit cap forces splitting", {}, dict(max_batch_hits=5000)),
 ]
 
 
