@@ -337,15 +337,16 @@ def run_gpu_arm(args, cfg, rank, world, local_rank):
         gix.set_profiling(False)
 
     # ---- end-to-end timing: host buffers in, host results out ----
-    hr, ho = h_reads.numpy(), h_off.numpy().astype(np.uint64)
+    # (mtsvgpu_bin_batch_pinned: host buffers in, host results out in the handle's page-locked buffers)
+    hr, ho = h_reads.numpy(), h_off.numpy().view(np.uint64)
     for _ in range(2):
-        gix.bin_reads((hr, ho), params)
+        gix.bin_reads_pinned((hr, ho), params)
     torch.cuda.synchronize()
     barrier()
     t0 = time.perf_counter()
     d2h = 0
     for _ in range(args.steps):
-        hits, offs = gix.bin_reads((hr, ho), params)
+        hits, offs = gix.bin_reads_pinned((hr, ho), params)
         d2h = hits.nbytes + offs.nbytes
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0

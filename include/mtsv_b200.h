@@ -135,6 +135,11 @@ MTSVGPU_API int mtsvgpu_index_get_info(const mtsvgpu_index* ix, mtsvgpu_index_in
 MTSVGPU_API int mtsvgpu_bin_batch(mtsvgpu_index* ix, const uint8_t* seqs, const uint64_t* seq_off,
                       uint64_t n_reads, const mtsvgpu_params* params, mtsvgpu_hit** hits,
                       uint64_t** hit_off);
+/* Same, but the results are left in page-locked buffers owned by the handle (no allocation, no extra
+ * copy): valid until the next batch call on this handle or its close; do not free them. */
+MTSVGPU_API int mtsvgpu_bin_batch_pinned(mtsvgpu_index* ix, const uint8_t* seqs, const uint64_t* seq_off,
+                             uint64_t n_reads, const mtsvgpu_params* params,
+                             const mtsvgpu_hit** hits, const uint64_t** hit_off, uint64_t* n_hits);
 /* Same with inputs already resident in device memory and results left there.  The returned device
  * pointers are owned by the handle and stay valid until its next batch call or close. */
 MTSVGPU_API int mtsvgpu_bin_batch_device(mtsvgpu_index* ix, const uint8_t* d_seqs, const uint64_t* d_seq_off,

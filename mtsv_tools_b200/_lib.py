@@ -58,7 +58,7 @@ class StatsStruct(C.Structure):
 # every symbol include/mtsv_b200.h declares
 EXPORTS = [
     "mtsvgpu_index_open", "mtsvgpu_index_from_parts", "mtsvgpu_index_close", "mtsvgpu_index_get_info",
-    "mtsvgpu_bin_batch", "mtsvgpu_bin_batch_device", "mtsvgpu_last_batch_stats", "mtsvgpu_set_stream",
+    "mtsvgpu_bin_batch", "mtsvgpu_bin_batch_pinned", "mtsvgpu_bin_batch_device", "mtsvgpu_last_batch_stats", "mtsvgpu_set_stream",
     "mtsvgpu_set_profiling", "mtsvgpu_backward_search", "mtsvgpu_locate", "mtsvgpu_edit_distance",
     "mtsvgpu_free", "mtsvgpu_last_error", "mtsvgpu_launch_count", "mtsvgpu_version",
 ]
@@ -95,6 +95,8 @@ def load_library():
     L.mtsvgpu_index_get_info.argtypes = [vp, C.POINTER(InfoStruct)]
     L.mtsvgpu_bin_batch.argtypes = [vp, vp, vp, C.c_uint64, C.POINTER(ParamsStruct),
                                     C.POINTER(C.POINTER(HitStruct)), C.POINTER(u64p)]
+    L.mtsvgpu_bin_batch_pinned.argtypes = [vp, vp, vp, C.c_uint64, C.POINTER(ParamsStruct),
+                                           C.POINTER(vp), C.POINTER(vp), u64p]
     L.mtsvgpu_bin_batch_device.argtypes = [vp, vp, vp, C.c_uint64, C.POINTER(ParamsStruct),
                                            C.POINTER(vp), C.POINTER(vp), u64p]
     L.mtsvgpu_last_batch_stats.argtypes = [vp, C.POINTER(StatsStruct)]

@@ -23,9 +23,11 @@ namespace mtsv {
 // ------------------------------------------------------------------------------------------
 // small kernels
 // ------------------------------------------------------------------------------------------
+constexpr uint32_t kMaxReadLenDev = 1024;  // longer reads fail the batch (ELIMIT) before any seed work
+
 struct BatchCounters {  // device-side scalars of one sub-batch
   unsigned long long total_slots, total_hits, total_cands, total_out;
-  unsigned int max_len, overflow, n_medium, n_large, medium_cursor, large_cursor;
+  unsigned int max_len, overflow, n_medium, n_large, bad_offsets, reserved0;
   unsigned long long rank_steps, window_bytes;
 };
 
@@ -34,8 +36,14 @@ __global__ void count_slots_kernel(ReadsView rv, Params p, uint32_t nq, uint32_t
   uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
   uint32_t L = 0;
   if (q < nq) {
-    L = query_len(rv, p.ns, q);
-    q_nslots[q] = seed_slots(L, p.S, p.G);
+    uint64_t r = rv.read0 + q / p.ns;
+    uint64_t a = rv.seq_off[r], b = rv.seq_off[r + 1];
+    if (b < a || b - a > 0xffffffffull) {  // not monotone: treat as empty and flag the batch
+      atomicExch(&ctr->bad_offsets, 1u);
+    } else {
+      L = (uint32_t)(b - a);
+    }
+    q_nslots[q] = L <= kMaxReadLenDev ? seed_slots(L, p.S, p.G) : 0;
   }
   // block max of L -> one atomic per block
   __shared__ unsigned int smax;
@@ -276,6 +284,67 @@ __global__ void __launch_bounds__(1024) sort_large_kernel(uint64_t* __restrict__
 // ------------------------------------------------------------------------------------------
 // coalesce / rank
 // ------------------------------------------------------------------------------------------
+// Queries with few items are handled by their own lane; a query with many items (a read whose seeds
+// hit thousands of loci) is handled by the whole warp so that one heavy read does not serialise 31
+// idle lanes behind it.  Heavy queries are taken one after the other (ballot loop).
+constexpr uint32_t kLightItems = 16;
+
+// coalesce_seed_sites (src/index.rs:435-487) with the warp: lanes compute bins and windows of 32
+// hits at a time, then every lane replays the (cheap, inherently sequential) merge automaton on the
+// shuffled windows so that control flow stays uniform; lane 0 writes.
+__device__ uint32_t coalesce_warp(const BinsView& bv, const uint64_t* __restrict__ keys, uint32_t n_hits,
+                                  uint32_t min_seeds, uint32_t L, uint32_t k, CandRec* __restrict__ cand,
+                                  uint64_t* __restrict__ rkey) {
+  const unsigned lane = threadIdx.x & 31;
+  uint32_t nc = 0;
+  bool have = false;
+  CandRec cur{0, 0, 0, 0};
+  for (uint32_t t0 = 0; t0 < n_hits; t0 += 32) {
+    uint32_t h = t0 + lane;
+    uint32_t ws = 0, we = 0, b = 0;
+    bool some = false;
+    if (h < n_hits) {
+      uint64_t key = keys[h];
+      uint32_t site = (uint32_t)(key >> 16), q_off = (uint32_t)(key & 0xffff);
+      b = find_bin(bv, site);
+      some = candidate_window(site, q_off, ldg(&bv.start[b]), ldg(&bv.end[b]), L, k, &ws, &we);
+    }
+    uint32_t cnt = n_hits - t0 < 32 ? n_hits - t0 : 32;
+    for (uint32_t i = 0; i < cnt; ++i) {
+      uint32_t ws_i = __shfl_sync(0xffffffffu, ws, i), we_i = __shfl_sync(0xffffffffu, we, i);
+      uint32_t b_i = __shfl_sync(0xffffffffu, b, i);
+      bool some_i = __shfl_sync(0xffffffffu, (int)some, i) != 0;
+      bool merged = false;
+      if (have && some_i && b_i == cur.bin &&
+          ((cur.start <= ws_i && ws_i < cur.end) || (cur.start < we_i && we_i <= cur.end))) {
+        cur.start = ws_i < cur.start ? ws_i : cur.start;
+        cur.end = we_i > cur.end ? we_i : cur.end;
+        cur.num_seeds += 1;
+        merged = true;
+      }
+      if (!merged) {
+        if (have && cur.num_seeds >= min_seeds) {
+          if (lane == 0) {
+            cand[nc] = cur;
+            rkey[nc] = make_rank_key(cur.num_seeds, nc);
+          }
+          ++nc;
+        }
+        have = some_i;
+        if (some_i) cur = CandRec{ws_i, we_i, b_i, 1};
+      }
+    }
+  }
+  if (have && cur.num_seeds >= min_seeds) {
+    if (lane == 0) {
+      cand[nc] = cur;
+      rkey[nc] = make_rank_key(cur.num_seeds, nc);
+    }
+    ++nc;
+  }
+  return nc;
+}
+
 __global__ void __launch_bounds__(128) coalesce_kernel(BinsView bv, ReadsView rv, Params p, uint32_t nq,
                                                        const uint32_t* __restrict__ hit_off,
                                                        const uint32_t* __restrict__ q_nhits,
@@ -285,32 +354,63 @@ __global__ void __launch_bounds__(128) coalesce_kernel(BinsView bv, ReadsView rv
                                                        uint64_t* __restrict__ rank_keys,
                                                        uint32_t* __restrict__ q_ncand) {
   uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
-  if (q >= nq) return;
-  uint32_t nh = q_nhits[q];
-  uint32_t nc = 0;
+  const unsigned lane = threadIdx.x & 31;
+  uint32_t nh = q < nq ? q_nhits[q] : 0;
+  uint32_t nc = 0, L = 0, k = 0, ms = 0, base = 0;
   if (nh) {
-    uint32_t L = query_len(rv, p.ns, q);
-    uint32_t k = edit_budget(L, p.edit_rate);
-    uint32_t ms = min_seeds_of(q_nseeds[q], p.min_seed);
-    uint32_t base = hit_off[q];
-    nc = coalesce_item(bv, hit_keys + base, nh, ms, L, k, cand_sparse + base, rank_keys + base);
+    L = query_len(rv, p.ns, q);
+    k = edit_budget(L, p.edit_rate);
+    ms = min_seeds_of(q_nseeds[q], p.min_seed);
+    base = hit_off[q];
+    if (nh <= kLightItems)
+      nc = coalesce_item(bv, hit_keys + base, nh, ms, L, k, cand_sparse + base, rank_keys + base);
   }
-  q_ncand[q] = nc;
+  unsigned heavy = __ballot_sync(0xffffffffu, nh > kLightItems);
+  while (heavy) {
+    int src = __ffs(heavy) - 1;
+    heavy &= heavy - 1;
+    uint32_t nh_s = __shfl_sync(0xffffffffu, nh, src), base_s = __shfl_sync(0xffffffffu, base, src);
+    uint32_t L_s = __shfl_sync(0xffffffffu, L, src), k_s = __shfl_sync(0xffffffffu, k, src);
+    uint32_t ms_s = __shfl_sync(0xffffffffu, ms, src);
+    uint32_t r = coalesce_warp(bv, hit_keys + base_s, nh_s, ms_s, L_s, k_s, cand_sparse + base_s,
+                               rank_keys + base_s);
+    if ((int)lane == src) nc = r;
+  }
+  if (q < nq) q_ncand[q] = nc;
 }
 
-__global__ void rank_emit_kernel(uint32_t nq, const uint32_t* __restrict__ hit_off,
-                                 const uint32_t* __restrict__ q_ncand, const uint32_t* __restrict__ cand_off,
-                                 const uint64_t* __restrict__ rank_keys,
-                                 const CandRec* __restrict__ cand_sparse, CandRec* __restrict__ cand_dense,
-                                 uint32_t* __restrict__ cand_q) {
+__global__ void __launch_bounds__(256) rank_emit_kernel(uint32_t nq, const uint32_t* __restrict__ hit_off,
+                                                        const uint32_t* __restrict__ q_ncand,
+                                                        const uint32_t* __restrict__ cand_off,
+                                                        const uint64_t* __restrict__ rank_keys,
+                                                        const CandRec* __restrict__ cand_sparse,
+                                                        CandRec* __restrict__ cand_dense,
+                                                        uint32_t* __restrict__ cand_q) {
   uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
-  if (q >= nq) return;
-  uint32_t nc = q_ncand[q];
-  uint32_t src = hit_off[q], dst = cand_off[q];
-  for (uint32_t i = 0; i < nc; ++i) {
-    uint32_t idx = (uint32_t)(rank_keys[src + i] & 0xffffffffu);
-    cand_dense[dst + i] = cand_sparse[src + idx];
-    cand_q[dst + i] = q;
+  const unsigned lane = threadIdx.x & 31;
+  uint32_t nc = q < nq ? q_ncand[q] : 0;
+  uint32_t src = 0, dst = 0;
+  if (nc) {
+    src = hit_off[q];
+    dst = cand_off[q];
+    if (nc <= kLightItems)
+      for (uint32_t i = 0; i < nc; ++i) {
+        uint32_t idx = (uint32_t)(rank_keys[src + i] & 0xffffffffu);
+        cand_dense[dst + i] = cand_sparse[src + idx];
+        cand_q[dst + i] = q;
+      }
+  }
+  unsigned heavy = __ballot_sync(0xffffffffu, nc > kLightItems);
+  while (heavy) {
+    int sl = __ffs(heavy) - 1;
+    heavy &= heavy - 1;
+    uint32_t nc_s = __shfl_sync(0xffffffffu, nc, sl), src_s = __shfl_sync(0xffffffffu, src, sl);
+    uint32_t dst_s = __shfl_sync(0xffffffffu, dst, sl), q_s = __shfl_sync(0xffffffffu, q, sl);
+    for (uint32_t i = lane; i < nc_s; i += 32) {
+      uint32_t idx = (uint32_t)(rank_keys[src_s + i] & 0xffffffffu);
+      cand_dense[dst_s + i] = cand_sparse[src_s + idx];
+      cand_q[dst_s + i] = q_s;
+    }
   }
 }
 
@@ -430,42 +530,23 @@ __global__ void __launch_bounds__(kVerifyThreads) verify_kernel(Jobs jobs, uint3
 #pragma unroll
     for (int c = 0; c < NCLS; ++c) peq[(c * W + w) * kVerifyThreads + threadIdx.x] = m[c];
   }
-  uint64_t Pv[W], Mv[W];
-#pragma unroll
-  for (int w = 0; w < W; ++w) {
-    Pv[w] = ~0ull;
-    Mv[w] = 0;
-  }
-  const uint32_t sbit = (L - 1) & 63;
-  uint32_t score = L, best = L;
-  const uint8_t* t = job.txt;
-  const uint32_t T = job.T;
   // text is read through 8-byte aligned words (the device text has 16 bytes of slack at the end)
-  uint64_t addr = (uint64_t)t;
-  const uint64_t* wp = reinterpret_cast<const uint64_t*>(addr & ~7ull);
-  uint32_t sh = (uint32_t)(addr & 7ull);
-  uint64_t word = 0;
-  for (uint32_t j = 0; j < T; ++j) {
-    uint32_t bi = (j + sh) & 7;
-    if (j == 0 || bi == 0) word = __ldg(wp + ((j + sh) >> 3));
-    uint8_t byte = (uint8_t)(word >> (bi * 8));
-    uint32_t c = text_code(byte);
-    bool none = c >= (uint32_t)NCLS;
-    uint32_t phin = 0, mhin = 0;
-#pragma unroll
-    for (int w = 0; w < W; ++w) {
-      if (w <= last) {
-        uint64_t Eq = none ? 0ull : peq[(c * W + w) * kVerifyThreads + threadIdx.x];
-        uint64_t Ph, Mh;
-        myers_block(Eq, Pv[w], Mv[w], phin, mhin, Ph, Mh);
-        if (w == last) {
-          score += (uint32_t)((Ph >> sbit) & 1);
-          score -= (uint32_t)((Mh >> sbit) & 1);
-        }
-      }
+  struct TextReader {
+    const uint64_t* wp;
+    uint32_t sh;
+    mutable uint64_t word;
+    __device__ __forceinline__ uint32_t operator()(uint32_t j) const {
+      uint32_t bi = (j + sh) & 7;
+      if (j == 0 || bi == 0) word = __ldg(wp + ((j + sh) >> 3));
+      uint32_t c = text_code((uint8_t)(word >> (bi * 8)));
+      return c < (uint32_t)NCLS ? c : 7u;
     }
-    best = score < best ? score : best;
-  }
+  };
+  const uint64_t addr = (uint64_t)job.txt;
+  TextReader text{reinterpret_cast<const uint64_t*>(addr & ~7ull), (uint32_t)(addr & 7ull), 0};
+  const uint32_t T = job.T;
+  auto peq_f = [&](uint32_t c, int w) -> uint64_t { return peq[(c * W + w) * kVerifyThreads + threadIdx.x]; };
+  const uint32_t best = myers_bounded<W>(L, T, job.limit, peq_f, text);
   out[i] = best <= job.limit ? best : kNoEdit;
   if (ctr) atomicAdd(&ctr->window_bytes, (unsigned long long)T);
 }
@@ -501,6 +582,51 @@ constexpr uint32_t kMaxReadLen = 1024;
 // ------------------------------------------------------------------------------------------
 // select / emit
 // ------------------------------------------------------------------------------------------
+// The verification loop control of src/index.rs:375-431 with the warp, for queries with many
+// candidates: 32 candidates per step, the (rare) passing ones are taken in rank order; the
+// "TaxID already matched" test scans the accepted list with all lanes.
+__device__ uint32_t select_warp(const BinsView& bv, const Params& p, const CandRec* __restrict__ cand,
+                                const uint32_t* __restrict__ edits, uint32_t n_cand, uint32_t k,
+                                HitRec* __restrict__ out) {
+  const unsigned lane = threadIdx.x & 31;
+  uint32_t n_out = 0;
+  if (p.max_candidates >= 0 && (uint64_t)n_cand > (uint64_t)p.max_candidates) n_cand = (uint32_t)p.max_candidates;
+  for (uint32_t t0 = 0; t0 < n_cand; t0 += 32) {
+    uint32_t c = t0 + lane;
+    uint32_t e = c < n_cand ? edits[c] : kNoEdit;
+    bool pass = e != kNoEdit && e <= k;
+    CandRec cr{0, 0, 0, 0};
+    uint32_t tax = 0;
+    if (pass) {
+      cr = cand[c];
+      tax = ldg(&bv.tax[cr.bin]);
+    }
+    unsigned m = __ballot_sync(0xffffffffu, pass);
+    while (m) {
+      int i = __ffs(m) - 1;
+      m &= m - 1;
+      uint32_t tax_i = __shfl_sync(0xffffffffu, tax, i);
+      bool seen = false;
+      for (uint32_t j = lane; j < n_out; j += 32) seen |= out[j].tax_id == tax_i;
+      if (__any_sync(0xffffffffu, seen)) continue;
+      if ((int)lane == i) {
+        HitRec h;
+        h.tax_id = tax;
+        h.gi = ldg(&bv.gi[cr.bin]);
+        uint32_t bs = ldg(&bv.start[cr.bin]);
+        h.offset = cr.start >= bs ? cr.start - bs : 0;
+        h.edit = e;
+        h.reserved = 0;
+        out[n_out] = h;
+      }
+      __syncwarp();
+      ++n_out;
+      if (p.max_assignments >= 0 && (uint64_t)n_out >= (uint64_t)p.max_assignments) return n_out;
+    }
+  }
+  return n_out;
+}
+
 __global__ void __launch_bounds__(128) select_kernel(BinsView bv, ReadsView rv, Params p, uint32_t nq,
                                                      const uint32_t* __restrict__ cand_off,
                                                      const CandRec* __restrict__ cand_dense,
@@ -508,30 +634,55 @@ __global__ void __launch_bounds__(128) select_kernel(BinsView bv, ReadsView rv, 
                                                      HitRec* __restrict__ hit_tmp,
                                                      uint32_t* __restrict__ q_nout) {
   uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
-  if (q >= nq) return;
-  uint32_t b = cand_off[q], e = cand_off[q + 1];
-  uint32_t n = 0;
-  if (e > b) {
-    uint32_t L = query_len(rv, p.ns, q);
-    uint32_t k = edit_budget(L, p.edit_rate);
-    n = select_item(bv, p, cand_dense + b, cand_edit + b, e - b, k, hit_tmp + b);
+  const unsigned lane = threadIdx.x & 31;
+  uint32_t b = 0, nc = 0, k = 0, n = 0;
+  if (q < nq) {
+    b = cand_off[q];
+    nc = cand_off[q + 1] - b;
   }
-  q_nout[q] = n;
+  if (nc) {
+    uint32_t L = query_len(rv, p.ns, q);
+    k = edit_budget(L, p.edit_rate);
+    if (nc <= kLightItems) n = select_item(bv, p, cand_dense + b, cand_edit + b, nc, k, hit_tmp + b);
+  }
+  unsigned heavy = __ballot_sync(0xffffffffu, nc > kLightItems);
+  while (heavy) {
+    int sl = __ffs(heavy) - 1;
+    heavy &= heavy - 1;
+    uint32_t nc_s = __shfl_sync(0xffffffffu, nc, sl), b_s = __shfl_sync(0xffffffffu, b, sl);
+    uint32_t k_s = __shfl_sync(0xffffffffu, k, sl);
+    uint32_t r = select_warp(bv, p, cand_dense + b_s, cand_edit + b_s, nc_s, k_s, hit_tmp + b_s);
+    if ((int)lane == sl) n = r;
+  }
+  if (q < nq) q_nout[q] = n;
 }
 
-__global__ void gather_hits_kernel(uint32_t nq, uint32_t ns, const uint32_t* __restrict__ cand_off,
-                                   const uint32_t* __restrict__ out_off, const HitRec* __restrict__ hit_tmp,
-                                   HitRec* __restrict__ out_hits, uint64_t out_base,
-                                   uint64_t* __restrict__ out_hit_off /*indexed by read within batch*/,
-                                   uint64_t read_base) {
+__global__ void __launch_bounds__(256) gather_hits_kernel(uint32_t nq, uint32_t ns,
+                                                          const uint32_t* __restrict__ cand_off,
+                                                          const uint32_t* __restrict__ out_off,
+                                                          const HitRec* __restrict__ hit_tmp,
+                                                          HitRec* __restrict__ out_hits, uint64_t out_base,
+                                                          uint64_t* __restrict__ out_hit_off, uint64_t read_base) {
   uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
-  if (q > nq) return;
-  if (q % ns == 0) out_hit_off[read_base + q / ns] = out_base + out_off[q];  // also q == nq: the end
-  if (q == nq) return;
-  uint32_t n = out_off[q + 1] - out_off[q];
-  const HitRec* src = hit_tmp + cand_off[q];
-  HitRec* dst = out_hits + out_base + out_off[q];
-  for (uint32_t i = 0; i < n; ++i) dst[i] = src[i];
+  const unsigned lane = threadIdx.x & 31;
+  if (q <= nq && q % ns == 0) out_hit_off[read_base + q / ns] = out_base + out_off[q];  // q == nq: the end
+  uint32_t n = 0, src = 0;
+  uint64_t dst = 0;
+  if (q < nq) {
+    n = out_off[q + 1] - out_off[q];
+    src = cand_off[q];
+    dst = out_base + out_off[q];
+    if (n <= kLightItems)
+      for (uint32_t i = 0; i < n; ++i) out_hits[dst + i] = hit_tmp[src + i];
+  }
+  unsigned heavy = __ballot_sync(0xffffffffu, n > kLightItems);
+  while (heavy) {
+    int sl = __ffs(heavy) - 1;
+    heavy &= heavy - 1;
+    uint32_t n_s = __shfl_sync(0xffffffffu, n, sl), src_s = __shfl_sync(0xffffffffu, src, sl);
+    uint64_t dst_s = __shfl_sync(0xffffffffu, dst, sl);
+    for (uint32_t i = lane; i < n_s; i += 32) out_hits[dst_s + i] = hit_tmp[src_s + i];
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -666,10 +817,10 @@ static int run_sub_batch(mtsvgpu_index* h, const Params& p, const uint8_t* d_seq
   uint32_t* slot_off = ws.slot_off.as<uint32_t>();
   MTSV_LAUNCH(count_slots_kernel, qgrid, 256, 0, st, rv, p, nq, slot_off, d_ctr);
   MTSV_TRY(exclusive_scan_u32(slot_off, slot_off, nq, ws.scan_tmp, (uint64_t*)&d_ctr->total_slots, st));
-  MTSV_LAUNCH(expand_slots_kernel, qgrid, 256, 0, st, slot_off, nq, ws.slot_q.as<uint32_t>());
   clk.end();
   MTSV_CUDA_TRY(cudaMemcpyAsync(&hc, d_ctr, sizeof hc, cudaMemcpyDeviceToHost, st));
   MTSV_CUDA_TRY(cudaStreamSynchronize(st));
+  if (hc.bad_offsets) return set_error(MTSVGPU_EINVAL, "seq_off is not monotone");
   if (hc.max_len > kMaxReadLen)
     return set_error(MTSVGPU_ELIMIT, "a read of %u bases exceeds this build's limit of %u", hc.max_len,
                      kMaxReadLen);
@@ -678,6 +829,10 @@ static int run_sub_batch(mtsvgpu_index* h, const Params& p, const uint8_t* d_seq
                      (unsigned long long)slot_bound);
   const uint32_t n_slots = (uint32_t)hc.total_slots;
   h->stats.n_seed_slots += n_slots;
+  // (only now that the slot count is known to fit the buffers)
+  clk.begin(ST_PREP);
+  MTSV_LAUNCH(expand_slots_kernel, qgrid, 256, 0, st, slot_off, nq, ws.slot_q.as<uint32_t>());
+  clk.end();
 
   // ---- seed search ----
   clk.begin(ST_SEARCH);
@@ -792,25 +947,39 @@ static int run_sub_batch(mtsvgpu_index* h, const Params& p, const uint8_t* d_seq
   return 0;
 }
 
+// seq_off accessor: host copy when the caller has one, otherwise single 8-byte D2H reads
+struct OffsetSource {
+  const uint64_t* host;
+  const uint64_t* dev;
+  cudaStream_t st;
+  int get(uint64_t i, uint64_t* v) const {
+    if (host) {
+      *v = host[i];
+      return 0;
+    }
+    MTSV_CUDA_TRY(cudaMemcpyAsync(v, dev + i, 8, cudaMemcpyDeviceToHost, st));
+    MTSV_CUDA_TRY(cudaStreamSynchronize(st));
+    return 0;
+  }
+};
+
 static int run_range(mtsvgpu_index* h, const Params& p, const uint8_t* d_seqs, const uint64_t* d_seq_off,
-                     const uint64_t* h_seq_off, uint64_t read0, uint64_t n_reads, uint64_t batch_read0,
-                     uint64_t* out_total) {
+                     const OffsetSource& offs, uint64_t read0, uint64_t n_reads, uint64_t off_lo,
+                     uint64_t off_hi, uint64_t* out_total) {
   // bound on seed slots from the byte count: slots(L) <= L/G + 1 per strand
-  uint64_t bytes = h_seq_off[read0 + n_reads - batch_read0] - h_seq_off[read0 - batch_read0];
+  if (off_hi < off_lo) return set_error(MTSVGPU_EINVAL, "seq_off is not monotone");
+  uint64_t bytes = off_hi - off_lo;
   uint64_t slot_bound = (bytes / p.G + n_reads) * p.ns + 1;
-  if (slot_bound > 0xfffffff0ull || n_reads * p.ns > 0x7ffffff0ull) {
-    if (n_reads == 1) return set_error(MTSVGPU_ELIMIT, "read too long");
-    uint64_t half = n_reads / 2;
-    MTSV_TRY(run_range(h, p, d_seqs, d_seq_off, h_seq_off, read0, half, batch_read0, out_total));
-    return run_range(h, p, d_seqs, d_seq_off, h_seq_off, read0 + half, n_reads - half, batch_read0, out_total);
+  bool split = slot_bound > 0xfffffff0ull || n_reads * p.ns > 0x7ffffff0ull;
+  if (!split) {
+    int rc = run_sub_batch(h, p, d_seqs, d_seq_off, read0, (uint32_t)n_reads, slot_bound, 0, out_total);
+    if (rc != 1) return rc;
   }
-  int rc = run_sub_batch(h, p, d_seqs, d_seq_off, read0, (uint32_t)n_reads, slot_bound, batch_read0, out_total);
-  if (rc == 1) {
-    uint64_t half = n_reads / 2;
-    MTSV_TRY(run_range(h, p, d_seqs, d_seq_off, h_seq_off, read0, half, batch_read0, out_total));
-    return run_range(h, p, d_seqs, d_seq_off, h_seq_off, read0 + half, n_reads - half, batch_read0, out_total);
-  }
-  return rc;
+  if (n_reads == 1) return set_error(MTSVGPU_ELIMIT, "a single read exceeds the device batch limits");
+  uint64_t half = n_reads / 2, off_mid = 0;
+  MTSV_TRY(offs.get(read0 + half, &off_mid));
+  MTSV_TRY(run_range(h, p, d_seqs, d_seq_off, offs, read0, half, off_lo, off_mid, out_total));
+  return run_range(h, p, d_seqs, d_seq_off, offs, read0 + half, n_reads - half, off_mid, off_hi, out_total);
 }
 
 int bin_batch_device(mtsvgpu_index* h, const uint8_t* d_seqs, const uint64_t* d_seq_off, uint64_t n_reads,
@@ -825,25 +994,30 @@ int bin_batch_device(mtsvgpu_index* h, const uint8_t* d_seqs, const uint64_t* d_
   memset(&h->stats, 0, sizeof h->stats);
   BatchWorkspace& ws = h->ws;
   MTSV_TRY(ws.out_hit_off.reserve((n_reads + 1) * 8));
-  std::vector<uint64_t> off_copy;
-  const uint64_t* h_off = h_seq_off_or_null;
-  if (!h_off) {  // device-resident caller: fetch the offsets once (8 B/read)
-    off_copy.resize(n_reads + 1);
-    MTSV_CUDA_TRY(cudaMemcpyAsync(off_copy.data(), d_seq_off, (n_reads + 1) * 8, cudaMemcpyDeviceToHost, st));
-    MTSV_CUDA_TRY(cudaStreamSynchronize(st));
-    h_off = off_copy.data();
-  }
-  for (uint64_t i = 0; i < n_reads; ++i)
-    if (h_off[i + 1] < h_off[i]) return set_error(MTSVGPU_EINVAL, "seq_off is not monotone at read %llu", (unsigned long long)i);
   uint64_t total = 0;
   const uint64_t step = h->opts.batch_reads ? h->opts.batch_reads : (1u << 20);
   if (n_reads == 0) {
     MTSV_CUDA_TRY(cudaMemsetAsync(ws.out_hit_off.p, 0, 8, st));
     MTSV_TRY(grow_preserve(ws.out_hits, 0, sizeof(HitRec), st));
   }
-  for (uint64_t r0 = 0; r0 < n_reads; r0 += step) {
-    uint64_t nr = std::min(step, n_reads - r0);
-    MTSV_TRY(run_range(h, p, d_seqs, d_seq_off, h_off, r0, nr, 0, &total));
+  // sub-batch boundaries of seq_off: one strided gather instead of copying 8 B per read
+  const uint64_t n_sub = (n_reads + step - 1) / step;
+  std::vector<uint64_t> bounds(n_sub + 1, 0);
+  OffsetSource offs{h_seq_off_or_null, d_seq_off, st};
+  if (n_reads) {
+    if (h_seq_off_or_null) {
+      for (uint64_t i = 0; i < n_sub; ++i) bounds[i] = h_seq_off_or_null[i * step];
+      bounds[n_sub] = h_seq_off_or_null[n_reads];
+    } else {
+      MTSV_CUDA_TRY(cudaMemcpy2DAsync(bounds.data(), 8, d_seq_off, step * 8, 8, n_sub, cudaMemcpyDeviceToHost, st));
+      MTSV_CUDA_TRY(cudaMemcpyAsync(&bounds[n_sub], d_seq_off + n_reads, 8, cudaMemcpyDeviceToHost, st));
+      MTSV_CUDA_TRY(cudaStreamSynchronize(st));
+    }
+  }
+  for (uint64_t i = 0; i < n_sub; ++i) {
+    uint64_t r0 = i * step, nr = std::min(step, n_reads - r0);
+    if (h->sub_batch_hook) MTSV_TRY(h->sub_batch_hook(h, i));
+    MTSV_TRY(run_range(h, p, d_seqs, d_seq_off, offs, r0, nr, bounds[i], bounds[i + 1], &total));
   }
   MTSV_CUDA_TRY(cudaStreamSynchronize(st));
   if (d_hits) *d_hits = reinterpret_cast<const mtsvgpu_hit*>(ws.out_hits.p);

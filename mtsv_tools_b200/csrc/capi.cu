@@ -2,6 +2,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
+
 #include "ctx.h"
 
 namespace mtsv {
@@ -75,7 +77,7 @@ static int ensure_pinned(void** p, size_t* cap, size_t bytes) {
   if (*p) cudaFreeHost(*p);
   *p = nullptr;
   *cap = 0;
-  size_t want = bytes + bytes / 4 + 4096;
+  size_t want = bytes + bytes / 2 + 4096;
   cudaError_t e = cudaMallocHost(p, want);
   if (e != cudaSuccess) {
     (void)cudaGetLastError();
@@ -86,18 +88,28 @@ static int ensure_pinned(void** p, size_t* cap, size_t bytes) {
   return 0;
 }
 
-int mtsvgpu_bin_batch(mtsvgpu_index* ix, const uint8_t* seqs, const uint64_t* seq_off, uint64_t n_reads,
-                      const mtsvgpu_params* params, mtsvgpu_hit** hits, uint64_t** hit_off) {
+static int wait_for_sub_batch_input(mtsvgpu_index* ix, uint64_t i) {
+  if (i < ix->in_events.size()) MTSV_CUDA_TRY(cudaStreamWaitEvent(ix->stream, ix->in_events[i], 0));
+  return 0;
+}
+
+// Host-buffer batch: the reads are uploaded sub-batch by sub-batch on a copy stream while earlier
+// sub-batches compute (pass page-locked buffers to get the overlap; pageable ones work, serially).
+// pinned_result: 0 = results in malloc'ed memory (mtsvgpu_free), 1 = in the handle's page-locked
+// buffers, valid until the next batch call on this handle.
+static int bin_batch_host(mtsvgpu_index* ix, const uint8_t* seqs, const uint64_t* seq_off, uint64_t n_reads,
+                          const mtsvgpu_params* params, int pinned_result, mtsvgpu_hit** hits,
+                          uint64_t** hit_off, uint64_t* n_hits_out) {
   if (!ix || !seq_off || !hits || !hit_off) return set_error(MTSVGPU_EINVAL, "null argument");
   *hits = nullptr;
   *hit_off = nullptr;
   MTSV_CUDA_TRY(cudaSetDevice(ix->ix.device));
-  cudaStream_t st = ix->stream;
+  cudaStream_t st = ix->stream, cin = ix->copy_in_stream;
   const uint64_t base = seq_off[0];
+  if (seq_off[n_reads] < base) return set_error(MTSVGPU_EINVAL, "seq_off is not monotone");
   const uint64_t bytes = seq_off[n_reads] - base;
   if (bytes && !seqs) return set_error(MTSVGPU_EINVAL, "seqs is NULL");
   BatchWorkspace& ws = ix->ws;
-  // ---- H2D: read bytes and offsets (rebased to 0) ----
   MTSV_TRY(ws.d_seqs.reserve(bytes + 16));
   MTSV_TRY(ws.d_seq_off.reserve((n_reads + 1) * 8));
   std::vector<uint64_t> rebased;
@@ -107,36 +119,86 @@ int mtsvgpu_bin_batch(mtsvgpu_index* ix, const uint8_t* seqs, const uint64_t* se
     for (uint64_t i = 0; i <= n_reads; ++i) rebased[i] = seq_off[i] - base;
     offs = rebased.data();
   }
-  if (bytes) MTSV_CUDA_TRY(cudaMemcpyAsync(ws.d_seqs.p, seqs + base, bytes, cudaMemcpyHostToDevice, st));
-  MTSV_CUDA_TRY(cudaMemcpyAsync(ws.d_seq_off.p, offs, (n_reads + 1) * 8, cudaMemcpyHostToDevice, st));
-  // ---- compute ----
+  // ---- H2D, pipelined per device sub-batch ----
+  const uint64_t step = ix->opts.batch_reads ? ix->opts.batch_reads : (1u << 20);
+  const uint64_t n_sub = (n_reads + step - 1) / step;
+  while (ix->in_events.size() < n_sub) {
+    cudaEvent_t e;
+    MTSV_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    ix->in_events.push_back(e);
+  }
+  MTSV_CUDA_TRY(cudaMemcpyAsync(ws.d_seq_off.p, offs, (n_reads + 1) * 8, cudaMemcpyHostToDevice, cin));
+  for (uint64_t i = 0; i < n_sub; ++i) {
+    uint64_t r0 = i * step, r1 = std::min(n_reads, r0 + step);
+    if (r1 < r0 || offs[r1] < offs[r0]) return set_error(MTSVGPU_EINVAL, "seq_off is not monotone");
+    uint64_t b0 = offs[r0], nb = offs[r1] - b0;
+    if (b0 + nb > bytes) return set_error(MTSVGPU_EINVAL, "seq_off exceeds the reads buffer");
+    if (nb)
+      MTSV_CUDA_TRY(cudaMemcpyAsync(ws.d_seqs.as<uint8_t>() + b0, seqs + base + b0, nb, cudaMemcpyHostToDevice, cin));
+    MTSV_CUDA_TRY(cudaEventRecord(ix->in_events[i], cin));
+  }
+  // ---- compute (each sub-batch waits for its slice) ----
   const mtsvgpu_hit* d_hits = nullptr;
   const uint64_t* d_hit_off = nullptr;
   uint64_t n_hits = 0;
-  MTSV_TRY(bin_batch_device(ix, ws.d_seqs.as<uint8_t>(), ws.d_seq_off.as<uint64_t>(), n_reads, offs, params,
-                            &d_hits, &d_hit_off, &n_hits));
+  ix->sub_batch_hook = wait_for_sub_batch_input;
+  int rc = bin_batch_device(ix, ws.d_seqs.as<uint8_t>(), ws.d_seq_off.as<uint64_t>(), n_reads, offs, params,
+                            &d_hits, &d_hit_off, &n_hits);
+  ix->sub_batch_hook = nullptr;
+  if (rc != 0) {
+    cudaStreamSynchronize(cin);
+    return rc;
+  }
+  MTSV_CUDA_TRY(cudaStreamSynchronize(cin));
   // ---- D2H ----
-  mtsvgpu_hit* h_hits = (mtsvgpu_hit*)malloc((n_hits ? n_hits : 1) * sizeof(mtsvgpu_hit));
-  uint64_t* h_off = (uint64_t*)malloc((n_reads + 1) * sizeof(uint64_t));
-  if (!h_hits || !h_off) {
-    free(h_hits);
-    free(h_off);
-    return set_error(MTSVGPU_ENOMEM, "host allocation of the result failed");
+  mtsvgpu_hit* h_hits = nullptr;
+  uint64_t* h_off = nullptr;
+  const size_t hb = (n_hits ? n_hits : 1) * sizeof(mtsvgpu_hit), ob = (n_reads + 1) * sizeof(uint64_t);
+  if (pinned_result) {
+    MTSV_TRY(ensure_pinned(&ix->pin_hits, &ix->pin_hits_cap, hb));
+    MTSV_TRY(ensure_pinned(&ix->pin_off, &ix->pin_off_cap, ob));
+    h_hits = (mtsvgpu_hit*)ix->pin_hits;
+    h_off = (uint64_t*)ix->pin_off;
+  } else {
+    h_hits = (mtsvgpu_hit*)malloc(hb);
+    h_off = (uint64_t*)malloc(ob);
+    if (!h_hits || !h_off) {
+      free(h_hits);
+      free(h_off);
+      return set_error(MTSVGPU_ENOMEM, "host allocation of the result failed");
+    }
   }
   cudaError_t e = cudaSuccess;
   if (n_hits) e = cudaMemcpyAsync(h_hits, d_hits, n_hits * sizeof(mtsvgpu_hit), cudaMemcpyDeviceToHost, st);
-  if (e == cudaSuccess)
-    e = cudaMemcpyAsync(h_off, d_hit_off, (n_reads + 1) * 8, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(h_off, d_hit_off, ob, cudaMemcpyDeviceToHost, st);
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
   if (e != cudaSuccess) {
-    free(h_hits);
-    free(h_off);
+    if (!pinned_result) {
+      free(h_hits);
+      free(h_off);
+    }
     return set_error(MTSVGPU_ECUDA, "result copy failed: %s", cudaGetErrorString(e));
   }
   *hits = h_hits;
   *hit_off = h_off;
-  (void)ensure_pinned;
+  if (n_hits_out) *n_hits_out = n_hits;
   return 0;
+}
+
+int mtsvgpu_bin_batch(mtsvgpu_index* ix, const uint8_t* seqs, const uint64_t* seq_off, uint64_t n_reads,
+                      const mtsvgpu_params* params, mtsvgpu_hit** hits, uint64_t** hit_off) {
+  return bin_batch_host(ix, seqs, seq_off, n_reads, params, 0, hits, hit_off, nullptr);
+}
+
+int mtsvgpu_bin_batch_pinned(mtsvgpu_index* ix, const uint8_t* seqs, const uint64_t* seq_off, uint64_t n_reads,
+                             const mtsvgpu_params* params, const mtsvgpu_hit** hits,
+                             const uint64_t** hit_off, uint64_t* n_hits) {
+  mtsvgpu_hit* h = nullptr;
+  uint64_t* o = nullptr;
+  int rc = bin_batch_host(ix, seqs, seq_off, n_reads, params, 1, &h, &o, n_hits);
+  if (hits) *hits = h;
+  if (hit_off) *hit_off = o;
+  return rc;
 }
 
 int mtsvgpu_backward_search(mtsvgpu_index* ix, const uint8_t* pats, uint32_t pat_len, uint64_t n_pats,

@@ -77,7 +77,7 @@ MTSV_HD uint32_t comp_code(uint32_t c) { return c < 4 ? 3u - c : c; }
 // u64 checkpoint arrays (Occ::get) — same counts, different bytes.
 // ---------------------------------------------------------------------------------------------
 struct __attribute__((aligned(32))) FmBlock {
-  uint16_t rel[4];
+  uint64_t rel;  // four u16 relative counts: A | C << 16 | G << 32 | T << 48
   uint64_t exc;
   uint64_t lo;
   uint64_t hi;
@@ -95,7 +95,7 @@ struct FmView {
   const FmBlock* blocks;      // n/64 + 1
   const SuperCounts* super;   // per 512 blocks
   const uint32_t* n_before;   // per block: number of N in bwt[0 .. 64*blk)
-  uint32_t C[5];              // `less` for A,C,G,T,N (byte order $ < A < C < G < N < T)
+  const uint32_t* C;          // device array[5]: `less` for A,C,G,T,N (byte order $ < A < C < G < N < T)
   uint32_t n;                 // rows (= text length incl. '$')
   uint32_t dollar_row;        // the single row whose BWT symbol is '$'
 };
@@ -105,10 +105,7 @@ MTSV_HD FmBlock load_block(const FmBlock* p) {
   FmBlock b;
   const uint4* q = reinterpret_cast<const uint4*>(p);
   uint4 v0 = __ldg(q), v1 = __ldg(q + 1);
-  b.rel[0] = (uint16_t)(v0.x & 0xffff);
-  b.rel[1] = (uint16_t)(v0.x >> 16);
-  b.rel[2] = (uint16_t)(v0.y & 0xffff);
-  b.rel[3] = (uint16_t)(v0.y >> 16);
+  b.rel = (uint64_t)v0.x | ((uint64_t)v0.y << 32);
   b.exc = (uint64_t)v0.z | ((uint64_t)v0.w << 32);
   b.lo = (uint64_t)v1.x | ((uint64_t)v1.y << 32);
   b.hi = (uint64_t)v1.z | ((uint64_t)v1.w << 32);
@@ -121,7 +118,7 @@ MTSV_HD FmBlock load_block(const FmBlock* p) {
 // occurrences of symbol a (0..3) among the first j (0..63) rows of the block, plus its rel count
 MTSV_HD uint32_t block_occ(const FmBlock& b, uint32_t a, uint32_t j) {
   uint64_t m = ~b.exc & ((a & 1) ? b.lo : ~b.lo) & ((a & 2) ? b.hi : ~b.hi);
-  return (uint32_t)b.rel[a] + (uint32_t)popc64(m & ((1ull << j) - 1));
+  return (uint32_t)((b.rel >> (16 * a)) & 0xffff) + (uint32_t)popc64(m & ((1ull << j) - 1));
 }
 
 // occ(a, i) = number of `a` in bwt[0 .. i)   (== bio Occ::get(bwt, i-1, a) for i > 0)
@@ -164,12 +161,14 @@ MTSV_HD uint32_t fm_step(const FmView& fm, uint32_t a, uint32_t& l, uint32_t& u)
       ou = ldg(&fm.super[bu >> 9].c[a]) + block_occ(b2, a, u & 63);
       sectors = 2;
     }
-    l = fm.C[a] + ol;
-    u = fm.C[a] + ou;
+    uint32_t ca = ldg(&fm.C[a]);
+    l = ca + ol;
+    u = ca + ou;
   } else {
     uint32_t ol = fm_occ(fm, SYM_N, l), ou = fm_occ(fm, SYM_N, u);
-    l = fm.C[SYM_N] + ol;
-    u = fm.C[SYM_N] + ou;
+    uint32_t cn = ldg(&fm.C[SYM_N]);
+    l = cn + ol;
+    u = cn + ou;
     sectors = 4;  // two FmBlock sectors + two n_before sectors
   }
   return sectors;
@@ -178,11 +177,11 @@ MTSV_HD uint32_t fm_step(const FmView& fm, uint32_t a, uint32_t& l, uint32_t& u)
 // LF mapping used by locate — bio SampledSuffixArray::get: pos = less[c] + occ(pos-1, c)
 MTSV_HD uint32_t fm_lf(const FmView& fm, uint32_t c, const FmBlock& b, uint32_t row) {
   uint32_t blk = row >> 6, j = row & 63;
-  if (c < 4) return fm.C[c] + ldg(&fm.super[blk >> 9].c[c]) + block_occ(b, c, j);
+  if (c < 4) return ldg(&fm.C[c]) + ldg(&fm.super[blk >> 9].c[c]) + block_occ(b, c, j);
   uint32_t cnt = ldg(&fm.n_before[blk]) + (uint32_t)popc64(b.exc & ((1ull << j) - 1));
   uint32_t base = blk << 6;
   if (fm.dollar_row >= base && fm.dollar_row < row) cnt -= 1;
-  return fm.C[SYM_N] + cnt;
+  return ldg(&fm.C[SYM_N]) + cnt;
 }
 
 // Suffix array as kept on the device: rows 0, s', 2s', ... (s' = 1 means the full array).
@@ -483,38 +482,92 @@ MTSV_HD void myers_block(uint64_t Eq, uint64_t& Pv, uint64_t& Mv, uint32_t& phin
   mhin = mho;
 }
 
-// Reference implementation of the multi-word recurrence with the pattern masks supplied by a
-// functor peq(sym, word) -> u64 and the text by text(j) -> class (0..4 match classes, >4 = none).
-// Used directly by the CPU emulation and by the generic device path; the tuned kernel in
-// binner.cu specialises the same recurrence.
+// Bounded semi-global edit distance over W 64-row blocks: returns min_j D[L][j] when that is <= k and
+// some value > k otherwise (only values <= k are observable at src/index.rs:410).  Pattern masks come
+// from peq(class, word) -> u64, the text from text(j) -> class (0..4 match classes, > 4 = matches nothing).
+//
+// Three exact prunings (transformation 6), all of the form "cells that cannot lie on a
+// complete alignment of cost <= k are not computed and are treated as +infinity (over-estimated)":
+//   * Ukkonen cut-off, per 64-row block as in Myers' block algorithm: blocks below `last` hold only
+//     values > k; block last+1 is (re)activated in the column where the bottom cell of block `last`
+//     is <= k in this or the previous column, initialised with vertical deltas +1; a block whose
+//     bottom value is >= k + rows holds only values > k and is dropped.
+//   * static band: rows above j - (T - L) - k at column j cannot reach row L by column T; whole blocks
+//     above it are dropped, the block below receives a horizontal delta of +1 (an over-estimate).
+//   * early exit when the active rows can no longer reach row L within the remaining columns.
+// Used by the verify kernel (binner.cu) and, compiled with g++, by tests/emul/.
 template <int W, typename PeqF, typename TextF>
-MTSV_HD uint32_t myers_semiglobal(uint32_t L, uint32_t T, PeqF peq, TextF text) {
+MTSV_HD uint32_t myers_bounded(uint32_t L, uint32_t T, uint32_t k, PeqF peq, TextF text) {
   if (L == 0) return 0;
+  if (k > L) k = L;  // D[L][0] = L bounds the answer; also keeps k + rows small
   uint64_t Pv[W], Mv[W];
+  uint32_t bs[W];  // bs[w] = D[bottom row of block w][current column]
+  const int nb = (int)((L - 1) >> 6);
+  const uint32_t sbit = (L - 1) & 63;
 #pragma unroll
   for (int w = 0; w < W; ++w) {
     Pv[w] = ~0ull;
     Mv[w] = 0;
+    uint32_t bottom = (uint32_t)(w + 1) * 64;
+    bs[w] = bottom < L ? bottom : L;
   }
-  const int last = (int)((L - 1) >> 6);
-  const uint32_t sbit = (L - 1) & 63;
-  uint32_t score = L, best = L;
+  // column 0: D[i][0] = i, so block w (rows 64w+1..) is active iff 64w + 1 <= k; block 0 always
+  int last = k ? (int)((k - 1) >> 6) : 0;
+  if (last > nb) last = nb;
+  int first = 0;
+  uint32_t best = last == nb ? L : k + 1;
+  const uint32_t slack = T + k;  // a row i at column j is useful only if i + slack >= L + j
   for (uint32_t j = 0; j < T; ++j) {
-    uint32_t c = text(j);
-    uint32_t phin = 0, mhin = 0;
+    {
+      uint32_t reach = (uint32_t)(last + 1) * 64;  // bottom row of the active region
+      if (reach < L && (L - reach) > (T - j) + k) break;
+    }
+    // blocks entirely above the band at column j+1: 64(w+1) + slack < L + j + 1.  The bottom-most
+    // active block is never dropped this way: the activation of the block below needs its bottom cell.
+#pragma unroll
+    for (int w = 0; w < W - 1; ++w)
+      if (w == first && w < last && (uint32_t)(w + 1) * 64 + slack < L + j + 1) first = w + 1;
+    const uint32_t c = text(j);
+    uint32_t phin = first > 0 ? 1u : 0u, mhin = 0;
+    uint32_t prev_old = 0, prev_new = 0, bottom_score = k + 1;
+    bool prev_valid = false;
 #pragma unroll
     for (int w = 0; w < W; ++w) {
-      if (w <= last) {
-        uint64_t Eq = c <= 4 ? peq(c, w) : 0ull;
-        uint64_t Ph, Mh;
-        myers_block(Eq, Pv[w], Mv[w], phin, mhin, Ph, Mh);
-        if (w == last) {
-          score += (uint32_t)((Ph >> sbit) & 1);
-          score -= (uint32_t)((Mh >> sbit) & 1);
+      if (w <= nb) {
+        bool active = w >= first && w <= last;
+        if (!active && w == last + 1 && prev_valid && (prev_old <= k || prev_new <= k)) {
+          uint32_t rows = w == nb ? L - (uint32_t)w * 64 : 64u;
+          Pv[w] = ~0ull;
+          Mv[w] = 0;
+          bs[w] = prev_old + rows;
+          last = w;
+          active = true;
+        }
+        if (active) {
+          uint64_t Eq = c <= 4 ? peq(c, w) : 0ull;
+          uint64_t Ph, Mh;
+          prev_old = bs[w];
+          myers_block(Eq, Pv[w], Mv[w], phin, mhin, Ph, Mh);
+          const uint32_t bit = w == nb ? sbit : 63u;
+          bs[w] += (uint32_t)((Ph >> bit) & 1);
+          bs[w] -= (uint32_t)((Mh >> bit) & 1);
+          prev_new = bs[w];
+          prev_valid = true;
+          if (w == nb) bottom_score = bs[w];
+        } else {
+          prev_valid = false;
         }
       }
     }
-    best = score < best ? score : best;
+    // drop blocks that hold only values > k (keep the top-most active one)
+#pragma unroll
+    for (int w = W - 1; w >= 1; --w) {
+      if (w <= nb && w == last && w > first) {
+        uint32_t rows = w == nb ? L - (uint32_t)w * 64 : 64u;
+        if (bs[w] >= k + rows) last = w - 1;
+      }
+    }
+    if (bottom_score < best) best = bottom_score;
   }
   return best;
 }
@@ -535,13 +588,15 @@ MTSV_HD uint32_t select_item(const BinsView& bv, const Params& p, const CandRec*
   uint32_t n_out = 0;
   for (uint32_t c = 0; c < n_cand; ++c) {
     if (p.max_candidates >= 0 && (uint64_t)c >= (uint64_t)p.max_candidates) break;  // :385-389
+    // (the edit test comes first here: a candidate that fails :406/:410 never changes the loop's
+    //  state, so testing it before the "TaxID already matched" scan of :393-396 gives the same hits)
+    uint32_t e = edits[c];
+    if (e == kNoEdit || e > k) continue;  // :406,:410
     uint32_t bin = cand[c].bin;
     uint32_t tax = ldg(&bv.tax[bin]);
     bool seen = false;
     for (uint32_t m = 0; m < n_out; ++m) seen |= out[m].tax_id == tax;  // :393-396
     if (seen) continue;
-    uint32_t e = edits[c];
-    if (e == kNoEdit || e > k) continue;  // :406,:410
     HitRec h;
     h.tax_id = tax;
     h.gi = ldg(&bv.gi[bin]);

@@ -60,6 +60,7 @@ struct DeviceIndex {
   uint32_t* n_before = nullptr;
   uint64_t n_blocks = 0, n_super = 0;
   uint32_t C[5] = {0, 0, 0, 0, 0};
+  uint32_t* d_C = nullptr;  // device copy of C
   uint32_t dollar_row = 0;
   // suffix array at the device rate
   uint32_t* sa = nullptr;
@@ -81,7 +82,7 @@ struct DeviceIndex {
     v.blocks = blocks;
     v.super = super;
     v.n_before = n_before;
-    for (int i = 0; i < 5; ++i) v.C[i] = C[i];
+    v.C = d_C;
     v.n = (uint32_t)n;
     v.dollar_row = dollar_row;
     return v;
@@ -136,11 +137,14 @@ struct mtsvgpu_index {
   bool profiling = false;
   mtsv::BatchWorkspace ws;
   mtsvgpu_batch_stats stats{};
-  // pinned staging for the host API
-  void* pin_in = nullptr;
-  size_t pin_in_cap = 0;
-  void* pin_out = nullptr;
-  size_t pin_out_cap = 0;
+  // host API: copy streams, per-sub-batch "input landed" events, pinned result buffers
+  cudaStream_t copy_in_stream = nullptr;
+  std::vector<cudaEvent_t> in_events;
+  int (*sub_batch_hook)(mtsvgpu_index*, uint64_t) = nullptr;  // called before each sub-batch
+  void* pin_hits = nullptr;
+  size_t pin_hits_cap = 0;
+  void* pin_off = nullptr;
+  size_t pin_off_cap = 0;
   // event pool for profiling
   std::vector<cudaEvent_t> ev_pool;
   std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> ev_used;

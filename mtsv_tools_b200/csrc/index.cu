@@ -106,18 +106,8 @@ __global__ void __launch_bounds__(kBlocksPerSuper) fm_pack_kernel(
   }
   uint64_t ex = base + inc - packed, nex = nbase + ninc - nn;
   if (blk < n_blocks) {
-    FmBlock b;
-    b.rel[0] = (uint16_t)(ex & 0xffff);
-    b.rel[1] = (uint16_t)((ex >> 16) & 0xffff);
-    b.rel[2] = (uint16_t)((ex >> 32) & 0xffff);
-    b.rel[3] = (uint16_t)((ex >> 48) & 0xffff);
-    b.exc = exc;
-    b.lo = lo;
-    b.hi = hi;
     uint4* dst = reinterpret_cast<uint4*>(blocks + blk);
-    dst[0] = make_uint4((uint32_t)b.rel[0] | ((uint32_t)b.rel[1] << 16),
-                        (uint32_t)b.rel[2] | ((uint32_t)b.rel[3] << 16), (uint32_t)exc,
-                        (uint32_t)(exc >> 32));
+    dst[0] = make_uint4((uint32_t)ex, (uint32_t)(ex >> 32), (uint32_t)exc, (uint32_t)(exc >> 32));
     dst[1] = make_uint4((uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)hi, (uint32_t)(hi >> 32));
     n_before[blk] = (uint32_t)nex;  // relative for now; fm_finish_kernel adds the superblock base
   }
@@ -240,6 +230,7 @@ void index_destroy(mtsvgpu_index* h) {
   cudaFree(d.blocks);
   cudaFree(d.super);
   cudaFree(d.n_before);
+  cudaFree(d.d_C);
   cudaFree(d.sa);
   cudaFree(d.ktab);
   cudaFree(d.text);
@@ -248,8 +239,10 @@ void index_destroy(mtsvgpu_index* h) {
   cudaFree(d.bin_tax);
   cudaFree(d.bin_gi);
   h->ws.release_all();
-  if (h->pin_in) cudaFreeHost(h->pin_in);
-  if (h->pin_out) cudaFreeHost(h->pin_out);
+  if (h->pin_hits) cudaFreeHost(h->pin_hits);
+  if (h->pin_off) cudaFreeHost(h->pin_off);
+  for (cudaEvent_t e : h->in_events) cudaEventDestroy(e);
+  if (h->copy_in_stream) cudaStreamDestroy(h->copy_in_stream);
   for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;
@@ -324,6 +317,7 @@ int index_from_host_parts(const uint8_t* text, uint64_t n, const mtsvgpu_bin* bi
 
   MTSV_CUDA_TRY(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
   h->stream = h->own_stream;
+  MTSV_CUDA_TRY(cudaStreamCreateWithFlags(&h->copy_in_stream, cudaStreamNonBlocking));
   cudaStream_t st = h->stream;
 
   // ---- text and bins ----
@@ -403,6 +397,8 @@ int index_from_host_parts(const uint8_t* text, uint64_t n, const mtsvgpu_bin* bi
   d.C[SYM_G] = (uint32_t)(1 + totals[0] + totals[1]);
   d.C[SYM_N] = (uint32_t)(1 + totals[0] + totals[1] + totals[2]);
   d.C[SYM_T] = (uint32_t)(1 + totals[0] + totals[1] + totals[2] + totals[4]);
+  MTSV_TRY(dev_alloc(&d.d_C, 8, &d.device_bytes));
+  MTSV_CUDA_TRY(cudaMemcpy(d.d_C, d.C, 5 * sizeof(uint32_t), cudaMemcpyHostToDevice));
   cudaFree(d_bwt);
   d_bwt = nullptr;
 

@@ -152,6 +152,23 @@ class MGIndex:
         L.mtsvgpu_free(op)
         return hits, offs
 
+    def bin_reads_pinned(self, reads, params=None, strands=2):
+        """Like bin_reads but zero-copy on the way out: returns numpy views of the handle's page-locked
+        result buffers, valid until the next batch call on this index."""
+        L = _lib.load_library()
+        params = params or Params()
+        cat, off = reads if isinstance(reads, tuple) else pack_reads(reads)
+        assert cat.dtype == np.uint8 and off.dtype == np.uint64 and cat.flags.c_contiguous
+        n = len(off) - 1
+        ps = params.c_struct(strands)
+        hp, op, nh = C.c_void_p(), C.c_void_p(), C.c_uint64()
+        check(L.mtsvgpu_bin_batch_pinned(self._h, _ptr(cat), _ptr(off), n, C.byref(ps), C.byref(hp),
+                                         C.byref(op), C.byref(nh)))
+        offs = np.frombuffer((C.c_uint8 * ((n + 1) * 8)).from_address(op.value), dtype=np.uint64)
+        total = int(nh.value)
+        hits = np.frombuffer((C.c_uint8 * (max(total, 1) * 24)).from_address(hp.value), dtype=HIT_DTYPE)[:total]
+        return hits, offs
+
     def bin_reads_device(self, d_seqs_ptr, d_seq_off_ptr, n_reads, params=None, strands=2):
         """Device-resident variant: inputs are device pointers (e.g. torch tensors' data_ptr());
         returns (d_hits_ptr, d_hit_off_ptr, n_hits) valid until the next batch call."""

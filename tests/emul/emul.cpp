@@ -23,6 +23,7 @@ struct EmulIndex {
   std::vector<uint2> ktab;
   std::vector<uint8_t> text;
   std::vector<uint32_t> bin_start, bin_end, bin_tax, bin_gi;
+  uint32_t C[5] = {0, 0, 0, 0, 0};
   FmView fm{};
   SaView sv{};
   KtabView kt{};
@@ -61,7 +62,7 @@ void* emul_index_build(const uint8_t* text, uint64_t n, const emul_bin* bins, ui
   }
   uint64_t n_blocks = n / 64 + 1;
   uint64_t n_super = (n_blocks + kBlocksPerSuper - 1) / kBlocksPerSuper;
-  e->blocks.assign(n_super * kBlocksPerSuper, FmBlock{{0, 0, 0, 0}, 0, 0, 0});
+  e->blocks.assign(n_super * kBlocksPerSuper, FmBlock{0, 0, 0, 0});
   e->super.resize(n_super);
   e->n_before.assign(n_super * kBlocksPerSuper, 0);
   uint32_t run[5] = {0, 0, 0, 0, 0};
@@ -74,8 +75,8 @@ void* emul_index_build(const uint8_t* text, uint64_t n, const emul_bin* bins, ui
         e->super[blk / kBlocksPerSuper].c[a] = run[a];
       }
     }
-    FmBlock b{{0, 0, 0, 0}, 0, 0, 0};
-    for (int a = 0; a < 4; ++a) b.rel[a] = (uint16_t)(run[a] - sup[a]);
+    FmBlock b{0, 0, 0, 0};
+    for (int a = 0; a < 4; ++a) b.rel |= (uint64_t)(uint16_t)(run[a] - sup[a]) << (16 * a);
     e->n_before[blk] = run[4];
     for (uint32_t j = 0; j < 64; ++j) {
       uint64_t r = blk * 64 + j;
@@ -98,11 +99,12 @@ void* emul_index_build(const uint8_t* text, uint64_t n, const emul_bin* bins, ui
   e->fm.n_before = e->n_before.data();
   e->fm.n = (uint32_t)n;
   e->fm.dollar_row = dollar;
-  e->fm.C[SYM_A] = 1;
-  e->fm.C[SYM_C] = 1 + run[0];
-  e->fm.C[SYM_G] = 1 + run[0] + run[1];
-  e->fm.C[SYM_N] = 1 + run[0] + run[1] + run[2];
-  e->fm.C[SYM_T] = 1 + run[0] + run[1] + run[2] + run[4];
+  e->C[SYM_A] = 1;
+  e->C[SYM_C] = 1 + run[0];
+  e->C[SYM_G] = 1 + run[0] + run[1];
+  e->C[SYM_N] = 1 + run[0] + run[1] + run[2];
+  e->C[SYM_T] = 1 + run[0] + run[1] + run[2] + run[4];
+  e->fm.C = e->C;
   // suffix array at the requested rate: same walk as sa_densify_kernel
   if (sa_rate == 0) sa_rate = 1;
   e->sa.assign((n + sa_rate - 1) / sa_rate, 0xffffffffu);
@@ -161,8 +163,8 @@ void emul_backward_search(void* p, const uint8_t* pat, uint32_t len, uint32_t* l
 }
 
 // Myers recurrence exactly as verify_kernel evaluates it (ncls = 4: binner rule, 5: raw bytes)
-uint32_t emul_edit_distance(const uint8_t* pat, uint32_t L, uint32_t rc, const uint8_t* txt, uint32_t T,
-                            int ncls) {
+uint32_t emul_edit_distance_k(const uint8_t* pat, uint32_t L, uint32_t rc, const uint8_t* txt, uint32_t T,
+                              int ncls, uint32_t k) {
   if (L == 0) return 0;
   if (L > 1024) return 0xffffffffu;
   uint64_t peq[5][16];
@@ -185,7 +187,12 @@ uint32_t emul_edit_distance(const uint8_t* pat, uint32_t L, uint32_t rc, const u
     uint32_t c = text_code(txt[j]);
     return c < (uint32_t)ncls ? c : 7u;
   };
-  return myers_semiglobal<16>(L, T, pf, tf);
+  return myers_bounded<16>(L, T, k, pf, tf);
+}
+
+uint32_t emul_edit_distance(const uint8_t* pat, uint32_t L, uint32_t rc, const uint8_t* txt, uint32_t T,
+                            int ncls) {
+  return emul_edit_distance_k(pat, L, rc, txt, T, ncls, 0xfffffffeu);
 }
 
 // the whole pipeline, one query at a time, in the stage order of binner.cu
@@ -239,7 +246,7 @@ int emul_bin_reads(void* p, const uint8_t* seqs, const uint64_t* seq_off, uint64
                   2ull * k > (uint64_t)L || L == 0;
       uint32_t ed = kNoEdit;
       if (!skip) {
-        ed = emul_edit_distance(seq, L, rc, e->text.data() + dense[i].start, dense[i].end - dense[i].start, 4);
+        ed = emul_edit_distance_k(seq, L, rc, e->text.data() + dense[i].start, dense[i].end - dense[i].start, 4, k);
         if (ed > k) ed = kNoEdit;
       }
       edits[i] = ed;

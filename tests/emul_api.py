@@ -51,6 +51,9 @@ def lib():
                                        C.POINTER(C.c_uint32)]
     L.emul_edit_distance.restype = C.c_uint32
     L.emul_edit_distance.argtypes = [C.c_char_p, C.c_uint32, C.c_uint32, C.c_char_p, C.c_uint32, C.c_int]
+    L.emul_edit_distance_k.restype = C.c_uint32
+    L.emul_edit_distance_k.argtypes = [C.c_char_p, C.c_uint32, C.c_uint32, C.c_char_p, C.c_uint32, C.c_int,
+                                       C.c_uint32]
     L.emul_bin_reads.argtypes = [vp, vp, vp, C.c_uint64, C.POINTER(Params), C.POINTER(vp), C.POINTER(vp)]
     L.emul_free.argtypes = [vp]
     _LIB = L
@@ -110,5 +113,8 @@ class EmulIndex:
         return hits, offs
 
 
-def edit_distance(pat, txt, rc=0, ncls=5):
-    return int(lib().emul_edit_distance(bytes(pat), len(pat), rc, bytes(txt), len(txt), ncls))
+def edit_distance(pat, txt, rc=0, ncls=5, k=None):
+    """k=None: exact value; otherwise the bounded variant (exact when <= k, anything > k otherwise)."""
+    if k is None:
+        return int(lib().emul_edit_distance(bytes(pat), len(pat), rc, bytes(txt), len(txt), ncls))
+    return int(lib().emul_edit_distance_k(bytes(pat), len(pat), rc, bytes(txt), len(txt), ncls, k))

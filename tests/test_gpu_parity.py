@@ -155,8 +155,8 @@ def test_pipeline_small(oracle, small_ref, small_index, name, flags, opts):
     with _gpu_index(small_index, **opts) as g:
         h2, o2 = g.bin_reads(reads, pg)
         _same(h1, o1, h2, o2)
-        # idempotence: the same batch again on the same handle
-        h3, o3 = g.bin_reads(reads, pg)
+        # idempotence: the same batch again on the same handle, through the pinned-result entry point
+        h3, o3 = g.bin_reads_pinned(reads, pg)
         _same(h2, o2, h3, o3)
 
 

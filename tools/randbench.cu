@@ -26,7 +26,19 @@ __global__ void chase(const uint4* __restrict__ tab, uint64_t n_gran, int steps,
 }
 
 int main(int argc, char** argv) {
-  size_t sizes_mb[] = {64, 512, 2048, 8192};
+  // optional: L2 fetch granularity hint (bytes) as argv[1]
+  if (argc > 1) {
+    size_t g = atoi(argv[1]);
+    cudaError_t e = cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, g);
+    size_t got = 0;
+    cudaDeviceGetLimit(&got, cudaLimitMaxL2FetchGranularity);
+    printf("{\"l2_fetch_granularity_requested\":%zu,\"got\":%zu,\"err\":\"%s\"}\n", g, got, cudaGetErrorString(e));
+  } else {
+    size_t got = 0;
+    cudaDeviceGetLimit(&got, cudaLimitMaxL2FetchGranularity);
+    printf("{\"l2_fetch_granularity_default\":%zu}\n", got);
+  }
+  size_t sizes_mb[] = {64, 2048, 8192};
   int steps = 64;
   for (size_t smb : sizes_mb) {
     size_t bytes = smb << 20;
@@ -35,7 +47,7 @@ int main(int argc, char** argv) {
     cudaMalloc(&out, 8);
     cudaMemset(tab, 1, bytes);
     for (int gran : {32, 64}) {
-      for (int blocks_per_sm : {4, 8}) {
+      for (int blocks_per_sm : {8}) {
         int threads = 256, grid = 148 * blocks_per_sm * 8;  // 8 waves
         uint64_t n_gran = bytes / gran;
         cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
