@@ -7,6 +7,8 @@ This is offline scaffolding for tests and bench.py, not the h
 array of a '$'-terminated text is unique, so the result equals what any correct builder produces
 (checked against the oracle's SA-IS in tests/test_build_index.py).  Works on CPU tensors too.
 """
+import sys
+
 import numpy as np
 import torch
 
@@ -78,7 +80,7 @@ def suffix_array(text_u8, device=None, verbose=False):
         del grp
         rounds += 1
         if verbose:
-            print("  suffix_array: h=%d groups=%d/%d" % (h, ngroups, n), flush=True)
+            print("  suffix_array: h=%d groups=%d/%d" % (h, ngroups, n), file=sys.stderr, flush=True)
         if ngroups == n:
             return sa
         del sa

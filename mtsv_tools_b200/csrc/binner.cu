@@ -63,9 +63,35 @@ __global__ void expand_slots_kernel(const uint32_t* __restrict__ slot_off, uint3
   for (uint32_t s = b; s < e; ++s) slot_q[s] = q;
 }
 
+// read encoding: one thread per (read, 64-base word).  Streaming: reads the batch's bytes once, writes
+// 24 B per 64 bases and strand.
+__global__ void __launch_bounds__(256) encode_fwd_kernel(ReadsView rv, ReadWord* __restrict__ words,
+                                                         uint32_t w_max, int raw) {
+  uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t r = (uint32_t)(t / w_max), w = (uint32_t)(t % w_max);
+  if (r >= rv.n_reads) return;
+  uint64_t a = rv.seq_off[rv.read0 + r], b = rv.seq_off[rv.read0 + r + 1];
+  uint32_t L = (uint32_t)(b - a);
+  if (w * 64 >= L) return;
+  uint32_t woff = (uint32_t)((a - rv.seq_off[rv.read0]) >> 6) + r;
+  words[woff + w] = encode_fwd_word(rv.seqs + a, L, w, raw != 0);
+}
+
+__global__ void __launch_bounds__(256) encode_rc_kernel(ReadsView rv, ReadWord* __restrict__ words,
+                                                        uint32_t total_words, uint32_t w_max) {
+  uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t r = (uint32_t)(t / w_max), w = (uint32_t)(t % w_max);
+  if (r >= rv.n_reads) return;
+  uint64_t a = rv.seq_off[rv.read0 + r], b = rv.seq_off[rv.read0 + r + 1];
+  uint32_t L = (uint32_t)(b - a);
+  if (w * 64 >= L) return;
+  uint32_t woff = (uint32_t)((a - rv.seq_off[rv.read0]) >> 6) + r;
+  words[total_words + woff + w] = encode_rc_word(words + woff, L, w);
+}
+
 // seed search: one thread per slot.  Each thread owns one dependent chain of sector fetches;
 // ~2048 chains per SM keep the HBM random-access pipeline full.
-__global__ void __launch_bounds__(256) seed_search_kernel(FmView fm, KtabView kt, ReadsView rv, Params p,
+__global__ void __launch_bounds__(256) seed_search_kernel(FmView fm, KtabView kt, ReadsView rv, EncView ev, Params p,
                                                           const uint32_t* __restrict__ slot_off,
                                                           const uint32_t* __restrict__ slot_q,
                                                           uint32_t n_slots,
@@ -79,7 +105,7 @@ __global__ void __launch_bounds__(256) seed_search_kernel(FmView fm, KtabView kt
     uint32_t j = s - slot_off[q];
     uint32_t L = query_len(rv, p.ns, q);
     uint32_t lo, cnt;
-    seed_search_item(fm, kt, query_seq(rv, p.ns, q), q % p.ns, L, p.S, j * p.G, &lo, &cnt, &steps);
+    seed_search_item(fm, kt, ev.words + query_word_off(rv, ev, p.ns, q), L, p.S, j * p.G, &lo, &cnt, &steps);
     slot_lo[s] = lo;
     slot_cnt[s] = cnt;
   }
@@ -424,37 +450,40 @@ __global__ void __launch_bounds__(256) rank_emit_kernel(uint32_t nq, const uint3
 constexpr int kVerifyThreads = 128;
 
 struct VerifyJob {
-  const uint8_t* pat;   // pattern bytes (raw read bytes for the binner)
+  const ReadWord* enc;  // pattern as bit planes (one strand)
   uint32_t L;           // pattern length
-  uint32_t rc;          // 1 = use the reverse complement of the normalised pattern
   const uint8_t* txt;   // text window
   uint32_t T;           // window length
   uint32_t limit;       // edit budget k; result > limit is reported as kNoEdit
   uint32_t skip;        // 1 = do not verify (result kNoEdit)
+  uint32_t out;         // where the result goes
 };
 
-// binner jobs: dense candidate list
+// binner jobs: dense candidate list, visited through `order` so that a warp gets candidates of similar
+// cost (single-seed candidates — mostly chance hits that the Ukkonen cut-off rejects within one block —
+// are grouped after the multi-seed ones)
 struct BinnerJobs {
   ReadsView rv;
+  EncView ev;
   Params p;
   const CandRec* cand;
   const uint32_t* cand_q;
   const uint32_t* cand_off;
+  const uint32_t* order;
   const uint8_t* text;
   uint32_t n;
   __device__ __forceinline__ VerifyJob get(uint32_t i) const {
     VerifyJob j;
-    CandRec c = cand[i];
-    uint32_t q = cand_q[i];
-    uint64_t r = rv.read0 + q / p.ns;
-    uint64_t so = rv.seq_off[r];
-    j.pat = rv.seqs + so;
-    j.L = (uint32_t)(rv.seq_off[r + 1] - so);
-    j.rc = q % p.ns;
+    uint32_t ci = order[i];
+    CandRec c = cand[ci];
+    uint32_t q = cand_q[ci];
+    j.enc = ev.words + query_word_off(rv, ev, p.ns, q);
+    j.L = query_len(rv, p.ns, q);
     j.txt = text + c.start;
     j.T = c.end - c.start;
     j.limit = edit_budget(j.L, p.edit_rate);
-    uint32_t rank = i - cand_off[q];
+    j.out = ci;
+    uint32_t rank = ci - cand_off[q];
     // src/index.rs:385-389 (prefix of the ranked list) and :406 (L - 2k wraps when 2k > L)
     j.skip = (p.max_candidates >= 0 && (uint64_t)rank >= (uint64_t)p.max_candidates) ||
              (2ull * j.limit > (uint64_t)j.L) || j.L == 0;
@@ -462,37 +491,25 @@ struct BinnerJobs {
   }
 };
 
-// stage-level jobs: explicit pairs
+// stage-level jobs: explicit pairs; patterns were encoded (raw mode) like a one-strand read batch
 struct PairJobs {
-  const uint8_t* pats;
-  const uint64_t* pat_off;
+  ReadsView pv;  // the patterns as "reads"
+  EncView ev;
   const uint8_t* texts;
   const uint64_t* text_off;
   uint32_t n;
   __device__ __forceinline__ VerifyJob get(uint32_t i) const {
     VerifyJob j;
-    j.pat = pats + pat_off[i];
-    j.L = (uint32_t)(pat_off[i + 1] - pat_off[i]);
-    j.rc = 0;
+    j.enc = ev.words + query_word_off(pv, ev, 1, i);
+    j.L = query_len(pv, 1, i);
     j.txt = texts + text_off[i];
     j.T = (uint32_t)(text_off[i + 1] - text_off[i]);
     j.limit = 0xfffffffeu;
     j.skip = 0;
+    j.out = i;
     return j;
   }
 };
-
-template <int NCLS>
-__device__ __forceinline__ uint32_t pattern_class(uint8_t b, uint32_t rc) {
-  if (NCLS == 4) {  // binner: normalise (src/binner.rs:88-100), N never matches
-    uint32_t c = read_code(b);
-    if (rc) c = comp_code(c);
-    return c;  // 0..3 or 4 (= none)
-  } else {  // raw bytes: A,C,G,T,N are classes, anything else matches nothing
-    uint32_t c = text_code(b);
-    return c <= SYM_N ? c : 7u;
-  }
-}
 
 template <int W, int NCLS, typename Jobs>
 __global__ void __launch_bounds__(kVerifyThreads) verify_kernel(Jobs jobs, uint32_t* __restrict__ out,
@@ -502,33 +519,22 @@ __global__ void __launch_bounds__(kVerifyThreads) verify_kernel(Jobs jobs, uint3
   if (i >= jobs.n) return;
   VerifyJob job = jobs.get(i);
   if (job.skip) {
-    out[i] = kNoEdit;
+    out[job.out] = kNoEdit;
     return;
   }
   const uint32_t L = job.L;
   if (L == 0) {  // empty needle aligns anywhere with 0 edits (src/align.rs test_empty)
-    out[i] = 0;
+    out[job.out] = 0;
     return;
   }
   const int last = (int)((L - 1) >> 6);
-  // pattern masks
+  // pattern-match masks straight from the read's bit planes
 #pragma unroll
   for (int w = 0; w < W; ++w) {
-    uint64_t m[NCLS];
+    ReadWord rw{0, 0, ~0ull};
+    if (w <= last) rw = job.enc[w];
 #pragma unroll
-    for (int c = 0; c < NCLS; ++c) m[c] = 0;
-    if (w <= last) {
-      uint32_t lim = L - (uint32_t)w * 64 < 64 ? L - (uint32_t)w * 64 : 64;
-      for (uint32_t b = 0; b < lim; ++b) {
-        uint32_t pi = (uint32_t)w * 64 + b;
-        uint8_t byte = job.rc ? job.pat[L - 1 - pi] : job.pat[pi];
-        uint32_t c = pattern_class<NCLS>(byte, job.rc);
-#pragma unroll
-        for (int cc = 0; cc < NCLS; ++cc) m[cc] |= (uint64_t)(c == (uint32_t)cc) << b;
-      }
-    }
-#pragma unroll
-    for (int c = 0; c < NCLS; ++c) peq[(c * W + w) * kVerifyThreads + threadIdx.x] = m[c];
+    for (int c = 0; c < NCLS; ++c) peq[(c * W + w) * kVerifyThreads + threadIdx.x] = word_peq(rw, c);
   }
   // text is read through 8-byte aligned words (the device text has 16 bytes of slack at the end)
   struct TextReader {
@@ -547,7 +553,7 @@ __global__ void __launch_bounds__(kVerifyThreads) verify_kernel(Jobs jobs, uint3
   const uint32_t T = job.T;
   auto peq_f = [&](uint32_t c, int w) -> uint64_t { return peq[(c * W + w) * kVerifyThreads + threadIdx.x]; };
   const uint32_t best = myers_bounded<W>(L, T, job.limit, peq_f, text);
-  out[i] = best <= job.limit ? best : kNoEdit;
+  out[job.out] = best <= job.limit ? best : kNoEdit;
   if (ctr) atomicAdd(&ctr->window_bytes, (unsigned long long)T);
 }
 
@@ -685,6 +691,21 @@ __global__ void __launch_bounds__(256) gather_hits_kernel(uint32_t nq, uint32_t 
   }
 }
 
+// verification order: multi-seed candidates first, single-seed ones after (stable within each class)
+__global__ void cand_class_kernel(const CandRec* __restrict__ cand, uint32_t n, uint32_t* __restrict__ flag) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) flag[i] = cand[i].num_seeds > 1 ? 1u : 0u;
+}
+
+__global__ void cand_order_kernel(const CandRec* __restrict__ cand, const uint32_t* __restrict__ multi_before,
+                                  uint32_t n, uint32_t* __restrict__ order) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t mb = multi_before[i], n_multi = multi_before[n];
+  uint32_t pos = cand[i].num_seeds > 1 ? mb : n_multi + (i - mb);
+  order[pos] = i;
+}
+
 // ------------------------------------------------------------------------------------------
 // host orchestration
 // ------------------------------------------------------------------------------------------
@@ -781,7 +802,8 @@ static int grow_preserve(DevBuf& buf, size_t used_bytes, size_t need_bytes, cuda
 // in-flight cap and the caller must split the range (nothing was emitted in that case).
 static int run_sub_batch(mtsvgpu_index* h, const Params& p, const uint8_t* d_seqs,
                          const uint64_t* d_seq_off, uint64_t read0, uint32_t n_reads,
-                         uint64_t slot_bound, uint64_t batch_read0, uint64_t* out_total) {
+                         uint64_t slot_bound, uint64_t sub_bytes, uint64_t* out_total) {
+  const uint64_t batch_read0 = 0;
   DeviceIndex& ix = h->ix;
   BatchWorkspace& ws = h->ws;
   cudaStream_t st = h->stream;
@@ -808,6 +830,11 @@ static int run_sub_batch(mtsvgpu_index* h, const Params& p, const uint8_t* d_seq
   MTSV_TRY(ws.slot_cnt.reserve((slot_bound + 1) * 4));
   MTSV_TRY(ws.slot_hoff.reserve((slot_bound + 1) * 4));
   MTSV_TRY(ws.scan_tmp.reserve(((qn + 2047) / 2048 + 1) * 8));
+  const uint64_t total_words64 = (sub_bytes >> 6) + n_reads;  // words of one strand (closed-form layout)
+  if (total_words64 * p.ns > 0x7fffffffull) return 1;        // caller splits
+  const uint32_t total_words = (uint32_t)total_words64;
+  MTSV_TRY(ws.enc.reserve(((size_t)total_words * p.ns + 1) * sizeof(ReadWord)));
+  EncView ev{ws.enc.as<ReadWord>(), total_words};
 
   BatchCounters hc;
   const unsigned qgrid = (nq + 255) / 256;
@@ -832,12 +859,21 @@ static int run_sub_batch(mtsvgpu_index* h, const Params& p, const uint8_t* d_seq
   // (only now that the slot count is known to fit the buffers)
   clk.begin(ST_PREP);
   MTSV_LAUNCH(expand_slots_kernel, qgrid, 256, 0, st, slot_off, nq, ws.slot_q.as<uint32_t>());
+  {
+    const uint32_t w_max = hc.max_len ? (hc.max_len + 63) / 64 : 1;
+    const uint64_t threads = (uint64_t)n_reads * w_max;
+    MTSV_LAUNCH(encode_fwd_kernel, (unsigned)((threads + 255) / 256), 256, 0, st, rv, ws.enc.as<ReadWord>(),
+                w_max, 0);
+    if (p.ns == 2)
+      MTSV_LAUNCH(encode_rc_kernel, (unsigned)((threads + 255) / 256), 256, 0, st, rv, ws.enc.as<ReadWord>(),
+                  total_words, w_max);
+  }
   clk.end();
 
   // ---- seed search ----
   clk.begin(ST_SEARCH);
   if (n_slots)
-    MTSV_LAUNCH(seed_search_kernel, (n_slots + 255) / 256, 256, 0, st, ix.fm_view(), ix.ktab_view(), rv, p,
+    MTSV_LAUNCH(seed_search_kernel, (n_slots + 255) / 256, 256, 0, st, ix.fm_view(), ix.ktab_view(), rv, ev, p,
                 slot_off, ws.slot_q.as<uint32_t>(), n_slots, ws.slot_lo.as<uint32_t>(),
                 ws.slot_cnt.as<uint32_t>(), d_ctr, h->profiling ? 1 : 0);
   clk.end();
@@ -910,8 +946,16 @@ static int run_sub_batch(mtsvgpu_index* h, const Params& p, const uint8_t* d_seq
     clk.end();
     // ---- verify ----
     clk.begin(ST_VERIFY);
-    BinnerJobs jobs{rv, p, ws.cand_dense.as<CandRec>(), ws.cand_q.as<uint32_t>(),
-                    ws.cand_off.as<uint32_t>(), ix.text, n_cand};
+    MTSV_TRY(ws.cand_flag.reserve(((size_t)n_cand + 1) * 4));
+    MTSV_TRY(ws.cand_order.reserve((size_t)n_cand * 4));
+    MTSV_LAUNCH(cand_class_kernel, (n_cand + 255) / 256, 256, 0, st, ws.cand_dense.as<CandRec>(), n_cand,
+                ws.cand_flag.as<uint32_t>());
+    MTSV_TRY(exclusive_scan_u32(ws.cand_flag.as<uint32_t>(), ws.cand_flag.as<uint32_t>(), n_cand, ws.scan_tmp,
+                                nullptr, st));
+    MTSV_LAUNCH(cand_order_kernel, (n_cand + 255) / 256, 256, 0, st, ws.cand_dense.as<CandRec>(),
+                ws.cand_flag.as<uint32_t>(), n_cand, ws.cand_order.as<uint32_t>());
+    BinnerJobs jobs{rv, ev, p, ws.cand_dense.as<CandRec>(), ws.cand_q.as<uint32_t>(),
+                    ws.cand_off.as<uint32_t>(), ws.cand_order.as<uint32_t>(), ix.text, n_cand};
     MTSV_TRY(launch_verify<4>(jobs, hc.max_len, ws.cand_edit.as<uint32_t>(),
                               h->profiling ? d_ctr : nullptr, st));
     clk.end();
@@ -972,7 +1016,7 @@ static int run_range(mtsvgpu_index* h, const Params& p, const uint8_t* d_seqs, c
   uint64_t slot_bound = (bytes / p.G + n_reads) * p.ns + 1;
   bool split = slot_bound > 0xfffffff0ull || n_reads * p.ns > 0x7ffffff0ull;
   if (!split) {
-    int rc = run_sub_batch(h, p, d_seqs, d_seq_off, read0, (uint32_t)n_reads, slot_bound, 0, out_total);
+    int rc = run_sub_batch(h, p, d_seqs, d_seq_off, read0, (uint32_t)n_reads, slot_bound, bytes, out_total);
     if (rc != 1) return rc;
   }
   if (n_reads == 1) return set_error(MTSVGPU_ELIMIT, "a single read exceeds the device batch limits");
@@ -1029,13 +1073,13 @@ int bin_batch_device(mtsvgpu_index* h, const uint8_t* d_seqs, const uint64_t* d_
 // ------------------------------------------------------------------------------------------
 // stage-level entry points
 // ------------------------------------------------------------------------------------------
-__global__ void bs_patterns_kernel(FmView fm, KtabView kt, const uint8_t* __restrict__ pats, uint32_t len,
-                                   uint64_t n, uint64_t* __restrict__ lower, uint64_t* __restrict__ upper) {
+__global__ void bs_patterns_kernel(FmView fm, KtabView kt, ReadsView pv, EncView ev, uint32_t len, uint64_t n,
+                                   uint64_t* __restrict__ lower, uint64_t* __restrict__ upper) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   // a pattern is a forward-strand "read" whose single seed covers it entirely
   uint32_t lo, cnt;
-  seed_search_item(fm, kt, pats + i * len, 0, len, len, 0, &lo, &cnt, nullptr);
+  seed_search_item(fm, kt, ev.words + query_word_off(pv, ev, 1, (uint32_t)i), len, len, 0, &lo, &cnt, nullptr);
   lower[i] = cnt ? lo : 0;
   upper[i] = cnt ? (uint64_t)lo + cnt : 0;
 }
@@ -1045,23 +1089,37 @@ int backward_search_batch(mtsvgpu_index* h, const uint8_t* pats, uint32_t pat_le
   if (!h || !pats || !lower || !upper) return set_error(MTSVGPU_EINVAL, "null argument");
   if (pat_len == 0) return set_error(MTSVGPU_EINVAL, "pattern length must be > 0");
   if (n_pats == 0) return 0;
+  if (n_pats > 0x0fffffffull || n_pats * pat_len > 0x7fffffffull) return set_error(MTSVGPU_ELIMIT, "too many patterns");
   MTSV_CUDA_TRY(cudaSetDevice(h->ix.device));
   cudaStream_t st = h->stream;
-  DevBuf dp, dl, du;
+  DevBuf dp, doff, dw, dl, du;
   int rc = 0;
   do {
-    if ((rc = dp.reserve(n_pats * pat_len))) break;
+    std::vector<uint64_t> off(n_pats + 1);
+    for (uint64_t i = 0; i <= n_pats; ++i) off[i] = i * pat_len;
+    const uint32_t w_max = (pat_len + 63) / 64;
+    const uint32_t total_words = (uint32_t)((n_pats * pat_len) >> 6) + (uint32_t)n_pats;
+    if ((rc = dp.reserve(n_pats * pat_len + 16))) break;
+    if ((rc = doff.reserve((n_pats + 1) * 8))) break;
+    if ((rc = dw.reserve(((size_t)total_words + 1) * sizeof(ReadWord)))) break;
     if ((rc = dl.reserve(n_pats * 8))) break;
     if ((rc = du.reserve(n_pats * 8))) break;
     cudaMemcpyAsync(dp.p, pats, n_pats * pat_len, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(doff.p, off.data(), (n_pats + 1) * 8, cudaMemcpyHostToDevice, st);
+    ReadsView pv{dp.as<uint8_t>(), doff.as<uint64_t>(), 0, (uint32_t)n_pats};
+    EncView ev{dw.as<ReadWord>(), total_words};
+    const uint64_t threads = n_pats * w_max;
+    MTSV_LAUNCH(encode_fwd_kernel, (unsigned)((threads + 255) / 256), 256, 0, st, pv, dw.as<ReadWord>(), w_max, 0);
     MTSV_LAUNCH(bs_patterns_kernel, (unsigned)((n_pats + 127) / 128), 128, 0, st, h->ix.fm_view(),
-                h->ix.ktab_view(), dp.as<uint8_t>(), pat_len, n_pats, dl.as<uint64_t>(), du.as<uint64_t>());
+                h->ix.ktab_view(), pv, ev, pat_len, n_pats, dl.as<uint64_t>(), du.as<uint64_t>());
     cudaMemcpyAsync(lower, dl.p, n_pats * 8, cudaMemcpyDeviceToHost, st);
     cudaMemcpyAsync(upper, du.p, n_pats * 8, cudaMemcpyDeviceToHost, st);
     cudaError_t e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) rc = set_error(MTSVGPU_ECUDA, "backward_search: %s", cudaGetErrorString(e));
   } while (0);
   dp.release();
+  doff.release();
+  dw.release();
   dl.release();
   du.release();
   return rc;
@@ -1116,7 +1174,7 @@ int edit_distance_batch(int device, const uint8_t* pats, const uint64_t* pat_off
   }
   if (max_len > kMaxReadLen) return set_error(MTSVGPU_ELIMIT, "pattern longer than %u", kMaxReadLen);
   uint64_t pb = pat_off[n_pairs], tb = text_off[n_pairs];
-  DevBuf dp, dpo, dt, dto, de;
+  DevBuf dp, dpo, dt, dto, de, dw;
   int rc = 0;
   do {
     if ((rc = dp.reserve(pb + 16))) break;
@@ -1128,7 +1186,15 @@ int edit_distance_batch(int device, const uint8_t* pats, const uint64_t* pat_off
     if (tb) cudaMemcpy(dt.p, texts, tb, cudaMemcpyHostToDevice);
     cudaMemcpy(dpo.p, pat_off, (n_pairs + 1) * 8, cudaMemcpyHostToDevice);
     cudaMemcpy(dto.p, text_off, (n_pairs + 1) * 8, cudaMemcpyHostToDevice);
-    PairJobs jobs{dp.as<uint8_t>(), dpo.as<uint64_t>(), dt.as<uint8_t>(), dto.as<uint64_t>(), (uint32_t)n_pairs};
+    // encode the patterns (raw bytes: N is its own class) like a one-strand read batch
+    const uint32_t w_max = std::max(1u, (max_len + 63) / 64);
+    const uint32_t total_words = (uint32_t)(pb >> 6) + (uint32_t)n_pairs;
+    if ((rc = dw.reserve(((size_t)total_words + 1) * sizeof(ReadWord)))) break;
+    ReadsView pv{dp.as<uint8_t>(), dpo.as<uint64_t>(), 0, (uint32_t)n_pairs};
+    EncView ev{dw.as<ReadWord>(), total_words};
+    const uint64_t threads = n_pairs * w_max;
+    MTSV_LAUNCH(encode_fwd_kernel, (unsigned)((threads + 255) / 256), 256, 0, 0, pv, dw.as<ReadWord>(), w_max, 1);
+    PairJobs jobs{pv, ev, dt.as<uint8_t>(), dto.as<uint64_t>(), (uint32_t)n_pairs};
     if ((rc = launch_verify<5>(jobs, std::max(max_len, 1u), de.as<uint32_t>(), nullptr, 0))) break;
     cudaError_t e = cudaMemcpy(edits, de.p, n_pairs * 4, cudaMemcpyDeviceToHost);
     if (e != cudaSuccess) rc = set_error(MTSVGPU_ECUDA, "edit_distance: %s", cudaGetErrorString(e));
@@ -1138,6 +1204,7 @@ int edit_distance_batch(int device, const uint8_t* pats, const uint64_t* pat_off
   dt.release();
   dto.release();
   de.release();
+  dw.release();
   return rc;
 }
 

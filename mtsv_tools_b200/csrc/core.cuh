@@ -42,27 +42,33 @@ MTSV_HD T ldg(const T* p) {
 // symbol codes used on the device: A C G T in 2 bits, N and '$' are "exceptions"
 enum : uint32_t { SYM_A = 0, SYM_C = 1, SYM_G = 2, SYM_T = 3, SYM_N = 4, SYM_DOLLAR = 5, SYM_OTHER = 6 };
 
-// read normalisation of src/binner.rs:88-100 fused with the 0..4 encoding
+// Branch-free byte -> symbol code.  (b >> 1) & 7 separates the five letters: A 0, C 1, T 2, G 3,
+// N 7; a 3-bit-per-entry table maps that to the code and a comparison against the canonical byte of
+// the code rejects every other byte.  (A `switch` here compiles to a divergent branch tree, which the
+// verifier would execute once per DP column.)
+MTSV_HD uint32_t upper_acgtn_code(uint32_t b) {  // A,C,G,T,N (upper case) -> 0..4, anything else -> 7
+  const uint32_t lut = (0u << 0) | (1u << 3) | (3u << 6) | (2u << 9) | (7u << 12) | (7u << 15) | (7u << 18) |
+                       (4u << 21);
+  uint32_t code = (lut >> (3 * ((b >> 1) & 7))) & 7;
+  const uint64_t canon = 0x4E54474341ull;  // "ACGTN" little-endian
+  uint32_t want = (uint32_t)(canon >> (8 * (code & 7))) & 0xff;  // code 7 -> 0 (never a letter)
+  return (code < 5 && want == b) ? code : 7u;
+}
+
+// read normalisation of src/binner.rs:88-100 fused with the 0..4 encoding: upper/lower case ACGT
+// keep their base, everything else (N, n, IUPAC, garbage) is N
 MTSV_HD uint32_t read_code(uint8_t b) {
-  switch (b) {
-    case 'A': case 'a': return SYM_A;
-    case 'C': case 'c': return SYM_C;
-    case 'G': case 'g': return SYM_G;
-    case 'T': case 't': return SYM_T;
-    default: return SYM_N;
-  }
+  uint32_t u = (uint32_t)b & 0xDFu;  // fold lower case onto upper case
+  uint32_t c = upper_acgtn_code(u);
+  // bytes whose folded value is a letter but which are not letters themselves (0x01/0x03/0x07/0x14
+  // | 0x20 variants are letters; only b in 0x41..0x5A or 0x61..0x7A can fold to a letter) are fine:
+  // folding only clears bit 5, so u is a letter iff b is that letter in either case.
+  return c < 4 ? c : (uint32_t)SYM_N;
 }
 // reference text bytes are already upper-case ACGTN (src/index.rs:543-553)
 MTSV_HD uint32_t text_code(uint8_t b) {
-  switch (b) {
-    case 'A': return SYM_A;
-    case 'C': return SYM_C;
-    case 'G': return SYM_G;
-    case 'T': return SYM_T;
-    case 'N': return SYM_N;
-    case '$': return SYM_DOLLAR;
-    default: return SYM_OTHER;
-  }
+  uint32_t c = upper_acgtn_code(b);
+  return c < 5 ? c : (b == '$' ? (uint32_t)SYM_DOLLAR : (uint32_t)SYM_OTHER);
 }
 // bio::alphabets::dna::revcomp on the normalised alphabet (src/binner.rs:115): A<->T C<->G N->N
 MTSV_HD uint32_t comp_code(uint32_t c) { return c < 4 ? 3u - c : c; }
@@ -210,7 +216,7 @@ MTSV_HD uint32_t fm_locate(const FmView& fm, const SaView& sv, uint32_t row, uin
   return ldg(&sv.sa[row / sv.rate]) + off;
 }
 
-// k-mer interval table: entry for a k-mer w (lexicographic index, first base most significant)
+// k-mer interval table: entry for a k-mer w (key = lo plane | hi plane << k, base j at bit j)
 // = SA interval [l,u) of w, or l == u when absent.  Legal shortcut 5 of SURVEY app. A.
 struct KtabView {
   const uint2* tab;
@@ -240,14 +246,107 @@ MTSV_HD uint32_t query_len(const ReadsView& rv, uint32_t ns, uint32_t q) {
   return (uint32_t)(ldg(&rv.seq_off[r + 1]) - ldg(&rv.seq_off[r]));
 }
 
-// base i of a read in the strand's own orientation (rc = 1: reverse complement), as a code 0..4
-MTSV_HD uint32_t strand_base(const uint8_t* seq, uint32_t rc, uint32_t L, uint32_t i) {
-  if (!rc) return read_code(ldg(seq + i));
-  return comp_code(read_code(ldg(seq + (L - 1 - i))));
+// ---------------------------------------------------------------------------------------------
+// reads as bit planes
+//
+// Every read-strand ("query") is encoded once per batch into 64-base words of three bit planes:
+// lo/hi = the two bits of the base code (A 0, C 1, G 2, T 3), nn = "not a base" (N after the
+// normalisation of src/binner.rs:88-100).  Seed search then takes a seed's bases and its k-mer table
+// key with a couple of shifts, and the verifier gets its pattern-match masks with a few logic ops,
+// instead of one byte load + classification per base per use.
+// ---------------------------------------------------------------------------------------------
+struct ReadWord {
+  uint64_t lo, hi, nn;
+};
+
+MTSV_HD uint64_t brev64(uint64_t x) {
+#ifdef __CUDA_ARCH__
+  return __brevll(x);
+#else
+  x = ((x >> 1) & 0x5555555555555555ull) | ((x & 0x5555555555555555ull) << 1);
+  x = ((x >> 2) & 0x3333333333333333ull) | ((x & 0x3333333333333333ull) << 2);
+  x = ((x >> 4) & 0x0f0f0f0f0f0f0f0full) | ((x & 0x0f0f0f0f0f0f0f0full) << 4);
+  return __builtin_bswap64(x);
+#endif
 }
 
-MTSV_HD const uint8_t* query_seq(const ReadsView& rv, uint32_t ns, uint32_t q) {
-  return rv.seqs + ldg(&rv.seq_off[rv.read0 + q / ns]);
+MTSV_HD uint64_t low_mask(uint32_t nbits) { return nbits >= 64 ? ~0ull : ((1ull << nbits) - 1); }
+
+// word w (bases 64w .. 64w+63) of the forward strand.  raw = false: binner normalisation (upper and
+// lower case ACGT are bases, everything else is N).  raw = true: bytes as they are (stage-level
+// edit-distance entry point): A,C,G,T bases, 'N' is nn with lo = hi = 0, any other byte is nn with lo = 1
+// ("matches nothing").
+MTSV_HD ReadWord encode_fwd_word(const uint8_t* seq, uint32_t L, uint32_t w, bool raw) {
+  ReadWord r{0, 0, 0};
+  uint32_t base = w * 64;
+  uint32_t lim = L > base ? (L - base < 64 ? L - base : 64) : 0;
+  for (uint32_t b = 0; b < lim; ++b) {
+    uint8_t byte = ldg(seq + base + b);
+    uint32_t c = raw ? text_code(byte) : read_code(byte);
+    uint64_t is_base = c < 4;
+    r.lo |= (uint64_t)((c & 1) & is_base) << b;
+    r.hi |= (uint64_t)(((c >> 1) & 1) & is_base) << b;
+    r.nn |= (uint64_t)(1 - is_base) << b;
+    if (raw && c > 4) r.lo |= 1ull << b;
+  }
+  return r;
+}
+
+// word w of the reverse-complement strand from the forward words (bio::alphabets::dna::revcomp on the
+// normalised alphabet, src/binner.rs:115): rc[i] = comp(fwd[L-1-i]), N stays N.
+MTSV_HD ReadWord encode_rc_word(const ReadWord* fwd, uint32_t L, uint32_t w) {
+  const uint32_t W = (L + 63) >> 6;
+  const uint32_t s = W * 64 - L;  // 0..63
+  ReadWord out{0, 0, 0};
+  // R[x] = bit-reversed complement of fwd[W-1-x]; rc = R >> s (multi-word)
+  for (uint32_t t = 0; t < 2; ++t) {
+    uint32_t x = w + t;
+    if (x >= W) break;
+    if (t == 1 && s == 0) break;
+    ReadWord f = fwd[W - 1 - x];
+    uint32_t fbits = (W - 1 - x) == W - 1 ? L - (W - 1) * 64 : 64;
+    uint64_t valid = low_mask(fbits) & ~f.nn;
+    uint64_t rlo = brev64(~f.lo & valid), rhi = brev64(~f.hi & valid), rnn = brev64(f.nn & low_mask(fbits));
+    if (t == 0) {
+      out.lo |= rlo >> s;
+      out.hi |= rhi >> s;
+      out.nn |= rnn >> s;
+    } else {
+      out.lo |= rlo << (64 - s);
+      out.hi |= rhi << (64 - s);
+      out.nn |= rnn << (64 - s);
+    }
+  }
+  return out;
+}
+
+// where a query's words live: reads are laid out by a closed form of their byte offset, so no scan
+// is needed: woff(r) = floor((seq_off[r] - seq_off[read0]) / 64) + (r - read0); the second strand
+// follows the first at + total_words.
+struct EncView {
+  const ReadWord* words;
+  uint32_t total_words;  // woff(n_reads): words of one strand
+};
+
+MTSV_HD uint32_t query_word_off(const ReadsView& rv, const EncView& ev, uint32_t ns, uint32_t q) {
+  uint32_t r = q / ns;
+  uint64_t rel = ldg(&rv.seq_off[rv.read0 + r]) - ldg(&rv.seq_off[rv.read0]);
+  return (uint32_t)(rel >> 6) + r + (q % ns) * ev.total_words;
+}
+
+// 64 consecutive bases starting at `pos` as plane windows (bit i = base pos + i)
+MTSV_HD ReadWord plane_window(const ReadWord* qw, uint32_t n_words, uint32_t pos) {
+  uint32_t w0 = pos >> 6, sh = pos & 63;
+  ReadWord a = qw[w0];
+  if (sh == 0) return a;
+  ReadWord out{a.lo >> sh, a.hi >> sh, a.nn >> sh};
+  if (w0 + 1 < n_words) {
+    ReadWord b = qw[w0 + 1];
+    out.lo |= b.lo << (64 - sh);
+    out.hi |= b.hi << (64 - sh);
+    out.nn |= b.nn << (64 - sh);
+  }
+  return out;
 }
 
 // k = ceil(len * edit_freq) in f64 — src/index.rs:281-282
@@ -272,32 +371,45 @@ MTSV_HD uint32_t seed_slots(uint32_t L, uint32_t S, uint32_t G) {
 // stage: seed search (one item per seed slot) — src/index.rs:305 + bio backward_search
 // Only `Complete` results matter to the caller (src/index.rs:312-332): cnt = 0 otherwise.
 // ---------------------------------------------------------------------------------------------
-MTSV_HD void seed_search_item(const FmView& fm, const KtabView& kt, const uint8_t* seq, uint32_t rc,
-                              uint32_t L, uint32_t S, uint32_t seed_off, uint32_t* out_lo,
-                              uint32_t* out_cnt, uint32_t* rank_steps) {
+// The k-mer table is keyed by the bit planes of the k-mer: key = lo | hi << k with base j at bit j.
+MTSV_HD void seed_search_item(const FmView& fm, const KtabView& kt, const ReadWord* qw, uint32_t L,
+                              uint32_t S, uint32_t seed_off, uint32_t* out_lo, uint32_t* out_cnt,
+                              uint32_t* rank_steps) {
+  const uint32_t n_words = (L + 63) >> 6;
   uint32_t l = 0, u = fm.n;
-  int i = (int)S - 1;
   uint32_t steps = 0;
-  if (kt.k && kt.k <= S) {
-    // the table replaces the first k steps (the last k bases of the seed) when none is N
-    uint32_t idx = 0;
-    bool has_n = false;
-    for (uint32_t t = 0; t < kt.k; ++t) {
-      uint32_t c = strand_base(seq, rc, L, seed_off + S - kt.k + t);
-      has_n |= c > 3;
-      idx = (idx << 2) | (c & 3);
+  if (S <= 64) {
+    // the whole seed in one window: bit i = base seed_off + i
+    ReadWord win = plane_window(qw, n_words, seed_off);
+    int i = (int)S - 1;
+    if (kt.k && kt.k <= S) {
+      // the table replaces the first k steps (the last k bases of the seed) when none is N
+      uint32_t sh = S - kt.k;
+      uint64_t km = low_mask(kt.k);
+      if (((win.nn >> sh) & km) == 0) {
+        uint64_t key = ((win.lo >> sh) & km) | (((win.hi >> sh) & km) << kt.k);
+        uint2 e = ldg(&kt.tab[key]);
+        l = e.x;
+        u = e.y;
+        i -= (int)kt.k;
+        steps = 1;  // one table sector
+      }
     }
-    if (!has_n) {
-      uint2 e = ldg(&kt.tab[idx]);
-      l = e.x;
-      u = e.y;
-      i -= (int)kt.k;
-      steps = 1;  // one table sector
+    for (; i >= 0 && l < u; --i) {
+      uint32_t a = ((win.nn >> i) & 1) ? (uint32_t)SYM_N
+                                       : ((uint32_t)((win.lo >> i) & 1) | ((uint32_t)((win.hi >> i) & 1) << 1));
+      steps += fm_step(fm, a, l, u);
     }
-  }
-  for (; i >= 0 && l < u; --i) {
-    uint32_t a = strand_base(seq, rc, L, seed_off + (uint32_t)i);
-    steps += fm_step(fm, a, l, u);
+  } else {
+    // long seeds: one plane read per base, no table
+    for (int i = (int)S - 1; i >= 0 && l < u; --i) {
+      uint32_t pos = seed_off + (uint32_t)i;
+      ReadWord w = qw[pos >> 6];
+      uint32_t b = pos & 63;
+      uint32_t a = ((w.nn >> b) & 1) ? (uint32_t)SYM_N
+                                     : ((uint32_t)((w.lo >> b) & 1) | ((uint32_t)((w.hi >> b) & 1) << 1));
+      steps += fm_step(fm, a, l, u);
+    }
   }
   if (rank_steps) *rank_steps = steps;
   if (l < u) {
@@ -306,6 +418,20 @@ MTSV_HD void seed_search_item(const FmView& fm, const KtabView& kt, const uint8_
   } else {
     *out_lo = 0;
     *out_cnt = 0;
+  }
+}
+
+// pattern-match masks of one 64-base word for the verifier: class 0..3 = A,C,G,T; class 4 = N
+// (only used by the raw-byte entry point, where N equals N; the binner never matches an N,
+// src/index.rs:272-279)
+MTSV_HD uint64_t word_peq(const ReadWord& w, uint32_t cls) {
+  uint64_t base = ~w.nn;
+  switch (cls) {
+    case 0: return base & ~w.lo & ~w.hi;
+    case 1: return base & w.lo & ~w.hi;
+    case 2: return base & ~w.lo & w.hi;
+    case 3: return base & w.lo & w.hi;
+    default: return w.nn & ~w.lo & ~w.hi;
   }
 }
 
@@ -496,6 +622,10 @@ MTSV_HD void myers_block(uint64_t Eq, uint64_t& Pv, uint64_t& Mv, uint32_t& phin
 //     above it are dropped, the block below receives a horizontal delta of +1 (an over-estimate).
 //   * early exit when the active rows can no longer reach row L within the remaining columns.
 // Used by the verify kernel (binner.cu) and, compiled with g++, by tests/emul/.
+#ifdef MTSV_COUNT_BLOCKS
+static unsigned long long g_myers_blocks = 0, g_myers_cols = 0;  // test-only instrumentation
+#endif
+
 template <int W, typename PeqF, typename TextF>
 MTSV_HD uint32_t myers_bounded(uint32_t L, uint32_t T, uint32_t k, PeqF peq, TextF text) {
   if (L == 0) return 0;
@@ -528,6 +658,9 @@ MTSV_HD uint32_t myers_bounded(uint32_t L, uint32_t T, uint32_t k, PeqF peq, Tex
     for (int w = 0; w < W - 1; ++w)
       if (w == first && w < last && (uint32_t)(w + 1) * 64 + slack < L + j + 1) first = w + 1;
     const uint32_t c = text(j);
+#ifdef MTSV_COUNT_BLOCKS
+    ++g_myers_cols;
+#endif
     uint32_t phin = first > 0 ? 1u : 0u, mhin = 0;
     uint32_t prev_old = 0, prev_new = 0, bottom_score = k + 1;
     bool prev_valid = false;
@@ -548,6 +681,9 @@ MTSV_HD uint32_t myers_bounded(uint32_t L, uint32_t T, uint32_t k, PeqF peq, Tex
           uint64_t Ph, Mh;
           prev_old = bs[w];
           myers_block(Eq, Pv[w], Mv[w], phin, mhin, Ph, Mh);
+#ifdef MTSV_COUNT_BLOCKS
+          ++g_myers_blocks;
+#endif
           const uint32_t bit = w == nb ? sbit : 63u;
           bs[w] += (uint32_t)((Ph >> bit) & 1);
           bs[w] -= (uint32_t)((Mh >> bit) & 1);

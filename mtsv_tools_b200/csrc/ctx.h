@@ -115,7 +115,9 @@ struct BatchWorkspace {
   // per seed hit
   DevBuf hit_keys, cand_sparse, rank_keys;
   // per candidate (dense)
-  DevBuf cand_dense, cand_q, cand_edit, hit_tmp;
+  DevBuf cand_dense, cand_q, cand_edit, hit_tmp, cand_flag, cand_order;
+  // bit-plane encoded reads of the sub-batch
+  DevBuf enc;
   // scan scratch, counters, worklists
   DevBuf scan_tmp, counters, worklist;
   // per sub-batch results before concatenation

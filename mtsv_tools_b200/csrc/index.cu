@@ -5,6 +5,7 @@
 #include <errno.h>
 #include <fcntl.h>
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 #include <sys/mman.h>
 #include <sys/stat.h>
@@ -189,16 +190,18 @@ __global__ void sa_densify_kernel(FmView fm, const uint64_t* __restrict__ sample
 // kernel A4: k-mer interval table, built level by level: interval(c.X) = step(interval(X), c)
 // ---------------------------------------------------------------------------------------------
 __global__ void ktab_level_kernel(FmView fm, const uint2* __restrict__ cur, uint2* __restrict__ next,
-                                  uint64_t cur_size) {
-  uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= cur_size * 4) return;
-  uint32_t c = (uint32_t)(t / cur_size);
-  uint64_t x = t % cur_size;
-  uint2 e = cur[x];
+                                  uint32_t t /* length of the k-mers in `next` */) {
+  // key of a t-mer = lo | hi << t (base j at bit j).  c.X prepends base c: X's planes shift up by one.
+  uint64_t key = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (key >= (1ull << (2 * t))) return;
+  uint64_t lo = key & ((1ull << t) - 1), hi = key >> t;
+  uint32_t c = (uint32_t)(lo & 1) | ((uint32_t)(hi & 1) << 1);
+  uint64_t prev = (lo >> 1) | ((hi >> 1) << (t - 1));
+  uint2 e = cur[prev];
   uint32_t l = e.x, u = e.y;
   if (l < u) fm_step(fm, c, l, u);
   if (l >= u) l = u = 0;
-  next[t] = make_uint2(l, u);
+  next[key] = make_uint2(l, u);
 }
 
 __global__ void ktab_init_kernel(uint2* cur, uint32_t n) { cur[0] = make_uint2(0, n); }
@@ -300,6 +303,10 @@ int index_from_host_parts(const uint8_t* text, uint64_t n, const mtsvgpu_bin* bi
   }
   if (device < 0 || device >= ndev) return set_error(MTSVGPU_EINVAL, "device %d out of range", device);
   MTSV_CUDA_TRY(cudaSetDevice(device));
+  if (const char* g = getenv("MTSV_B200_L2_FETCH")) {  // experiment knob: L2 fetch granularity hint
+    cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(g));
+    (void)cudaGetLastError();
+  }
 
   mtsvgpu_index* h = new mtsvgpu_index;
   if (opts) h->opts = *opts;
@@ -454,7 +461,7 @@ int index_from_host_parts(const uint8_t* text, uint64_t n, const mtsvgpu_bin* bi
       for (uint32_t lev = 1; lev <= kk; ++lev) {
         uint64_t threads = cur_size * 4;
         MTSV_LAUNCH(ktab_level_kernel, (unsigned)((threads + 255) / 256), 256, 0, st, d.fm_view(),
-                    bufs[cur], bufs[cur ^ 1], cur_size);
+                    bufs[cur], bufs[cur ^ 1], lev);
         cur ^= 1;
         cur_size *= 4;
       }

@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <vector>
 
+#define MTSV_COUNT_BLOCKS 1
 #include "../../mtsv_tools_b200/csrc/core.cuh"
 
 using namespace mtsv;
@@ -123,20 +124,22 @@ void* emul_index_build(const uint8_t* text, uint64_t n, const emul_bin* bins, ui
   }
   e->sv.sa = e->sa.data();
   e->sv.rate = sa_rate;
-  // k-mer table, level by level like ktab_level_kernel
+  // k-mer table, level by level like ktab_level_kernel (key = lo | hi << t, base j at bit j)
   if (ktab_k) {
     std::vector<uint2> cur(1), next;
     cur[0].x = 0;
     cur[0].y = (uint32_t)n;
-    for (uint32_t lev = 1; lev <= ktab_k; ++lev) {
-      next.resize(cur.size() * 4);
-      for (uint64_t t = 0; t < next.size(); ++t) {
-        uint32_t c = (uint32_t)(t / cur.size());
-        uint32_t l = cur[t % cur.size()].x, u = cur[t % cur.size()].y;
+    for (uint32_t t = 1; t <= ktab_k; ++t) {
+      next.resize(1ull << (2 * t));
+      for (uint64_t key = 0; key < next.size(); ++key) {
+        uint64_t lo = key & ((1ull << t) - 1), hi = key >> t;
+        uint32_t c = (uint32_t)(lo & 1) | ((uint32_t)(hi & 1) << 1);
+        uint64_t prev = (lo >> 1) | ((hi >> 1) << (t - 1));
+        uint32_t l = cur[prev].x, u = cur[prev].y;
         if (l < u) fm_step(e->fm, c, l, u);
         if (l >= u) l = u = 0;
-        next[t].x = l;
-        next[t].y = u;
+        next[key].x = l;
+        next[key].y = u;
       }
       cur.swap(next);
     }
@@ -157,9 +160,20 @@ uint32_t emul_locate(void* p, uint32_t row) {
   EmulIndex* e = (EmulIndex*)p;
   return fm_locate(e->fm, e->sv, row, nullptr);
 }
+static std::vector<ReadWord> encode_query(const uint8_t* seq, uint32_t L, bool rc, bool raw) {
+  uint32_t W = (L + 63) / 64;
+  std::vector<ReadWord> fwd(W ? W : 1, ReadWord{0, 0, 0});
+  for (uint32_t w = 0; w < W; ++w) fwd[w] = encode_fwd_word(seq, L, w, raw);
+  if (!rc) return fwd;
+  std::vector<ReadWord> out(W ? W : 1, ReadWord{0, 0, 0});
+  for (uint32_t w = 0; w < W; ++w) out[w] = encode_rc_word(fwd.data(), L, w);
+  return out;
+}
+
 void emul_backward_search(void* p, const uint8_t* pat, uint32_t len, uint32_t* lo, uint32_t* cnt) {
   EmulIndex* e = (EmulIndex*)p;
-  seed_search_item(e->fm, e->kt, pat, 0, len, len, 0, lo, cnt, nullptr);
+  std::vector<ReadWord> q = encode_query(pat, len, false, false);
+  seed_search_item(e->fm, e->kt, q.data(), len, len, 0, lo, cnt, nullptr);
 }
 
 // Myers recurrence exactly as verify_kernel evaluates it (ncls = 4: binner rule, 5: raw bytes)
@@ -167,21 +181,12 @@ uint32_t emul_edit_distance_k(const uint8_t* pat, uint32_t L, uint32_t rc, const
                               int ncls, uint32_t k) {
   if (L == 0) return 0;
   if (L > 1024) return 0xffffffffu;
+  // pattern masks from the bit planes, as verify_kernel builds them
+  std::vector<ReadWord> q = encode_query(pat, L, rc != 0, ncls == 5);
   uint64_t peq[5][16];
   memset(peq, 0, sizeof peq);
-  for (uint32_t i = 0; i < L; ++i) {
-    uint8_t byte = rc ? pat[L - 1 - i] : pat[i];
-    uint32_t c;
-    if (ncls == 4) {
-      c = read_code(byte);
-      if (rc) c = comp_code(c);
-      if (c > 3) continue;
-    } else {
-      c = text_code(byte);
-      if (c > SYM_N) continue;
-    }
-    peq[c][i >> 6] |= 1ull << (i & 63);
-  }
+  for (uint32_t w = 0; w < (L + 63) / 64; ++w)
+    for (int c = 0; c < ncls; ++c) peq[c][w] = word_peq(q[w], c);
   auto pf = [&](uint32_t c, int w) { return peq[c][w]; };
   auto tf = [&](uint32_t j) {
     uint32_t c = text_code(txt[j]);
@@ -216,12 +221,13 @@ int emul_bin_reads(void* p, const uint8_t* seqs, const uint64_t* seq_off, uint64
   for (uint32_t q = 0; q < nq; ++q) {
     if (q % prm.ns == 0) offs[q / prm.ns] = all.size();
     uint32_t L = query_len(rv, prm.ns, q);
-    const uint8_t* seq = query_seq(rv, prm.ns, q);
+    const uint8_t* seq = seqs + seq_off[q / prm.ns];
     uint32_t rc = q % prm.ns;
+    std::vector<ReadWord> qwords = encode_query(seq, L, rc != 0, false);
     uint32_t nslots = seed_slots(L, prm.S, prm.G);
     std::vector<uint32_t> lo(nslots), cnt(nslots), hoff(nslots);
     for (uint32_t j = 0; j < nslots; ++j)
-      seed_search_item(e->fm, e->kt, seq, rc, L, prm.S, j * prm.G, &lo[j], &cnt[j], nullptr);
+      seed_search_item(e->fm, e->kt, qwords.data(), L, prm.S, j * prm.G, &lo[j], &cnt[j], nullptr);
     uint32_t nseeds = 0, nhits = 0, ovf = 0;
     seed_select_item(prm, nslots, cnt.data(), hoff.data(), &nseeds, &nhits, &ovf);
     if (ovf) return -7;
@@ -264,5 +270,11 @@ int emul_bin_reads(void* p, const uint8_t* seqs, const uint64_t* seq_off, uint64
 }
 
 void emul_free(void* p) { free(p); }
+
+void emul_myers_counters(unsigned long long* blocks, unsigned long long* cols, int reset) {
+  *blocks = mtsv::g_myers_blocks;
+  *cols = mtsv::g_myers_cols;
+  if (reset) mtsv::g_myers_blocks = mtsv::g_myers_cols = 0;
+}
 
 }  // extern "C"

@@ -1,17 +1,19 @@
 #!/bin/bash
 # Runs on the GPU box (via gpurun): plain bench first, then ncu passes of the same command.
-# Outputs land in gpurun_out/ (copied to profiles/ by hand after reading them).
+# Usage: tools/profile.sh [kernel ...]   (default: launch list + verify_kernel + seed_search_kernel)
 set -u
 CMD="python bench.py --steps 1 --warmup 3 --no-cpu-baseline --parity-reads 20000"
 OUT=gpurun_out
 mkdir -p $OUT
+MYK='regex:^(count_slots|expand_slots|seed_search|seed_select|locate|sort_small|sort_medium|sort_large|coalesce|rank_emit|verify|select|gather_hits)_kernel|^scan_(tile_sums|sums_inplace|apply|empty)'
 $CMD > $OUT/prof_plain.json 2> $OUT/prof_plain.log || { echo "plain run failed"; tail -5 $OUT/prof_plain.log; exit 1; }
-# launch list of one timed step (my kernels only; 56 launches x 10 sub-batches per step)
-ncu --metrics gpu__time_duration.sum --clock-control none -k regex:mtsv -s 1760 -c 620 --csv \
+# launch list of one timed step (this library's kernels only; ~58 launches x 10 sub-batches per step;
+# the first 58 are the parity gate, then 3 warm-up steps)
+ncu --metrics gpu__time_duration.sum --clock-control none -k "$MYK" -s 1800 -c 580 --csv \
     --log-file $OUT/launches.csv $CMD > $OUT/ncu_launches.log 2>&1
-# full captures of the heaviest kernels
-for K in verify_kernel seed_search_kernel coalesce_kernel select_kernel; do
-  ncu --set full --clock-control none --import-source on -k regex:$K -s 32 -c 2 -f -o $OUT/prof_$K \
+KERNELS="${@:-verify_kernel seed_search_kernel}"
+for K in $KERNELS; do
+  ncu --set full --clock-control none --import-source on -k regex:^$K -s 32 -c 2 -f -o $OUT/prof_$K \
       $CMD > $OUT/ncu_$K.log 2>&1
 done
-ls -la $OUT
+ls -la $OUT | head -30
