@@ -67,14 +67,34 @@ __global__ void expand_slots_kernel(const uint32_t* __restrict__ slot_off, uint3
 // 24 B per 64 bases and strand.
 __global__ void __launch_bounds__(256) encode_fwd_kernel(ReadsView rv, ReadWord* __restrict__ words,
                                                          uint32_t w_max, int raw) {
-  uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  // one warp per (read, word): two coalesced 32-byte loads, the planes come out of warp ballots
+  uint64_t t = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const unsigned lane = threadIdx.x & 31;
   uint32_t r = (uint32_t)(t / w_max), w = (uint32_t)(t % w_max);
   if (r >= rv.n_reads) return;
   uint64_t a = rv.seq_off[rv.read0 + r], b = rv.seq_off[rv.read0 + r + 1];
   uint32_t L = (uint32_t)(b - a);
   if (w * 64 >= L) return;
-  uint32_t woff = (uint32_t)((a - rv.seq_off[rv.read0]) >> 6) + r;
-  words[woff + w] = encode_fwd_word(rv.seqs + a, L, w, raw != 0);
+  const uint8_t* seq = rv.seqs + a;
+  ReadWord out{0, 0, 0};
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    uint32_t pos = w * 64 + half * 32 + lane;
+    bool in = pos < L;
+    uint8_t byte = in ? __ldg(seq + pos) : (uint8_t)'A';
+    uint32_t c = raw ? text_code(byte) : read_code(byte);
+    bool is_base = c < 4;
+    uint32_t lo = __ballot_sync(0xffffffffu, in && ((is_base && (c & 1)) || (raw && c > 4)));
+    uint32_t hi = __ballot_sync(0xffffffffu, in && is_base && (c & 2));
+    uint32_t nn = __ballot_sync(0xffffffffu, in && !is_base);
+    out.lo |= (uint64_t)lo << (32 * half);
+    out.hi |= (uint64_t)hi << (32 * half);
+    out.nn |= (uint64_t)nn << (32 * half);
+  }
+  if (lane == 0) {
+    uint32_t woff = (uint32_t)((a - rv.seq_off[rv.read0]) >> 6) + r;
+    words[woff + w] = out;
+  }
 }
 
 __global__ void __launch_bounds__(256) encode_rc_kernel(ReadsView rv, ReadWord* __restrict__ words,
@@ -862,8 +882,8 @@ static int run_sub_batch(mtsvgpu_index* h, const Params& p, const uint8_t* d_seq
   {
     const uint32_t w_max = hc.max_len ? (hc.max_len + 63) / 64 : 1;
     const uint64_t threads = (uint64_t)n_reads * w_max;
-    MTSV_LAUNCH(encode_fwd_kernel, (unsigned)((threads + 255) / 256), 256, 0, st, rv, ws.enc.as<ReadWord>(),
-                w_max, 0);
+    MTSV_LAUNCH(encode_fwd_kernel, (unsigned)((threads * 32 + 255) / 256), 256, 0, st, rv,
+                ws.enc.as<ReadWord>(), w_max, 0);
     if (p.ns == 2)
       MTSV_LAUNCH(encode_rc_kernel, (unsigned)((threads + 255) / 256), 256, 0, st, rv, ws.enc.as<ReadWord>(),
                   total_words, w_max);
@@ -1109,7 +1129,7 @@ int backward_search_batch(mtsvgpu_index* h, const uint8_t* pats, uint32_t pat_le
     ReadsView pv{dp.as<uint8_t>(), doff.as<uint64_t>(), 0, (uint32_t)n_pats};
     EncView ev{dw.as<ReadWord>(), total_words};
     const uint64_t threads = n_pats * w_max;
-    MTSV_LAUNCH(encode_fwd_kernel, (unsigned)((threads + 255) / 256), 256, 0, st, pv, dw.as<ReadWord>(), w_max, 0);
+    MTSV_LAUNCH(encode_fwd_kernel, (unsigned)((threads * 32 + 255) / 256), 256, 0, st, pv, dw.as<ReadWord>(), w_max, 0);
     MTSV_LAUNCH(bs_patterns_kernel, (unsigned)((n_pats + 127) / 128), 128, 0, st, h->ix.fm_view(),
                 h->ix.ktab_view(), pv, ev, pat_len, n_pats, dl.as<uint64_t>(), du.as<uint64_t>());
     cudaMemcpyAsync(lower, dl.p, n_pats * 8, cudaMemcpyDeviceToHost, st);
@@ -1193,7 +1213,7 @@ int edit_distance_batch(int device, const uint8_t* pats, const uint64_t* pat_off
     ReadsView pv{dp.as<uint8_t>(), dpo.as<uint64_t>(), 0, (uint32_t)n_pairs};
     EncView ev{dw.as<ReadWord>(), total_words};
     const uint64_t threads = n_pairs * w_max;
-    MTSV_LAUNCH(encode_fwd_kernel, (unsigned)((threads + 255) / 256), 256, 0, 0, pv, dw.as<ReadWord>(), w_max, 1);
+    MTSV_LAUNCH(encode_fwd_kernel, (unsigned)((threads * 32 + 255) / 256), 256, 0, 0, pv, dw.as<ReadWord>(), w_max, 1);
     PairJobs jobs{pv, ev, dt.as<uint8_t>(), dto.as<uint64_t>(), (uint32_t)n_pairs};
     if ((rc = launch_verify<5>(jobs, std::max(max_len, 1u), de.as<uint32_t>(), nullptr, 0))) break;
     cudaError_t e = cudaMemcpy(edits, de.p, n_pairs * 4, cudaMemcpyDeviceToHost);
