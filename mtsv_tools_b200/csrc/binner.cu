@@ -28,8 +28,19 @@ constexpr uint32_t kMaxReadLenDev = 1024;  // longer reads fail the batch (ELIMI
 struct BatchCounters {  // device-side scalars of one sub-batch
   unsigned long long total_slots, total_hits, total_cands, total_out;
   unsigned int max_len, overflow, n_medium, n_large, bad_offsets, reserved0;
-  unsigned long long rank_steps, window_bytes;
+  unsigned long long rank_steps[32], window_bytes[32];  // profiling only; spread to avoid one hot address
 };
+
+// adds `v` of every thread of the CTA into one of 32 counters with a single global atomic per CTA
+__device__ __forceinline__ void cta_accumulate(unsigned long long* counters32, unsigned int v) {
+  __shared__ unsigned int cta_sum;
+  if (threadIdx.x == 0) cta_sum = 0;
+  __syncthreads();
+  unsigned int w = __reduce_add_sync(0xffffffffu, v);
+  if ((threadIdx.x & 31) == 0 && w) atomicAdd(&cta_sum, w);
+  __syncthreads();
+  if (threadIdx.x == 0 && cta_sum) atomicAdd(&counters32[blockIdx.x & 31], (unsigned long long)cta_sum);
+}
 
 __global__ void count_slots_kernel(ReadsView rv, Params p, uint32_t nq, uint32_t* __restrict__ q_nslots,
                                    BatchCounters* __restrict__ ctr) {
@@ -129,10 +140,7 @@ __global__ void __launch_bounds__(256) seed_search_kernel(FmView fm, KtabView kt
     slot_lo[s] = lo;
     slot_cnt[s] = cnt;
   }
-  if (count_ranks) {
-    unsigned int w = __reduce_add_sync(0xffffffffu, steps);
-    if ((threadIdx.x & 31) == 0 && w) atomicAdd(&ctr->rank_steps, (unsigned long long)w);
-  }
+  if (count_ranks) cta_accumulate(ctr->rank_steps, steps);
 }
 
 __global__ void seed_select_kernel(Params p, const uint32_t* __restrict__ slot_off, uint32_t nq,
@@ -574,7 +582,6 @@ __global__ void __launch_bounds__(kVerifyThreads) verify_kernel(Jobs jobs, uint3
   auto peq_f = [&](uint32_t c, int w) -> uint64_t { return peq[(c * W + w) * kVerifyThreads + threadIdx.x]; };
   const uint32_t best = myers_bounded<W>(L, T, job.limit, peq_f, text);
   out[job.out] = best <= job.limit ? best : kNoEdit;
-  if (ctr) atomicAdd(&ctr->window_bytes, (unsigned long long)T);
 }
 
 template <int NCLS, typename Jobs>
@@ -712,9 +719,16 @@ __global__ void __launch_bounds__(256) gather_hits_kernel(uint32_t nq, uint32_t 
 }
 
 // verification order: multi-seed candidates first, single-seed ones after (stable within each class)
-__global__ void cand_class_kernel(const CandRec* __restrict__ cand, uint32_t n, uint32_t* __restrict__ flag) {
+__global__ void cand_class_kernel(const CandRec* __restrict__ cand, uint32_t n, uint32_t* __restrict__ flag,
+                                  BatchCounters* __restrict__ ctr) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) flag[i] = cand[i].num_seeds > 1 ? 1u : 0u;
+  uint32_t wbytes = 0;
+  if (i < n) {
+    CandRec c = cand[i];
+    flag[i] = c.num_seeds > 1 ? 1u : 0u;
+    wbytes = c.end - c.start;
+  }
+  if (ctr) cta_accumulate(ctr->window_bytes, wbytes);  // profiling: reference bytes the verifier reads
 }
 
 __global__ void cand_order_kernel(const CandRec* __restrict__ cand, const uint32_t* __restrict__ multi_before,
@@ -918,7 +932,7 @@ static int run_sub_batch(mtsvgpu_index* h, const Params& p, const uint8_t* d_seq
   }
   const uint32_t n_hits = (uint32_t)hc.total_hits;
   h->stats.n_seed_hits += n_hits;
-  h->stats.rank_queries += hc.rank_steps;  // sectors touched by seed search (profiling only)
+  for (int i = 0; i < 32; ++i) h->stats.rank_queries += hc.rank_steps[i];  // sectors touched by seed search
 
   uint64_t sub_out = 0;
   uint32_t n_cand = 0;
@@ -969,7 +983,7 @@ static int run_sub_batch(mtsvgpu_index* h, const Params& p, const uint8_t* d_seq
     MTSV_TRY(ws.cand_flag.reserve(((size_t)n_cand + 1) * 4));
     MTSV_TRY(ws.cand_order.reserve((size_t)n_cand * 4));
     MTSV_LAUNCH(cand_class_kernel, (n_cand + 255) / 256, 256, 0, st, ws.cand_dense.as<CandRec>(), n_cand,
-                ws.cand_flag.as<uint32_t>());
+                ws.cand_flag.as<uint32_t>(), h->profiling ? d_ctr : nullptr);
     MTSV_TRY(exclusive_scan_u32(ws.cand_flag.as<uint32_t>(), ws.cand_flag.as<uint32_t>(), n_cand, ws.scan_tmp,
                                 nullptr, st));
     MTSV_LAUNCH(cand_order_kernel, (n_cand + 255) / 256, 256, 0, st, ws.cand_dense.as<CandRec>(),
@@ -990,7 +1004,7 @@ static int run_sub_batch(mtsvgpu_index* h, const Params& p, const uint8_t* d_seq
     MTSV_CUDA_TRY(cudaMemcpyAsync(&hc, d_ctr, sizeof hc, cudaMemcpyDeviceToHost, st));
     MTSV_CUDA_TRY(cudaStreamSynchronize(st));
     sub_out = hc.total_out;
-    h->stats.window_bytes += hc.window_bytes;
+    for (int i = 0; i < 32; ++i) h->stats.window_bytes += hc.window_bytes[i];
   } else {
     MTSV_CUDA_TRY(cudaMemsetAsync(ws.out_off.p, 0, qn * 4, st));
     MTSV_CUDA_TRY(cudaMemsetAsync(ws.cand_off.p, 0, qn * 4, st));

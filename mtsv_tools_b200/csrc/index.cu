@@ -252,10 +252,13 @@ void index_destroy(mtsvgpu_index* h) {
 }
 
 static uint32_t auto_ktab_k(uint64_t n) {
-  // largest k with 4^k <= n, minus nothing: table entries ~ n/4 .. n; clamp to [1, 14]
+  // floor(log4 n) + 2, clamped to [1, 16]: with ~n/16 expected chance matches per key most seeds that do
+  // not occur in the reference die at the table lookup itself (one DRAM line instead of ~4 rank steps);
+  // the caller shrinks k until the table fits a third of the free memory.
   uint32_t k = 0;
   while (k < 16 && (1ull << (2 * (k + 1))) <= n) ++k;
-  if (k > 14) k = 14;
+  k += 2;
+  if (k > 16) k = 16;
   if (k < 1) k = 1;
   return k;
 }
