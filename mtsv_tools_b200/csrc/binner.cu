@@ -27,7 +27,7 @@ constexpr uint32_t kMaxReadLenDev = 1024;  // longer reads fail the batch (ELIMI
 
 struct BatchCounters {  // device-side scalars of one sub-batch
   unsigned long long total_slots, total_hits, total_cands, total_out;
-  unsigned int max_len, overflow, n_medium, n_large, bad_offsets, reserved0;
+  unsigned int max_len, overflow, n_warp, n_medium, n_large, bad_offsets;
   unsigned long long rank_steps[32], window_bytes[32];  // profiling only; spread to avoid one hot address
 };
 
@@ -120,6 +120,44 @@ __global__ void __launch_bounds__(256) encode_rc_kernel(ReadsView rv, ReadWord* 
   words[total_words + woff + w] = encode_rc_word(words + woff, L, w);
 }
 
+// both strands of a read by one warp: forward words from two coalesced 32-byte loads + ballots each,
+// kept in shared memory, then lanes 0..W-1 derive the reverse-complement words from them.
+// (reads are at most kMaxReadLenDev = 1024 bases here: 16 words)
+__global__ void __launch_bounds__(256) encode_reads_kernel(ReadsView rv, ReadWord* __restrict__ words,
+                                                           uint32_t total_words, uint32_t ns) {
+  __shared__ ReadWord fw[8][16];
+  const unsigned lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (r >= rv.n_reads) return;
+  const uint64_t a = rv.seq_off[rv.read0 + r], b = rv.seq_off[rv.read0 + r + 1];
+  const uint32_t L = (uint32_t)(b - a);
+  const uint32_t W = (L + 63) >> 6;
+  const uint32_t woff = (uint32_t)((a - rv.seq_off[rv.read0]) >> 6) + r;
+  const uint8_t* seq = rv.seqs + a;
+  for (uint32_t w = 0; w < W; ++w) {
+    ReadWord out{0, 0, 0};
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      uint32_t pos = w * 64 + half * 32 + lane;
+      bool in = pos < L;
+      uint32_t c = read_code(in ? __ldg(seq + pos) : (uint8_t)'A');
+      bool is_base = c < 4;
+      uint32_t lo = __ballot_sync(0xffffffffu, in && is_base && (c & 1));
+      uint32_t hi = __ballot_sync(0xffffffffu, in && is_base && (c & 2));
+      uint32_t nn = __ballot_sync(0xffffffffu, in && !is_base);
+      out.lo |= (uint64_t)lo << (32 * half);
+      out.hi |= (uint64_t)hi << (32 * half);
+      out.nn |= (uint64_t)nn << (32 * half);
+    }
+    if (lane == 0) {
+      words[woff + w] = out;
+      fw[wib][w] = out;
+    }
+  }
+  __syncwarp();
+  if (ns == 2 && lane < W) words[total_words + woff + lane] = encode_rc_word(fw[wib], L, lane);
+}
+
 // seed search: one thread per slot.  Each thread owns one dependent chain of sector fetches;
 // ~2048 chains per SM keep the HBM random-access pipeline full.
 __global__ void __launch_bounds__(256) seed_search_kernel(FmView fm, KtabView kt, ReadsView rv, EncView ev, Params p,
@@ -207,6 +245,7 @@ __global__ void __launch_bounds__(256) locate_kernel(FmView fm, SaView sv, Param
 //   larger     : one CTA, in place in global memory (rare: > 4096 seed hits for one read-strand)
 // ------------------------------------------------------------------------------------------
 constexpr uint32_t kSortMedium = 4096;
+constexpr uint32_t kLightItems = 16;  // segments this small are ordered by their consumer's own lane
 
 __device__ __forceinline__ uint64_t warp_sort_u64(uint64_t v, unsigned lane) {
 #pragma unroll
@@ -226,25 +265,46 @@ __device__ __forceinline__ uint64_t warp_sort_u64(uint64_t v, unsigned lane) {
   return v;
 }
 
-__global__ void __launch_bounds__(256) sort_small_kernel(uint64_t* __restrict__ keys,
-                                                         const uint32_t* __restrict__ seg_off,
-                                                         const uint32_t* __restrict__ seg_cnt, uint32_t nq,
-                                                         uint32_t* __restrict__ medium_list,
-                                                         uint32_t* __restrict__ large_list,
-                                                         BatchCounters* __restrict__ ctr) {
-  uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+// Segments are classified once (warp-aggregated appends to three work lists); segments of at most
+// `min_count` keys are left to their consumer (the per-lane paths of coalesce / rank_emit order a
+// handful of keys themselves, which beats launching a warp per query).
+__global__ void __launch_bounds__(256) sort_classify_kernel(const uint32_t* __restrict__ seg_cnt, uint32_t nq,
+                                                            uint32_t min_count, uint32_t* __restrict__ warp_list,
+                                                            uint32_t* __restrict__ medium_list,
+                                                            uint32_t* __restrict__ large_list,
+                                                            BatchCounters* __restrict__ ctr) {
+  uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
   const unsigned lane = threadIdx.x & 31;
-  if (q >= nq) return;
-  uint32_t n = seg_cnt[q];
-  if (n < 2) return;
-  if (n <= 32) {
+  uint32_t n = q < nq ? seg_cnt[q] : 0;
+  int cls = n <= min_count || n < 2 ? -1 : (n <= 32 ? 0 : (n <= kSortMedium ? 1 : 2));
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    unsigned m = __ballot_sync(0xffffffffu, cls == c);
+    if (!m) continue;
+    unsigned int* counter = c == 0 ? &ctr->n_warp : (c == 1 ? &ctr->n_medium : &ctr->n_large);
+    uint32_t* list = c == 0 ? warp_list : (c == 1 ? medium_list : large_list);
+    uint32_t base = 0;
+    if (lane == (unsigned)(__ffs(m) - 1)) base = atomicAdd(counter, (unsigned)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+    if (cls == c) list[base + __popc(m & ((1u << lane) - 1))] = q;
+  }
+}
+
+__global__ void __launch_bounds__(256) sort_warp_kernel(uint64_t* __restrict__ keys,
+                                                        const uint32_t* __restrict__ seg_off,
+                                                        const uint32_t* __restrict__ seg_cnt,
+                                                        const uint32_t* __restrict__ list,
+                                                        const BatchCounters* __restrict__ ctr) {
+  const unsigned lane = threadIdx.x & 31;
+  const uint32_t n_list = ctr->n_warp;
+  const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t it = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; it < n_list; it += warps) {
+    uint32_t q = list[it];
+    uint32_t n = seg_cnt[q];
     uint64_t* base = keys + seg_off[q];
     uint64_t v = lane < n ? base[lane] : ~0ull;
     v = warp_sort_u64(v, lane);
     if (lane < n) base[lane] = v;
-  } else if (lane == 0) {
-    if (n <= kSortMedium) medium_list[atomicAdd(&ctr->n_medium, 1u)] = q;
-    else large_list[atomicAdd(&ctr->n_large, 1u)] = q;
   }
 }
 
@@ -341,7 +401,6 @@ __global__ void __launch_bounds__(1024) sort_large_kernel(uint64_t* __restrict__
 // Queries with few items are handled by their own lane; a query with many items (a read whose seeds
 // hit thousands of loci) is handled by the whole warp so that one heavy read does not serialise 31
 // idle lanes behind it.  Heavy queries are taken one after the other (ballot loop).
-constexpr uint32_t kLightItems = 16;
 
 // coalesce_seed_sites (src/index.rs:435-487) with the warp: lanes compute bins and windows of 32
 // hits at a time, then every lane replays the (cheap, inherently sequential) merge automaton on the
@@ -403,7 +462,7 @@ __global__ void __launch_bounds__(128) coalesce_kernel(BinsView bv, ReadsView rv
                                                        const uint32_t* __restrict__ hit_off,
                                                        const uint32_t* __restrict__ q_nhits,
                                                        const uint32_t* __restrict__ q_nseeds,
-                                                       const uint64_t* __restrict__ hit_keys,
+                                                       uint64_t* __restrict__ hit_keys,
                                                        CandRec* __restrict__ cand_sparse,
                                                        uint64_t* __restrict__ rank_keys,
                                                        uint32_t* __restrict__ q_ncand) {
@@ -416,8 +475,20 @@ __global__ void __launch_bounds__(128) coalesce_kernel(BinsView bv, ReadsView rv
     k = edit_budget(L, p.edit_rate);
     ms = min_seeds_of(q_nseeds[q], p.min_seed);
     base = hit_off[q];
-    if (nh <= kLightItems)
-      nc = coalesce_item(bv, hit_keys + base, nh, ms, L, k, cand_sparse + base, rank_keys + base);
+    if (nh <= kLightItems) {
+      // few hits: this lane orders them itself (they arrive seed by seed, i.e. almost sorted)
+      uint64_t* kq = hit_keys + base;
+      for (uint32_t i = 1; i < nh; ++i) {
+        uint64_t v = kq[i];
+        uint32_t j = i;
+        while (j > 0 && kq[j - 1] > v) {
+          kq[j] = kq[j - 1];
+          --j;
+        }
+        kq[j] = v;
+      }
+      nc = coalesce_item(bv, kq, nh, ms, L, k, cand_sparse + base, rank_keys + base);
+    }
   }
   unsigned heavy = __ballot_sync(0xffffffffu, nh > kLightItems);
   while (heavy) {
@@ -447,12 +518,22 @@ __global__ void __launch_bounds__(256) rank_emit_kernel(uint32_t nq, const uint3
   if (nc) {
     src = hit_off[q];
     dst = cand_off[q];
-    if (nc <= kLightItems)
+    if (nc <= kLightItems) {
+      // few candidates: emit them in (num_seeds desc, discovery order) by repeated selection — the
+      // rank keys were not sorted for such a segment (src/index.rs:369 is a stable sort)
+      uint64_t prev = 0;
       for (uint32_t i = 0; i < nc; ++i) {
-        uint32_t idx = (uint32_t)(rank_keys[src + i] & 0xffffffffu);
+        uint64_t best = ~0ull;
+        for (uint32_t j = 0; j < nc; ++j) {
+          uint64_t kj = rank_keys[src + j];
+          if ((i == 0 || kj > prev) && kj < best) best = kj;
+        }
+        prev = best;
+        uint32_t idx = (uint32_t)(best & 0xffffffffu);
         cand_dense[dst + i] = cand_sparse[src + idx];
         cand_q[dst + i] = q;
       }
+    }
   }
   unsigned heavy = __ballot_sync(0xffffffffu, nc > kLightItems);
   while (heavy) {
@@ -799,15 +880,19 @@ struct StageClock {
   }
 };
 
-static int run_segmented_sort(mtsvgpu_index* h, uint64_t* keys, const uint32_t* seg_off,
-                              const uint32_t* seg_cnt, uint32_t nq, BatchCounters* d_ctr) {
-  cudaStream_t st = h->stream;
-  uint32_t* lists = h->ws.worklist.as<uint32_t>();
-  MTSV_CUDA_TRY(cudaMemsetAsync(&d_ctr->n_medium, 0, 2 * sizeof(unsigned int), st));
-  unsigned grid = (unsigned)(((uint64_t)nq * 32 + 255) / 256);
-  MTSV_LAUNCH(sort_small_kernel, grid, 256, 0, st, keys, seg_off, seg_cnt, nq, lists, lists + nq, d_ctr);
-  MTSV_LAUNCH(sort_medium_kernel, 148 * 4, 512, 0, st, keys, seg_off, seg_cnt, lists, d_ctr);
-  MTSV_LAUNCH(sort_large_kernel, 148, 1024, 0, st, keys, seg_off, seg_cnt, lists + nq, d_ctr);
+static int run_segmented_sort(cudaStream_t st, DevBuf& worklist, uint64_t* keys, const uint32_t* seg_off,
+                              const uint32_t* seg_cnt, uint32_t nq, uint32_t min_count, BatchCounters* d_ctr) {
+  if (worklist.cap < (size_t)3 * nq * 4) {
+    MTSV_CUDA_TRY(cudaStreamSynchronize(st));
+    MTSV_TRY(worklist.reserve((size_t)3 * nq * 4));
+  }
+  uint32_t* lists = worklist.as<uint32_t>();
+  MTSV_CUDA_TRY(cudaMemsetAsync(&d_ctr->n_warp, 0, 3 * sizeof(unsigned int), st));
+  MTSV_LAUNCH(sort_classify_kernel, (nq + 255) / 256, 256, 0, st, seg_cnt, nq, min_count, lists, lists + nq,
+              lists + 2 * (size_t)nq, d_ctr);
+  MTSV_LAUNCH(sort_warp_kernel, 148 * 8, 256, 0, st, keys, seg_off, seg_cnt, lists, d_ctr);
+  MTSV_LAUNCH(sort_medium_kernel, 148 * 4, 512, 0, st, keys, seg_off, seg_cnt, lists + nq, d_ctr);
+  MTSV_LAUNCH(sort_large_kernel, 148, 1024, 0, st, keys, seg_off, seg_cnt, lists + 2 * (size_t)nq, d_ctr);
   MTSV_CUDA_TRY(cudaGetLastError());
   return 0;
 }
@@ -858,7 +943,7 @@ static int run_sub_batch(mtsvgpu_index* h, const Params& p, const uint8_t* d_seq
   MTSV_TRY(ws.cand_off.reserve(qn * 4));
   MTSV_TRY(ws.q_nout.reserve(qn * 4));
   MTSV_TRY(ws.out_off.reserve(qn * 4));
-  MTSV_TRY(ws.worklist.reserve(2 * qn * 4));
+  MTSV_TRY(ws.worklist.reserve(3 * qn * 4));
   MTSV_TRY(ws.slot_q.reserve((slot_bound + 1) * 4));
   MTSV_TRY(ws.slot_lo.reserve((slot_bound + 1) * 4));
   MTSV_TRY(ws.slot_cnt.reserve((slot_bound + 1) * 4));
@@ -893,15 +978,8 @@ static int run_sub_batch(mtsvgpu_index* h, const Params& p, const uint8_t* d_seq
   // (only now that the slot count is known to fit the buffers)
   clk.begin(ST_PREP);
   MTSV_LAUNCH(expand_slots_kernel, qgrid, 256, 0, st, slot_off, nq, ws.slot_q.as<uint32_t>());
-  {
-    const uint32_t w_max = hc.max_len ? (hc.max_len + 63) / 64 : 1;
-    const uint64_t threads = (uint64_t)n_reads * w_max;
-    MTSV_LAUNCH(encode_fwd_kernel, (unsigned)((threads * 32 + 255) / 256), 256, 0, st, rv,
-                ws.enc.as<ReadWord>(), w_max, 0);
-    if (p.ns == 2)
-      MTSV_LAUNCH(encode_rc_kernel, (unsigned)((threads + 255) / 256), 256, 0, st, rv, ws.enc.as<ReadWord>(),
-                  total_words, w_max);
-  }
+  MTSV_LAUNCH(encode_reads_kernel, (unsigned)(((uint64_t)n_reads * 32 + 255) / 256), 256, 0, st, rv,
+              ws.enc.as<ReadWord>(), total_words, p.ns);
   clk.end();
 
   // ---- seed search ----
@@ -948,8 +1026,8 @@ static int run_sub_batch(mtsvgpu_index* h, const Params& p, const uint8_t* d_seq
     clk.end();
     // ---- sort hits per query ----
     clk.begin(ST_SORT);
-    MTSV_TRY(run_segmented_sort(h, ws.hit_keys.as<uint64_t>(), ws.hit_off.as<uint32_t>(),
-                                ws.q_nhits.as<uint32_t>(), nq, d_ctr));
+    MTSV_TRY(run_segmented_sort(st, ws.worklist, ws.hit_keys.as<uint64_t>(), ws.hit_off.as<uint32_t>(),
+                                ws.q_nhits.as<uint32_t>(), nq, kLightItems, d_ctr));
     clk.end();
     // ---- coalesce ----
     clk.begin(ST_COALESCE);
@@ -972,8 +1050,8 @@ static int run_sub_batch(mtsvgpu_index* h, const Params& p, const uint8_t* d_seq
     MTSV_TRY(ws.hit_tmp.reserve((size_t)n_cand * sizeof(HitRec)));
     // ---- rank ----
     clk.begin(ST_RANK);
-    MTSV_TRY(run_segmented_sort(h, ws.rank_keys.as<uint64_t>(), ws.hit_off.as<uint32_t>(),
-                                ws.q_ncand.as<uint32_t>(), nq, d_ctr));
+    MTSV_TRY(run_segmented_sort(st, ws.worklist, ws.rank_keys.as<uint64_t>(), ws.hit_off.as<uint32_t>(),
+                                ws.q_ncand.as<uint32_t>(), nq, kLightItems, d_ctr));
     MTSV_LAUNCH(rank_emit_kernel, qgrid, 256, 0, st, nq, ws.hit_off.as<uint32_t>(),
                 ws.q_ncand.as<uint32_t>(), ws.cand_off.as<uint32_t>(), ws.rank_keys.as<uint64_t>(),
                 ws.cand_sparse.as<CandRec>(), ws.cand_dense.as<CandRec>(), ws.cand_q.as<uint32_t>());
