@@ -89,13 +89,14 @@ def get_index_parts(name, cfg, device, rank, world, barrier):
     """Build (GPU suffix sort) or load the cached MGIndex fields for the workload."""
     import torch
     from mtsv_tools_b200.build_index import build_index_parts
-    d = os.path.join(CACHE_DIR, "%s_seed3" % name)
+    seed = cfg.get("seed", 3)
+    d = os.path.join(CACHE_DIR, "%s_seed%d" % (name, seed))
     done = os.path.join(d, "DONE")
     if rank == 0 and not os.path.exists(done):
         t0 = time.time()
         os.makedirs(d, exist_ok=True)
         dev = device if torch.cuda.is_available() else "cpu"
-        cat, off, gi, tax = make_reference_torch(cfg, 3, dev)
+        cat, off, gi, tax = make_reference_torch(cfg, seed, dev)
         cat_np = cat.cpu().numpy()
         del cat
         if torch.cuda.is_available():
@@ -432,12 +433,92 @@ def run_gpu_arm(args, cfg, rank, world, local_rank):
     print(json.dumps(line), flush=True)
 
 
+def run_chunk_arm(args, cfg, rank, world, local_rank):
+    """BASELINE config 3, scaled: every rank holds a DIFFERENT ~1 Gbp chunk, every read visits every chunk,
+    per-read hit lists are exchanged over NCCL (all_to_all by read range) and merged on the device by the
+    mtsv-collapse rule (min edit per TaxID).  value = reads/s binned against ALL chunks."""
+    import torch
+    import torch.distributed as dist
+    from mtsv_tools_b200 import MGIndex, Params, synth, load_library, chunked
+
+    torch.cuda.set_device(local_rank)
+    dev = "cuda:%d" % local_rank
+    lib = load_library()
+    # each rank builds / loads its own chunk (seed 5 + rank), chunk 0 provides the reads for everybody
+    name = "%s_chunk%d" % (args.config, rank)
+    parts = get_index_parts(name, dict(cfg, seed=5 + rank), dev, 0, 1, lambda: None)
+    if world > 1:
+        dist.barrier()
+    parts0 = parts if rank == 0 else get_index_parts("%s_chunk0" % args.config, dict(cfg, seed=5), dev, 1, 1,
+                                                     lambda: None)
+    gix = MGIndex.from_parts(parts["text"], parts["bins"], parts["bwt"], parts["sa_sample"], 32, device=local_rank,
+                             sa_rate=args.sa_rate, ktab_k=args.ktab_k, batch_reads=args.batch_reads)
+    L = cfg["read_len"]
+    n_reads = args.reads or cfg["reads"]
+    ref_t = torch.from_numpy(parts0["text"][:-1]).to(dev)
+    d_reads = synth.make_reads_torch(ref_t, parts0["ref_off"], n_reads, L, 4, dev)
+    del ref_t
+    d_off = torch.arange(n_reads + 1, dtype=torch.int64, device=dev) * L
+    params = Params(**cfg["flags"])
+    stream = torch.cuda.current_stream()
+    gix.set_stream(stream.cuda_stream)
+
+    def step():
+        return chunked.bin_reads_chunk_sharded(gix, d_reads, d_off, n_reads, params, local_rank)
+
+    for _ in range(max(3, args.warmup)):
+        pairs, offs = step()
+    launches0 = lib.mtsvgpu_launch_count()
+    clocks = ClockSampler(local_rank)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        pairs, offs = step()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = e0.elapsed_time(e1)
+    clk = clocks.stop()
+    launches = lib.mtsvgpu_launch_count() - launches0
+    t = torch.tensor([ms, float(pairs.shape[0])], dtype=torch.float64, device=dev)
+    if world > 1:
+        tm = t.clone()
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        ts = t.clone()
+        dist.all_reduce(ts, op=dist.ReduceOp.SUM)
+        ms, total_pairs = float(tm[0]), float(ts[1])
+    else:
+        total_pairs = float(t[1])
+    if rank != 0:
+        return
+    value = n_reads * args.steps / (ms * 1e-3)
+    line = {
+        "metric": "reads/sec binned (150 bp)", "value": value, "unit": "reads/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/u32 integer",
+        "data": "synthetic",
+        "config": {"workload": "cfg3 (scaled): %d chunks x %.1f Gbp chunk-sharded, every read visits every chunk, "
+                               "NCCL all_to_all of hit lists + device collapse (min edit per TaxID)"
+                               % (world, len(parts["text"]) / 1e9),
+                   "reads_per_step": n_reads, "collapsed_taxid_hits_per_step": total_pairs,
+                   "scaling_note": "reference size grows with N (one chunk per GPU); reads per step fixed"},
+        "e2e": None, "gpu_launches": int(launches), "clocks": clk, "roofline": None, "cpu_baseline": None,
+    }
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--mode", default="reads", choices=["reads", "chunk"],
+                    help="reads: index replicated, reads sharded (default); chunk: one index chunk per GPU")
     ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS))
     ap.add_argument("--reads", type=int, default=0, help="reads per GPU per step (default: the config's)")
     ap.add_argument("--sa-rate", type=int, default=0)
@@ -464,7 +545,10 @@ def main():
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     try:
-        run_gpu_arm(args, cfg, rank, world, local_rank)
+        if args.mode == "chunk":
+            run_chunk_arm(args, cfg, rank, world, local_rank)
+        else:
+            run_gpu_arm(args, cfg, rank, world, local_rank)
     finally:
         if world > 1:
             import torch.distributed as dist

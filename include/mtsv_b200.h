@@ -166,6 +166,20 @@ MTSVGPU_API int mtsvgpu_edit_distance(int device, const uint8_t* pats, const uin
                           const uint8_t* texts, const uint64_t* text_off, uint64_t n_pairs,
                           uint32_t* edits);
 
+/* ---- chunk-sharded operation: the mtsv-collapse reduction (src/collapse.rs:543-654, mode TaxId) on
+ * the device.  Every part holds, for the SAME n_reads reads, a device array of hits and a device array
+ * of per-read counts (u32); the result lists, per read, each TaxID once with its minimum edit, by
+ * ascending TaxID (write_collapsed_taxid, src/collapse.rs:278-279).  *d_out / *d_out_off are device
+ * allocations released with mtsvgpu_device_free().  stream: a cudaStream_t or NULL. */
+typedef struct {
+  uint32_t tax_id;
+  uint32_t edit;
+} mtsvgpu_taxhit;
+MTSVGPU_API int mtsvgpu_collapse_device(int device, void* stream, uint32_t n_parts,
+                            const mtsvgpu_hit* const* d_hits, const uint32_t* const* d_counts,
+                            uint64_t n_reads, mtsvgpu_taxhit** d_out, uint64_t** d_out_off, uint64_t* n_out);
+MTSVGPU_API void mtsvgpu_device_free(void* d_ptr);
+
 MTSVGPU_API void mtsvgpu_free(void* p);
 MTSVGPU_API const char* mtsvgpu_last_error(void);
 /* Number of kernels this library has launched in this process (all handles). */

@@ -25,12 +25,6 @@ namespace mtsv {
 // ------------------------------------------------------------------------------------------
 constexpr uint32_t kMaxReadLenDev = 1024;  // longer reads fail the batch (ELIMIT) before any seed work
 
-struct BatchCounters {  // device-side scalars of one sub-batch
-  unsigned long long total_slots, total_hits, total_cands, total_out;
-  unsigned int max_len, overflow, n_warp, n_medium, n_large, bad_offsets;
-  unsigned long long rank_steps[32], window_bytes[32];  // profiling only; spread to avoid one hot address
-};
-
 // adds `v` of every thread of the CTA into one of 32 counters with a single global atomic per CTA
 __device__ __forceinline__ void cta_accumulate(unsigned long long* counters32, unsigned int v) {
   __shared__ unsigned int cta_sum;
@@ -140,10 +134,12 @@ __global__ void __launch_bounds__(256) encode_reads_kernel(ReadsView rv, ReadWor
     for (int half = 0; half < 2; ++half) {
       uint32_t pos = w * 64 + half * 32 + lane;
       bool in = pos < L;
-      uint32_t c = read_code(in ? __ldg(seq + pos) : (uint8_t)'A');
-      bool is_base = c < 4;
-      uint32_t lo = __ballot_sync(0xffffffffu, in && is_base && (c & 1));
-      uint32_t hi = __ballot_sync(0xffffffffu, in && is_base && (c & 2));
+      // src/binner.rs:88-100 on one byte per lane: fold case, then A 0, C 1, G 2, T 3, anything else N
+      uint32_t u = (in ? (uint32_t)__ldg(seq + pos) : (uint32_t)'A') & 0xDFu;
+      bool is_c = u == 'C', is_g = u == 'G', is_t = u == 'T';
+      bool is_base = (u == 'A') | is_c | is_g | is_t;
+      uint32_t lo = __ballot_sync(0xffffffffu, in && (is_c | is_t));
+      uint32_t hi = __ballot_sync(0xffffffffu, in && (is_g | is_t));
       uint32_t nn = __ballot_sync(0xffffffffu, in && !is_base);
       out.lo |= (uint64_t)lo << (32 * half);
       out.hi |= (uint64_t)hi << (32 * half);
@@ -402,6 +398,10 @@ __global__ void __launch_bounds__(1024) sort_large_kernel(uint64_t* __restrict__
 // hit thousands of loci) is handled by the whole warp so that one heavy read does not serialise 31
 // idle lanes behind it.  Heavy queries are taken one after the other (ballot loop).
 
+__device__ __forceinline__ bool carry_valid_or_lane(unsigned lane, bool carry_valid) {
+  return lane > 0 || carry_valid;  // lane 0 compares with the previous tile's last hit, if there is one
+}
+
 // coalesce_seed_sites (src/index.rs:435-487) with the warp: lanes compute bins and windows of 32
 // hits at a time, then every lane replays the (cheap, inherently sequential) merge automaton on the
 // shuffled windows so that control flow stays uniform; lane 0 writes.
@@ -412,17 +412,61 @@ __device__ uint32_t coalesce_warp(const BinsView& bv, const uint64_t* __restrict
   uint32_t nc = 0;
   bool have = false;
   CandRec cur{0, 0, 0, 0};
+  uint32_t carry_site = 0, carry_bin = 0;  // last hit of the previous tile
+  bool carry_valid = false;
   for (uint32_t t0 = 0; t0 < n_hits; t0 += 32) {
     uint32_t h = t0 + lane;
-    uint32_t ws = 0, we = 0, b = 0;
+    uint32_t ws = 0, we = 0, b = 0, site = 0;
     bool some = false;
     if (h < n_hits) {
       uint64_t key = keys[h];
-      uint32_t site = (uint32_t)(key >> 16), q_off = (uint32_t)(key & 0xffff);
+      site = (uint32_t)(key >> 16);
+      uint32_t q_off = (uint32_t)(key & 0xffff);
       b = find_bin(bv, site);
       some = candidate_window(site, q_off, ldg(&bv.start[b]), ldg(&bv.end[b]), L, k, &ws, &we);
     }
     uint32_t cnt = n_hits - t0 < 32 ? n_hits - t0 : 32;
+    // Fast path.  A hit whose site lies >= 2(L+k) after its predecessor (or in another bin) cannot
+    // overlap any window accumulated so far (windows reach at most L+k either side of their site and
+    // hits are sorted by site), so it certainly starts a new candidate.  If that holds for every hit
+    // of the tile the automaton degenerates: flush the incoming candidate, emit every hit but the last
+    // as a single-seed candidate, carry the last.  Typical for reads whose seeds hit hundreds of
+    // unrelated loci.
+    {
+      uint32_t prev_site = __shfl_up_sync(0xffffffffu, site, 1);
+      uint32_t prev_b = __shfl_up_sync(0xffffffffu, b, 1);
+      if (lane == 0) {
+        prev_site = carry_site;
+        prev_b = carry_bin;
+      }
+      bool brk = h >= n_hits || !carry_valid_or_lane(lane, carry_valid) || b != prev_b ||
+                 (uint64_t)site >= (uint64_t)prev_site + 2ull * ((uint64_t)L + k);
+      bool all_break = __all_sync(0xffffffffu, brk);
+      uint32_t last_site = __shfl_sync(0xffffffffu, site, cnt - 1), last_b = __shfl_sync(0xffffffffu, b, cnt - 1);
+      carry_site = last_site;
+      carry_bin = last_b;
+      carry_valid = true;
+      if (all_break) {
+        if (have && cur.num_seeds >= min_seeds) {
+          if (lane == 0) {
+            cand[nc] = cur;
+            rkey[nc] = make_rank_key(cur.num_seeds, nc);
+          }
+          ++nc;
+        }
+        bool emit = h + 1 < t0 + cnt && some && 1u >= min_seeds;  // every hit of the tile except the last
+        unsigned em = __ballot_sync(0xffffffffu, emit);
+        if (emit) {
+          uint32_t pos = nc + __popc(em & ((1u << lane) - 1));
+          cand[pos] = CandRec{ws, we, b, 1};
+          rkey[pos] = make_rank_key(1, pos);
+        }
+        nc += __popc(em);
+        have = __shfl_sync(0xffffffffu, (int)some, cnt - 1) != 0;
+        cur = CandRec{__shfl_sync(0xffffffffu, ws, cnt - 1), __shfl_sync(0xffffffffu, we, cnt - 1), last_b, 1};
+        continue;
+      }
+    }
     for (uint32_t i = 0; i < cnt; ++i) {
       uint32_t ws_i = __shfl_sync(0xffffffffu, ws, i), we_i = __shfl_sync(0xffffffffu, we, i);
       uint32_t b_i = __shfl_sync(0xffffffffu, b, i);
@@ -880,7 +924,7 @@ struct StageClock {
   }
 };
 
-static int run_segmented_sort(cudaStream_t st, DevBuf& worklist, uint64_t* keys, const uint32_t* seg_off,
+int run_segmented_sort(cudaStream_t st, DevBuf& worklist, uint64_t* keys, const uint32_t* seg_off,
                               const uint32_t* seg_cnt, uint32_t nq, uint32_t min_count, BatchCounters* d_ctr) {
   if (worklist.cap < (size_t)3 * nq * 4) {
     MTSV_CUDA_TRY(cudaStreamSynchronize(st));

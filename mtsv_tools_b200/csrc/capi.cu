@@ -201,6 +201,16 @@ int mtsvgpu_bin_batch_pinned(mtsvgpu_index* ix, const uint8_t* seqs, const uint6
   return rc;
 }
 
+int mtsvgpu_collapse_device(int device, void* stream, uint32_t n_parts, const mtsvgpu_hit* const* d_hits,
+                            const uint32_t* const* d_counts, uint64_t n_reads, mtsvgpu_taxhit** d_out,
+                            uint64_t** d_out_off, uint64_t* n_out) {
+  return collapse_device(device, (cudaStream_t)stream, n_parts, d_hits, d_counts, n_reads, d_out, d_out_off, n_out);
+}
+
+void mtsvgpu_device_free(void* d_ptr) {
+  if (d_ptr) cudaFree(d_ptr);
+}
+
 int mtsvgpu_backward_search(mtsvgpu_index* ix, const uint8_t* pats, uint32_t pat_len, uint64_t n_pats,
                             uint64_t* lower, uint64_t* upper) {
   return backward_search_batch(ix, pats, pat_len, n_pats, lower, upper);

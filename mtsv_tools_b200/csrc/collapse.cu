@@ -1,0 +1,149 @@
+// collapse.cu — chunk-sharded operation: merge the hit lists that several MG-index
+// chunks produced for the SAME reads.  This is the reduction mtsv-collapse performs on results files
+// (src/collapse.rs:543-654); mode TaxId: for equal read ids keep the minimum edit per TaxID
+// (:597-602), hits listed by ascending TaxID (write_collapsed_taxid, :278-279).
+//
+// Inputs: n_parts device arrays of mtsvgpu_hit, each with a per-read u32 count array for the same
+// n_reads reads (after the NCCL exchange every rank holds all parts for its own range of reads).
+// All kernels are flat over reads / hits; the per-read sort reuses the binner's segmented sorts.
+#include "ctx.h"
+
+namespace mtsv {
+
+struct PartsView {
+  const mtsvgpu_hit* hits[16];
+  const uint32_t* counts[16];
+  const uint32_t* offs[16];  // exclusive scans of counts
+  uint32_t n_parts;
+};
+
+__global__ void collapse_total_kernel(PartsView pv, uint32_t n_reads, uint32_t* __restrict__ total) {
+  uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_reads) return;
+  uint32_t t = 0;
+  for (uint32_t p = 0; p < pv.n_parts; ++p) t += pv.counts[p][r];
+  total[r] = t;
+}
+
+// key = tax << 32 | edit: ascending order groups a TaxID's hits with the smallest edit first
+__global__ void collapse_scatter_kernel(PartsView pv, uint32_t n_reads, const uint32_t* __restrict__ comb_off,
+                                        uint64_t* __restrict__ keys) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t r = t / pv.n_parts, p = t % pv.n_parts;
+  if (r >= n_reads) return;
+  uint32_t dst = comb_off[r];
+  for (uint32_t q = 0; q < p; ++q) dst += pv.counts[q][r];
+  const mtsvgpu_hit* src = pv.hits[p] + pv.offs[p][r];
+  uint32_t n = pv.counts[p][r];
+  for (uint32_t i = 0; i < n; ++i) keys[dst + i] = ((uint64_t)src[i].tax_id << 32) | src[i].edit;
+}
+
+__global__ void collapse_count_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ comb_off,
+                                      uint32_t n_reads, uint32_t* __restrict__ n_out) {
+  uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_reads) return;
+  uint32_t b = comb_off[r], e = comb_off[r + 1], c = 0;
+  for (uint32_t i = b; i < e; ++i) c += (i == b) || (keys[i] >> 32) != (keys[i - 1] >> 32);
+  n_out[r] = c;
+}
+
+__global__ void collapse_write_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ comb_off,
+                                      const uint32_t* __restrict__ out_off32, uint32_t n_reads,
+                                      mtsvgpu_taxhit* __restrict__ out, uint64_t* __restrict__ out_off) {
+  uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r > n_reads) return;
+  out_off[r] = out_off32[r];
+  if (r == n_reads) return;
+  uint32_t b = comb_off[r], e = comb_off[r + 1], w = out_off32[r];
+  for (uint32_t i = b; i < e; ++i)
+    if (i == b || (keys[i] >> 32) != (keys[i - 1] >> 32)) {
+      out[w].tax_id = (uint32_t)(keys[i] >> 32);
+      out[w].edit = (uint32_t)(keys[i] & 0xffffffffu);
+      ++w;
+    }
+}
+
+int collapse_device(int device, cudaStream_t st, uint32_t n_parts, const mtsvgpu_hit* const* d_hits,
+                    const uint32_t* const* d_counts, uint64_t n_reads, mtsvgpu_taxhit** d_out,
+                    uint64_t** d_out_off, uint64_t* n_out) {
+  if (!d_hits || !d_counts || !d_out || !d_out_off || !n_out) return set_error(MTSVGPU_EINVAL, "null argument");
+  if (n_parts == 0 || n_parts > 16) return set_error(MTSVGPU_EINVAL, "n_parts must be in [1,16]");
+  if (n_reads > 0x7ffffff0ull) return set_error(MTSVGPU_ELIMIT, "too many reads in one collapse call");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    (void)cudaGetLastError();
+    return set_error(MTSVGPU_ENODEVICE, "no CUDA device available (this library has no CPU path)");
+  }
+  MTSV_CUDA_TRY(cudaSetDevice(device));
+  const uint32_t nr = (uint32_t)n_reads;
+  DevBuf offs[16], total, comb_off, keys, scan_tmp, counters, worklist, cnt_out, off_out32;
+  struct Cleanup {
+    DevBuf* a[16 + 9];
+    ~Cleanup() {
+      for (DevBuf* b : a)
+        if (b) b->release();
+    }
+  } cl{};
+  for (int i = 0; i < 16; ++i) cl.a[i] = &offs[i];
+  DevBuf* rest[9] = {&total, &comb_off, &keys, &scan_tmp, &counters, &worklist, &cnt_out, &off_out32, nullptr};
+  for (int i = 0; i < 9; ++i) cl.a[16 + i] = rest[i];
+
+  PartsView pv{};
+  pv.n_parts = n_parts;
+  MTSV_TRY(counters.reserve(sizeof(BatchCounters) + 16));
+  MTSV_CUDA_TRY(cudaMemsetAsync(counters.p, 0, sizeof(BatchCounters) + 16, st));
+  uint64_t* d_tot = reinterpret_cast<uint64_t*>(counters.as<uint8_t>() + sizeof(BatchCounters));
+  for (uint32_t p = 0; p < n_parts; ++p) {
+    pv.hits[p] = d_hits[p];
+    pv.counts[p] = d_counts[p];
+    MTSV_TRY(offs[p].reserve(((size_t)nr + 1) * 4));
+    MTSV_TRY(exclusive_scan_u32(d_counts[p], offs[p].as<uint32_t>(), nr, scan_tmp, nullptr, st));
+    pv.offs[p] = offs[p].as<uint32_t>();
+  }
+  MTSV_TRY(total.reserve(((size_t)nr + 1) * 4));
+  MTSV_TRY(comb_off.reserve(((size_t)nr + 1) * 4));
+  MTSV_TRY(cnt_out.reserve(((size_t)nr + 1) * 4));
+  MTSV_TRY(off_out32.reserve(((size_t)nr + 1) * 4));
+  const unsigned rgrid = (nr + 255) / 256 + 1;
+  if (nr) MTSV_LAUNCH(collapse_total_kernel, rgrid, 256, 0, st, pv, nr, total.as<uint32_t>());
+  MTSV_TRY(exclusive_scan_u32(total.as<uint32_t>(), comb_off.as<uint32_t>(), nr, scan_tmp, d_tot, st));
+  uint64_t h_tot = 0;
+  MTSV_CUDA_TRY(cudaMemcpyAsync(&h_tot, d_tot, 8, cudaMemcpyDeviceToHost, st));
+  MTSV_CUDA_TRY(cudaStreamSynchronize(st));
+  if (h_tot > 0xfffffff0ull) return set_error(MTSVGPU_ELIMIT, "more than 2^32 hits in one collapse call");
+  MTSV_TRY(keys.reserve((size_t)(h_tot + 1) * 8));
+  if (nr && h_tot) {
+    const uint64_t threads = (uint64_t)nr * n_parts;
+    MTSV_LAUNCH(collapse_scatter_kernel, (unsigned)((threads + 255) / 256), 256, 0, st, pv, nr,
+                comb_off.as<uint32_t>(), keys.as<uint64_t>());
+    MTSV_TRY(run_segmented_sort(st, worklist, keys.as<uint64_t>(), comb_off.as<uint32_t>(), total.as<uint32_t>(), nr,
+                                1, counters.as<BatchCounters>()));
+  }
+  if (nr) MTSV_LAUNCH(collapse_count_kernel, rgrid, 256, 0, st, keys.as<uint64_t>(), comb_off.as<uint32_t>(), nr,
+                      cnt_out.as<uint32_t>());
+  MTSV_TRY(exclusive_scan_u32(cnt_out.as<uint32_t>(), off_out32.as<uint32_t>(), nr, scan_tmp, d_tot, st));
+  MTSV_CUDA_TRY(cudaMemcpyAsync(&h_tot, d_tot, 8, cudaMemcpyDeviceToHost, st));
+  MTSV_CUDA_TRY(cudaStreamSynchronize(st));
+  mtsvgpu_taxhit* out = nullptr;
+  uint64_t* out_off = nullptr;
+  if (cudaMalloc((void**)&out, (size_t)(h_tot + 1) * sizeof(mtsvgpu_taxhit)) != cudaSuccess ||
+      cudaMalloc((void**)&out_off, ((size_t)nr + 1) * 8) != cudaSuccess) {
+    (void)cudaGetLastError();
+    if (out) cudaFree(out);
+    return set_error(MTSVGPU_ENOMEM, "cudaMalloc of the collapsed result failed");
+  }
+  MTSV_LAUNCH(collapse_write_kernel, rgrid, 256, 0, st, keys.as<uint64_t>(), comb_off.as<uint32_t>(),
+              off_out32.as<uint32_t>(), nr, out, out_off);
+  cudaError_t e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) {
+    cudaFree(out);
+    cudaFree(out_off);
+    return set_error(MTSVGPU_ECUDA, "collapse: %s", cudaGetErrorString(e));
+  }
+  *d_out = out;
+  *d_out_off = out_off;
+  *n_out = h_tot;
+  return 0;
+}
+
+}  // namespace mtsv

@@ -50,6 +50,13 @@ struct DevBuf {
   }
 };
 
+struct BatchCounters {  // device-side scalars of one sub-batch
+  unsigned long long total_slots, total_hits, total_cands, total_out;
+  unsigned int max_len, overflow, n_warp, n_medium, n_large, bad_offsets;
+  unsigned long long rank_steps[32], window_bytes[32];  // profiling only; spread to avoid one hot address
+};
+
+
 // device-resident index (one per GPU)
 struct DeviceIndex {
   int device = 0;
@@ -173,6 +180,11 @@ int locate_batch(mtsvgpu_index* h, const uint64_t* rows, uint64_t n_rows, uint64
 int edit_distance_batch(int device, const uint8_t* pats, const uint64_t* pat_off,
                         const uint8_t* texts, const uint64_t* text_off, uint64_t n_pairs,
                         uint32_t* edits);
+int run_segmented_sort(cudaStream_t st, DevBuf& worklist, uint64_t* keys, const uint32_t* seg_off,
+                       const uint32_t* seg_cnt, uint32_t nq, uint32_t min_count, BatchCounters* d_ctr);
+int collapse_device(int device, cudaStream_t st, uint32_t n_parts, const mtsvgpu_hit* const* d_hits,
+                    const uint32_t* const* d_counts, uint64_t n_reads, mtsvgpu_taxhit** d_out,
+                    uint64_t** d_out_off, uint64_t* n_out);
 // scan.cuh users
 int exclusive_scan_u32(const uint32_t* d_in, uint32_t* d_out, uint64_t n, DevBuf& tmp,
                        uint64_t* d_total, cudaStream_t stream);

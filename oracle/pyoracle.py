@@ -309,3 +309,23 @@ def results_lines(names, hits, offs, long_format=False):
         if b > a:
             out.append(format_assignments(name, hits[a:b], long_format))
     return out
+
+
+def collapse_taxid(parts):
+    """mtsv-collapse, mode TaxId, for per-chunk hit lists of the SAME reads (src/collapse.rs:543-654): for
+    equal read ids keep the minimum edit per TaxID (:597-602), listed by ascending TaxID
+    (write_collapsed_taxid, :278-279).  parts: list of (hits structured array, offsets).  Returns
+    (pairs uint32 [n,2], offsets uint64 [n_reads+1])."""
+    n_reads = len(parts[0][1]) - 1
+    pairs, offs = [], np.zeros(n_reads + 1, dtype=np.uint64)
+    for r in range(n_reads):
+        best = {}
+        for hits, o in parts:
+            for h in hits[int(o[r]):int(o[r + 1])]:
+                t, e = int(h["tax_id"]), int(h["edit"])
+                if t not in best or e < best[t]:
+                    best[t] = e
+        for t in sorted(best):
+            pairs.append((t, best[t]))
+        offs[r + 1] = len(pairs)
+    return np.array(pairs, dtype=np.uint32).reshape(-1, 2), offs

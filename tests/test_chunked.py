@@ -1,0 +1,129 @@
+"""Chunk-sharded operation: the NCCL exchange logic on CPU with gloo (world_size 2) and the
+device collapse kernel against the oracle's restatement of mtsv-collapse's merge rule."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from mtsv_tools_b200 import chunked
+
+HIT_DTYPE = np.dtype([("tax_id", "<u4"), ("gi", "<u4"), ("offset", "<u8"), ("edit", "<u4"), ("reserved", "<u4")])
+
+
+def _fake_hits(rank, n_reads, seed=0):
+    """Deterministic per-rank hit lists (as a chunk would produce) for the same reads."""
+    rng = np.random.default_rng(seed * 100 + rank)
+    counts = rng.integers(0, 5, size=n_reads).astype(np.int32)
+    counts[rng.random(n_reads) < 0.3] = 0
+    hits = np.zeros(int(counts.sum()), dtype=HIT_DTYPE)
+    hits["tax_id"] = rng.integers(1, 8, size=len(hits)) + 10 * (rng.random(len(hits)) < 0.5) * rank
+    hits["gi"] = rng.integers(1, 100, size=len(hits))
+    hits["offset"] = rng.integers(0, 1000, size=len(hits))
+    hits["edit"] = rng.integers(0, 20, size=len(hits))
+    offs = np.zeros(n_reads + 1, dtype=np.uint64)
+    offs[1:] = np.cumsum(counts)
+    return hits, offs, counts
+
+
+def _collapse_numpy(parts_hits, parts_counts, n):
+    from oracle import pyoracle
+    parts = []
+    for hb, c in zip(parts_hits, parts_counts):
+        hits = np.frombuffer(hb.numpy().tobytes(), dtype=HIT_DTYPE)
+        offs = np.zeros(n + 1, dtype=np.uint64)
+        offs[1:] = np.cumsum(c.numpy())
+        parts.append((hits, offs))
+    return pyoracle.collapse_taxid(parts)
+
+
+def _worker(rank, world, port, n_reads, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        hits, offs, counts = _fake_hits(rank, n_reads)
+        hb = torch.from_numpy(np.frombuffer(hits.tobytes(), dtype=np.uint8).copy())
+        bounds = chunked.read_ranges(n_reads, world)
+        parts = chunked.exchange_hits(hb, torch.from_numpy(counts), bounds)
+        pairs, po = _collapse_numpy([p[0] for p in parts], [p[1] for p in parts], bounds[rank + 1] - bounds[rank])
+        out.put((rank, pairs, po))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_exchange_gloo_world2():
+    from oracle import pyoracle
+    world, n_reads = 2, 1001
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n_reads, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = {}
+    for _ in range(world):
+        r, pairs, po = q.get(timeout=120)
+        got[r] = (pairs, po)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    # expected: collapse of both ranks' full lists, then cut into the two ranges
+    full = [(_fake_hits(r, n_reads)[0], _fake_hits(r, n_reads)[1]) for r in range(world)]
+    want_pairs, want_off = pyoracle.collapse_taxid(full)
+    bounds = chunked.read_ranges(n_reads, world)
+    for r in range(world):
+        a, b = int(want_off[bounds[r]]), int(want_off[bounds[r + 1]])
+        assert np.array_equal(got[r][0], want_pairs[a:b])
+        assert np.array_equal(got[r][1], want_off[bounds[r]:bounds[r + 1] + 1] - want_off[bounds[r]])
+
+
+def test_collapse_rule_kats():
+    """src/collapse.rs:788-817 collapse_edit_distances_min_edit: r1:1=5,2=9 + r1:1=2,2=10 -> r1:1=2,2=9."""
+    from oracle import pyoracle
+
+    def mk(lists):
+        hits = np.zeros(sum(len(x) for x in lists), dtype=HIT_DTYPE)
+        offs = np.zeros(len(lists) + 1, dtype=np.uint64)
+        k = 0
+        for i, l in enumerate(lists):
+            for t, e in l:
+                hits[k]["tax_id"], hits[k]["edit"] = t, e
+                k += 1
+            offs[i + 1] = k
+        return hits, offs
+    a = mk([[(1, 5), (2, 9)], [(3, 4)]])
+    b = mk([[(1, 2), (2, 10)], [(3, 1)]])
+    pairs, offs = pyoracle.collapse_taxid([a, b])
+    assert pairs.tolist() == [[1, 2], [2, 9], [3, 1]] and offs.tolist() == [0, 2, 3]
+
+
+@pytest.mark.gpu
+def test_collapse_device_vs_oracle(oracle):
+    """Two different chunks, the same reads: device merge == oracle merge of the two oracle runs."""
+    from mtsv_tools_b200 import MGIndex, Params, synth
+    refs = [synth.make_reference(6, 20000, seed=s, n_frac=0.001, shared_frac=0.1, taxids=[5, 6, 7, 8, 9, 10])
+            for s in (31, 32)]
+    # chunk 2 shares some sequence with chunk 1 so that the same TaxIDs are reached from both chunks
+    refs[1][0][:30000] = refs[0][0][:30000]
+    idx = [oracle.Index.build((r[0], r[1]), r[2], r[3], 64, 32) for r in refs]
+    reads = synth.make_reads(np.concatenate([refs[0][0], refs[1][0]]),
+                             np.concatenate([refs[0][1], refs[1][1][1:] + refs[0][1][-1]]), 4000, 150, seed=33)
+    parts_o = [ix.bin_reads(reads, oracle.default_params(), threads=4) for ix in idx]
+    want_pairs, want_off = oracle.collapse_taxid(parts_o)
+    parts_h, parts_c = [], []
+    for ix in idx:
+        with MGIndex.from_parts(ix.text, ix.bins(), ix.bwt, ix.sa_sample, ix.sa_sample_rate) as g:
+            h, o = g.bin_reads(reads, Params())
+        parts_h.append(torch.from_numpy(np.frombuffer(h.tobytes(), dtype=np.uint8).copy()).cuda())
+        parts_c.append(torch.from_numpy((o[1:] - o[:-1]).astype(np.int32)).cuda())
+    pairs, offs = chunked.collapse_parts_device(0, None, parts_h, parts_c, 4000)
+    assert np.array_equal(offs.cpu().numpy().astype(np.uint64), want_off)
+    assert np.array_equal(pairs.cpu().numpy().astype(np.uint32), want_pairs)
+    assert len(want_pairs) > 3000
