@@ -459,6 +459,7 @@ def run_chunk_arm(args, cfg, rank, world, local_rank):
     d_reads = synth.make_reads_torch(ref_t, parts0["ref_off"], n_reads, L, 4, dev)
     del ref_t
     d_off = torch.arange(n_reads + 1, dtype=torch.int64, device=dev) * L
+    torch.cuda.synchronize()
     params = Params(**cfg["flags"])
     stream = torch.cuda.current_stream()
     gix.set_stream(stream.cuda_stream)
@@ -538,19 +539,20 @@ def main():
     if args.impl == "reference":
         run_reference_arm(args, cfg, rank, world)
         return
-    if world > 1:
+    if world > 1 or args.mode == "chunk":
         import torch
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29533")
         torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local_rank))
     try:
         if args.mode == "chunk":
             run_chunk_arm(args, cfg, rank, world, local_rank)
         else:
             run_gpu_arm(args, cfg, rank, world, local_rank)
     finally:
-        if world > 1:
+        if world > 1 or args.mode == "chunk":
             import torch.distributed as dist
             dist.destroy_process_group()
 

@@ -147,7 +147,9 @@ MTSVGPU_API int mtsvgpu_bin_batch_device(mtsvgpu_index* ix, const uint8_t* d_seq
                              const mtsvgpu_hit** d_hits, const uint64_t** d_hit_off,
                              uint64_t* n_hits);
 MTSVGPU_API int mtsvgpu_last_batch_stats(const mtsvgpu_index* ix, mtsvgpu_batch_stats* stats);
-/* Launch on a caller-provided cudaStream_t (e.g. torch's current stream); NULL = the handle's own. */
+/* Launch on a caller-provided cudaStream_t (e.g. torch's current stream); NULL = the handle's own
+ * non-blocking stream.  To use the legacy default stream pass cudaStreamLegacy ((cudaStream_t)0x1).
+ * Inputs produced on another stream must be complete (or ordered by the caller) before a batch call. */
 MTSVGPU_API int mtsvgpu_set_stream(mtsvgpu_index* ix, void* cuda_stream);
 /* Collect per-stage CUDA-event timings (costs a few event records per stage); 0 = off (default). */
 MTSVGPU_API int mtsvgpu_set_profiling(mtsvgpu_index* ix, int on);

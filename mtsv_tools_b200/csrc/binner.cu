@@ -1015,8 +1015,9 @@ static int run_sub_batch(mtsvgpu_index* h, const Params& p, const uint8_t* d_seq
     return set_error(MTSVGPU_ELIMIT, "a read of %u bases exceeds this build's limit of %u", hc.max_len,
                      kMaxReadLen);
   if (hc.total_slots > slot_bound)
-    return set_error(MTSVGPU_ECUDA, "internal: seed slots %llu exceed bound %llu", hc.total_slots,
-                     (unsigned long long)slot_bound);
+    return set_error(MTSVGPU_ECUDA, "internal: seed slots %llu exceed bound %llu (reads [%llu,+%u), %llu bytes)",
+                     hc.total_slots, (unsigned long long)slot_bound, (unsigned long long)read0, n_reads,
+                     (unsigned long long)sub_bytes);
   const uint32_t n_slots = (uint32_t)hc.total_slots;
   h->stats.n_seed_slots += n_slots;
   // (only now that the slot count is known to fit the buffers)

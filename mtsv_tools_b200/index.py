@@ -112,7 +112,14 @@ class MGIndex:
         return {n: getattr(i, n) for n, _ in i._fields_}
 
     def set_stream(self, cuda_stream_handle):
-        check(_lib.load_library().mtsvgpu_set_stream(self._h, C.c_void_p(cuda_stream_handle or 0)))
+        """Launch on the given cudaStream_t.  None = the handle's own (non-blocking) stream.  torch reports
+        its default stream as handle 0; that is passed as cudaStreamLegacy (1) so that the library's work is
+        ordered with torch's kernels and bracketed by torch.cuda.Event on the current stream."""
+        if cuda_stream_handle is None:
+            h = 0
+        else:
+            h = int(cuda_stream_handle) or 1
+        check(_lib.load_library().mtsvgpu_set_stream(self._h, C.c_void_p(h)))
 
     def set_profiling(self, on):
         check(_lib.load_library().mtsvgpu_set_profiling(self._h, int(bool(on))))
