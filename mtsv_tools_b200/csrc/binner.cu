@@ -114,44 +114,38 @@ __global__ void __launch_bounds__(256) encode_rc_kernel(ReadsView rv, ReadWord* 
   words[total_words + woff + w] = encode_rc_word(words + woff, L, w);
 }
 
-// both strands of a read by one warp: forward words from two coalesced 32-byte loads + ballots each,
-// kept in shared memory, then lanes 0..W-1 derive the reverse-complement words from them.
-// (reads are at most kMaxReadLenDev = 1024 bases here: 16 words)
-__global__ void __launch_bounds__(256) encode_reads_kernel(ReadsView rv, ReadWord* __restrict__ words,
-                                                           uint32_t total_words, uint32_t ns) {
-  __shared__ ReadWord fw[8][16];
-  const unsigned lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+// forward strand of the binner's reads: one thread per read, eight bases per step with SWAR
+// (core.cuh::encode8) on 8-byte aligned loads; ~30x fewer instructions than a byte-per-lane encoder.
+__global__ void __launch_bounds__(128) encode_reads_kernel(ReadsView rv, ReadWord* __restrict__ words) {
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= rv.n_reads) return;
   const uint64_t a = rv.seq_off[rv.read0 + r], b = rv.seq_off[rv.read0 + r + 1];
   const uint32_t L = (uint32_t)(b - a);
   const uint32_t W = (L + 63) >> 6;
   const uint32_t woff = (uint32_t)((a - rv.seq_off[rv.read0]) >> 6) + r;
-  const uint8_t* seq = rv.seqs + a;
+  const uint64_t addr = (uint64_t)(rv.seqs + a);
+  const uint64_t* wp = reinterpret_cast<const uint64_t*>(addr & ~7ull);
+  const uint32_t boff = (uint32_t)(addr & 7ull);
   for (uint32_t w = 0; w < W; ++w) {
     ReadWord out{0, 0, 0};
 #pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      uint32_t pos = w * 64 + half * 32 + lane;
-      bool in = pos < L;
-      // src/binner.rs:88-100 on one byte per lane: fold case, then A 0, C 1, G 2, T 3, anything else N
-      uint32_t u = (in ? (uint32_t)__ldg(seq + pos) : (uint32_t)'A') & 0xDFu;
-      bool is_c = u == 'C', is_g = u == 'G', is_t = u == 'T';
-      bool is_base = (u == 'A') | is_c | is_g | is_t;
-      uint32_t lo = __ballot_sync(0xffffffffu, in && (is_c | is_t));
-      uint32_t hi = __ballot_sync(0xffffffffu, in && (is_g | is_t));
-      uint32_t nn = __ballot_sync(0xffffffffu, in && !is_base);
-      out.lo |= (uint64_t)lo << (32 * half);
-      out.hi |= (uint64_t)hi << (32 * half);
-      out.nn |= (uint64_t)nn << (32 * half);
+    for (uint32_t c = 0; c < 8; ++c) {
+      uint32_t pos = w * 64 + c * 8;
+      if (pos < L) {
+        uint32_t nvalid = L - pos < 8 ? L - pos : 8;
+        uint32_t first = boff + pos, last = first + nvalid - 1;
+        uint64_t x = __ldg(wp + (first >> 3)) >> ((first & 7) * 8);
+        if ((last >> 3) != (first >> 3)) x |= __ldg(wp + (last >> 3)) << (64 - (first & 7) * 8);
+        uint32_t lo, hi, nn;
+        encode8(x, &lo, &hi, &nn);
+        uint32_t m = (1u << nvalid) - 1;
+        out.lo |= (uint64_t)(lo & m) << (c * 8);
+        out.hi |= (uint64_t)(hi & m) << (c * 8);
+        out.nn |= (uint64_t)(nn & m) << (c * 8);
+      }
     }
-    if (lane == 0) {
-      words[woff + w] = out;
-      fw[wib][w] = out;
-    }
+    words[woff + w] = out;
   }
-  __syncwarp();
-  if (ns == 2 && lane < W) words[total_words + woff + lane] = encode_rc_word(fw[wib], L, lane);
 }
 
 // seed search: one thread per slot.  Each thread owns one dependent chain of sector fetches;
@@ -510,42 +504,47 @@ __global__ void __launch_bounds__(128) coalesce_kernel(BinsView bv, ReadsView rv
                                                        CandRec* __restrict__ cand_sparse,
                                                        uint64_t* __restrict__ rank_keys,
                                                        uint32_t* __restrict__ q_ncand) {
-  uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+  // one lane per read: its strands are taken one after the other (usually exactly one of them has
+  // hits, so lanes carry similar loads); a strand with many hits is handed to the whole warp
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
   const unsigned lane = threadIdx.x & 31;
-  uint32_t nh = q < nq ? q_nhits[q] : 0;
-  uint32_t nc = 0, L = 0, k = 0, ms = 0, base = 0;
-  if (nh) {
-    L = query_len(rv, p.ns, q);
-    k = edit_budget(L, p.edit_rate);
-    ms = min_seeds_of(q_nseeds[q], p.min_seed);
-    base = hit_off[q];
-    if (nh <= kLightItems) {
-      // few hits: this lane orders them itself (they arrive seed by seed, i.e. almost sorted)
-      uint64_t* kq = hit_keys + base;
-      for (uint32_t i = 1; i < nh; ++i) {
-        uint64_t v = kq[i];
-        uint32_t j = i;
-        while (j > 0 && kq[j - 1] > v) {
-          kq[j] = kq[j - 1];
-          --j;
+  for (uint32_t s = 0; s < p.ns; ++s) {
+    const uint32_t q = r * p.ns + s;
+    uint32_t nh = q < nq ? q_nhits[q] : 0;
+    uint32_t nc = 0, L = 0, k = 0, ms = 0, base = 0;
+    if (nh) {
+      L = query_len(rv, p.ns, q);
+      k = edit_budget(L, p.edit_rate);
+      ms = min_seeds_of(q_nseeds[q], p.min_seed);
+      base = hit_off[q];
+      if (nh <= kLightItems) {
+        // few hits: this lane orders them itself (they arrive seed by seed, i.e. almost sorted)
+        uint64_t* kq = hit_keys + base;
+        for (uint32_t i = 1; i < nh; ++i) {
+          uint64_t v = kq[i];
+          uint32_t j = i;
+          while (j > 0 && kq[j - 1] > v) {
+            kq[j] = kq[j - 1];
+            --j;
+          }
+          kq[j] = v;
         }
-        kq[j] = v;
+        nc = coalesce_item(bv, kq, nh, ms, L, k, cand_sparse + base, rank_keys + base);
       }
-      nc = coalesce_item(bv, kq, nh, ms, L, k, cand_sparse + base, rank_keys + base);
     }
+    unsigned heavy = __ballot_sync(0xffffffffu, nh > kLightItems);
+    while (heavy) {
+      int src = __ffs(heavy) - 1;
+      heavy &= heavy - 1;
+      uint32_t nh_s = __shfl_sync(0xffffffffu, nh, src), base_s = __shfl_sync(0xffffffffu, base, src);
+      uint32_t L_s = __shfl_sync(0xffffffffu, L, src), k_s = __shfl_sync(0xffffffffu, k, src);
+      uint32_t ms_s = __shfl_sync(0xffffffffu, ms, src);
+      uint32_t rr = coalesce_warp(bv, hit_keys + base_s, nh_s, ms_s, L_s, k_s, cand_sparse + base_s,
+                                  rank_keys + base_s);
+      if ((int)lane == src) nc = rr;
+    }
+    if (q < nq) q_ncand[q] = nc;
   }
-  unsigned heavy = __ballot_sync(0xffffffffu, nh > kLightItems);
-  while (heavy) {
-    int src = __ffs(heavy) - 1;
-    heavy &= heavy - 1;
-    uint32_t nh_s = __shfl_sync(0xffffffffu, nh, src), base_s = __shfl_sync(0xffffffffu, base, src);
-    uint32_t L_s = __shfl_sync(0xffffffffu, L, src), k_s = __shfl_sync(0xffffffffu, k, src);
-    uint32_t ms_s = __shfl_sync(0xffffffffu, ms, src);
-    uint32_t r = coalesce_warp(bv, hit_keys + base_s, nh_s, ms_s, L_s, k_s, cand_sparse + base_s,
-                               rank_keys + base_s);
-    if ((int)lane == src) nc = r;
-  }
-  if (q < nq) q_ncand[q] = nc;
 }
 
 __global__ void __launch_bounds__(256) rank_emit_kernel(uint32_t nq, const uint32_t* __restrict__ hit_off,
@@ -1023,8 +1022,13 @@ static int run_sub_batch(mtsvgpu_index* h, const Params& p, const uint8_t* d_seq
   // (only now that the slot count is known to fit the buffers)
   clk.begin(ST_PREP);
   MTSV_LAUNCH(expand_slots_kernel, qgrid, 256, 0, st, slot_off, nq, ws.slot_q.as<uint32_t>());
-  MTSV_LAUNCH(encode_reads_kernel, (unsigned)(((uint64_t)n_reads * 32 + 255) / 256), 256, 0, st, rv,
-              ws.enc.as<ReadWord>(), total_words, p.ns);
+  MTSV_LAUNCH(encode_reads_kernel, (n_reads + 127) / 128, 128, 0, st, rv, ws.enc.as<ReadWord>());
+  if (p.ns == 2) {
+    const uint32_t w_max = hc.max_len ? (hc.max_len + 63) / 64 : 1;
+    const uint64_t threads = (uint64_t)n_reads * w_max;
+    MTSV_LAUNCH(encode_rc_kernel, (unsigned)((threads + 255) / 256), 256, 0, st, rv, ws.enc.as<ReadWord>(),
+                total_words, w_max);
+  }
   clk.end();
 
   // ---- seed search ----
@@ -1076,7 +1080,7 @@ static int run_sub_batch(mtsvgpu_index* h, const Params& p, const uint8_t* d_seq
     clk.end();
     // ---- coalesce ----
     clk.begin(ST_COALESCE);
-    MTSV_LAUNCH(coalesce_kernel, (nq + 127) / 128, 128, 0, st, ix.bins_view(), rv, p, nq,
+    MTSV_LAUNCH(coalesce_kernel, (n_reads + 127) / 128, 128, 0, st, ix.bins_view(), rv, p, nq,
                 ws.hit_off.as<uint32_t>(), ws.q_nhits.as<uint32_t>(), ws.q_nseeds.as<uint32_t>(),
                 ws.hit_keys.as<uint64_t>(), ws.cand_sparse.as<CandRec>(), ws.rank_keys.as<uint64_t>(),
                 ws.q_ncand.as<uint32_t>());

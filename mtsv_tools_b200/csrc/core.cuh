@@ -292,6 +292,24 @@ MTSV_HD ReadWord encode_fwd_word(const uint8_t* seq, uint32_t L, uint32_t w, boo
   return r;
 }
 
+// Eight read bytes at once (SWAR): returns the lo / hi / nn plane bits of the 8 bases in the low 8 bits
+// of each output.  Same normalisation as read_code (src/binner.rs:88-100).
+MTSV_HD void encode8(uint64_t x, uint32_t* lo, uint32_t* hi, uint32_t* nn) {
+  const uint64_t k7f = 0x7f7f7f7f7f7f7f7full, k80 = 0x8080808080808080ull;
+  uint64_t u = x & 0xdfdfdfdfdfdfdfdfull;  // fold lower case onto upper case
+  // zero-byte detector: 0x80 in every byte of v that is zero (exact, no cross-byte borrow)
+#define MTSV_ZB(v) (~((((v) & k7f) + k7f) | (v)) & k80)
+  uint64_t za = MTSV_ZB(u ^ 0x4141414141414141ull), zc = MTSV_ZB(u ^ 0x4343434343434343ull);
+  uint64_t zg = MTSV_ZB(u ^ 0x4747474747474747ull), zt = MTSV_ZB(u ^ 0x5454545454545454ull);
+#undef MTSV_ZB
+  uint64_t l = zc | zt, h = zg | zt, b = za | l | zg;
+  // gather bit 7 of every byte into 8 adjacent bits: (z >> 7) * 0x0102040810204080 puts byte i's flag at bit 56 + i
+  const uint64_t mul = 0x0102040810204080ull;
+  *lo = (uint32_t)(((l >> 7) * mul) >> 56);
+  *hi = (uint32_t)(((h >> 7) * mul) >> 56);
+  *nn = (uint32_t)((((b ^ k80) >> 7) * mul) >> 56);
+}
+
 // word w of the reverse-complement strand from the forward words (bio::alphabets::dna::revcomp on the
 // normalised alphabet, src/binner.rs:115): rc[i] = comp(fwd[L-1-i]), N stays N.
 MTSV_HD ReadWord encode_rc_word(const ReadWord* fwd, uint32_t L, uint32_t w) {
