@@ -32,6 +32,15 @@ CONFIGS = {
                  flags={}, label="cfg2: 1 Gbp chunk (200 x 5 Mbp), 150 bp reads, default flags"),
     "cfg1": dict(n_seqs=52, seq_len=192_308, shared=0.0, div=0.0, reads=100_000, read_len=150,
                  flags={}, label="cfg1: 10 Mbp reference, 100k x 150 bp reads, default flags"),
+    # config 4: 75 bp reads against a highly redundant reference (500 near-identical strains, distinct TaxIDs):
+    # large SA intervals, tune-max-hits doubling, hundreds of candidates per read
+    "cfg4": dict(n_seqs=500, seq_len=2_000_000, shared=0.0, div=0.0, strains=dict(base_len=2_000_000, div=0.003),
+                 reads=2_000_000, read_len=75, flags={},
+                 label="cfg4: 500 strains x 2 Mbp at 0.3 % divergence, 75 bp reads, default flags"),
+    # config 5: 250 bp reads at edit-rate 0.2 with dense seeding: verifier stress
+    "cfg5": dict(n_seqs=40, seq_len=5_000_000, shared=0.10, div=0.01, reads=2_000_000, read_len=250,
+                 flags=dict(edit_rate=0.2, seed_gap=3), read_sub=0.12,
+                 label="cfg5: 200 Mbp chunk, 250 bp reads mutated 12 %, --edit-rate 0.2 --seed-interval 3"),
     "cfg2s": dict(n_seqs=40, seq_len=5_000_000, shared=0.10, div=0.01, reads=2_000_000, read_len=150,
                   flags={}, label="cfg2s: 200 Mbp chunk (40 x 5 Mbp), 150 bp reads, default flags"),
 }
@@ -59,6 +68,15 @@ def make_reference_torch(cfg, seed, device):
         e = min(total, b + step)
         cat[b:e] = acgt[torch.randint(0, 4, (e - b,), generator=g, device=device)]
     rng = np.random.default_rng(seed)
+    if cfg.get("strains"):
+        # every sequence is a mutated copy of the first one (near-identical strains)
+        base = cat[:seq_len].clone()
+        nmut = int(seq_len * cfg["strains"]["div"])
+        for i in range(1, n_seqs):
+            piece = base.clone()
+            pos = torch.randint(0, seq_len, (nmut,), generator=g, device=device)
+            piece[pos] = acgt[torch.randint(0, 4, (nmut,), generator=g, device=device)]
+            cat[i * seq_len:(i + 1) * seq_len] = piece
     if cfg["shared"] > 0:
         seg = int(seq_len * cfg["shared"])
         for i in range(1, n_seqs):
@@ -202,14 +220,14 @@ def run_reference_arm(args, cfg, rank, world):
     dev = "cuda:0" if torch.cuda.is_available() else "cpu"
     # bounded sample per step: calibrate on 20k reads, aim at ~10 s per step
     ref_t = torch.from_numpy(parts["text"][:-1]).to(dev)
-    calib = synth.make_reads_torch(ref_t, parts["ref_off"], 20000, L, 4, dev).cpu().numpy()
+    calib = synth.make_reads_torch(ref_t, parts["ref_off"], 20000, L, 4, dev, sub=cfg.get("read_sub", 0.02)).cpu().numpy()
     off = np.arange(20001, dtype=np.uint64) * np.uint64(L)
     params = pyoracle.default_params(**cfg["flags"])
     t0 = time.time()
     oix.bin_reads((calib, off), params, threads=cores)
     rate = 20000 / (time.time() - t0)
     n_sample = int(min(cfg["reads"], max(20000, rate * args.ref_seconds)))
-    reads = synth.make_reads_torch(ref_t, parts["ref_off"], n_sample, L, 4, dev).cpu().numpy()
+    reads = synth.make_reads_torch(ref_t, parts["ref_off"], n_sample, L, 4, dev, sub=cfg.get("read_sub", 0.02)).cpu().numpy()
     del ref_t
     off = np.arange(n_sample + 1, dtype=np.uint64) * np.uint64(L)
     for _ in range(min(args.warmup, 1)):
@@ -267,7 +285,8 @@ def run_gpu_arm(args, cfg, rank, world, local_rank):
     n_reads = args.reads or cfg["reads"]
     ref_t = torch.from_numpy(parts["text"][:-1]).to(dev)
     t0 = time.time()
-    d_reads = synth.make_reads_torch(ref_t, parts["ref_off"], n_reads, L, 4 + 17 * rank, dev)
+    d_reads = synth.make_reads_torch(ref_t, parts["ref_off"], n_reads, L, 4 + 17 * rank, dev,
+                                     sub=cfg.get("read_sub", 0.02))
     del ref_t
     d_off = (torch.arange(n_reads + 1, dtype=torch.int64, device=dev) * L)
     torch.cuda.synchronize()

@@ -1145,6 +1145,8 @@ static int run_sub_batch(mtsvgpu_index* h, const Params& p, const uint8_t* d_seq
               ws.out_hit_off.as<uint64_t>(), read0 - batch_read0);
   clk.end();
   MTSV_CUDA_TRY(cudaGetLastError());
+  // host API: start copying this sub-batch's results out while the next one computes
+  if (h->results_hook) MTSV_TRY(h->results_hook(h, *out_total, sub_out, read0 - batch_read0, n_reads));
   clk.resolve();
   *out_total += sub_out;
   h->stats.n_hits += sub_out;

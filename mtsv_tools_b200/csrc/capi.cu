@@ -93,6 +93,32 @@ static int wait_for_sub_batch_input(mtsvgpu_index* ix, uint64_t i) {
   return 0;
 }
 
+// Results of a finished sub-batch go to the pinned result buffers on the copy-out stream while the next
+// sub-batch computes.  Only used when the pinned buffers are known to be large enough (they keep the size
+// of earlier batches); otherwise everything is copied at the end.
+static int copy_results_slice(mtsvgpu_index* ix, uint64_t first_hit, uint64_t n_hits, uint64_t first_read,
+                              uint64_t n_reads) {
+  if (!ix->out_overlap_ok) return 0;
+  if ((first_hit + n_hits) * sizeof(mtsvgpu_hit) > ix->pin_hits_cap ||
+      (first_read + n_reads + 1) * sizeof(uint64_t) > ix->pin_off_cap || first_hit != ix->out_copied_hits ||
+      first_read != ix->out_copied_reads) {
+    ix->out_overlap_ok = false;  // does not fit / unexpected order: the caller copies everything at the end
+    return 0;
+  }
+  MTSV_CUDA_TRY(cudaEventRecord(ix->out_event, ix->stream));
+  MTSV_CUDA_TRY(cudaStreamWaitEvent(ix->copy_out_stream, ix->out_event, 0));
+  const mtsvgpu_hit* d_hits = ix->ws.out_hits.as<mtsvgpu_hit>();
+  const uint64_t* d_off = ix->ws.out_hit_off.as<uint64_t>();
+  if (n_hits)
+    MTSV_CUDA_TRY(cudaMemcpyAsync((mtsvgpu_hit*)ix->pin_hits + first_hit, d_hits + first_hit,
+                                  n_hits * sizeof(mtsvgpu_hit), cudaMemcpyDeviceToHost, ix->copy_out_stream));
+  MTSV_CUDA_TRY(cudaMemcpyAsync((uint64_t*)ix->pin_off + first_read, d_off + first_read,
+                                (n_reads + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, ix->copy_out_stream));
+  ix->out_copied_hits = first_hit + n_hits;
+  ix->out_copied_reads = first_read + n_reads;
+  return 0;
+}
+
 // Host-buffer batch: the reads are uploaded sub-batch by sub-batch on a copy stream while earlier
 // sub-batches compute (pass page-locked buffers to get the overlap; pageable ones work, serially).
 // pinned_result: 0 = results in malloc'ed memory (mtsvgpu_free), 1 = in the handle's page-locked
@@ -142,11 +168,20 @@ static int bin_batch_host(mtsvgpu_index* ix, const uint8_t* seqs, const uint64_t
   const uint64_t* d_hit_off = nullptr;
   uint64_t n_hits = 0;
   ix->sub_batch_hook = wait_for_sub_batch_input;
+  // overlap the result copy when the pinned buffers from earlier batches are big enough for this one
+  ix->out_copied_hits = ix->out_copied_reads = 0;
+  ix->out_overlap_ok = pinned_result && ix->pin_hits && ix->pin_off &&
+                       (n_reads + 1) * sizeof(uint64_t) <= ix->pin_off_cap;
+  ix->results_hook = ix->out_overlap_ok ? copy_results_slice : nullptr;
+  // a device-side regrowth of the output buffer would invalidate copies in flight: reserve generously
+  if (ix->out_overlap_ok) (void)ws.out_hits.reserve(ix->pin_hits_cap);
   int rc = bin_batch_device(ix, ws.d_seqs.as<uint8_t>(), ws.d_seq_off.as<uint64_t>(), n_reads, offs, params,
                             &d_hits, &d_hit_off, &n_hits);
   ix->sub_batch_hook = nullptr;
+  ix->results_hook = nullptr;
   if (rc != 0) {
     cudaStreamSynchronize(cin);
+    cudaStreamSynchronize(ix->copy_out_stream);
     return rc;
   }
   MTSV_CUDA_TRY(cudaStreamSynchronize(cin));
@@ -169,9 +204,15 @@ static int bin_batch_host(mtsvgpu_index* ix, const uint8_t* seqs, const uint64_t
     }
   }
   cudaError_t e = cudaSuccess;
-  if (n_hits) e = cudaMemcpyAsync(h_hits, d_hits, n_hits * sizeof(mtsvgpu_hit), cudaMemcpyDeviceToHost, st);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(h_off, d_hit_off, ob, cudaMemcpyDeviceToHost, st);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (pinned_result && ix->out_overlap_ok && ix->out_copied_hits == n_hits && ix->out_copied_reads == n_reads) {
+    e = cudaStreamSynchronize(ix->copy_out_stream);  // everything was copied slice by slice
+  } else {
+    e = cudaStreamSynchronize(ix->copy_out_stream);
+    if (e == cudaSuccess && n_hits)
+      e = cudaMemcpyAsync(h_hits, d_hits, n_hits * sizeof(mtsvgpu_hit), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h_off, d_hit_off, ob, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  }
   if (e != cudaSuccess) {
     if (!pinned_result) {
       free(h_hits);

@@ -150,6 +150,12 @@ struct mtsvgpu_index {
   cudaStream_t copy_in_stream = nullptr;
   std::vector<cudaEvent_t> in_events;
   int (*sub_batch_hook)(mtsvgpu_index*, uint64_t) = nullptr;  // called before each sub-batch
+  // called after each sub-batch's results are enqueued: (first hit, #hits, first read, #reads)
+  int (*results_hook)(mtsvgpu_index*, uint64_t, uint64_t, uint64_t, uint64_t) = nullptr;
+  cudaStream_t copy_out_stream = nullptr;
+  cudaEvent_t out_event = nullptr;
+  uint64_t out_copied_hits = 0, out_copied_reads = 0;  // prefix already on its way to the pinned buffers
+  bool out_overlap_ok = false;
   void* pin_hits = nullptr;
   size_t pin_hits_cap = 0;
   void* pin_off = nullptr;

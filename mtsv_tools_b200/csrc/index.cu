@@ -246,6 +246,8 @@ void index_destroy(mtsvgpu_index* h) {
   if (h->pin_off) cudaFreeHost(h->pin_off);
   for (cudaEvent_t e : h->in_events) cudaEventDestroy(e);
   if (h->copy_in_stream) cudaStreamDestroy(h->copy_in_stream);
+  if (h->copy_out_stream) cudaStreamDestroy(h->copy_out_stream);
+  if (h->out_event) cudaEventDestroy(h->out_event);
   for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;
@@ -328,6 +330,8 @@ int index_from_host_parts(const uint8_t* text, uint64_t n, const mtsvgpu_bin* bi
   MTSV_CUDA_TRY(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
   h->stream = h->own_stream;
   MTSV_CUDA_TRY(cudaStreamCreateWithFlags(&h->copy_in_stream, cudaStreamNonBlocking));
+  MTSV_CUDA_TRY(cudaStreamCreateWithFlags(&h->copy_out_stream, cudaStreamNonBlocking));
+  MTSV_CUDA_TRY(cudaEventCreateWithFlags(&h->out_event, cudaEventDisableTiming));
   cudaStream_t st = h->stream;
 
   // ---- text and bins ----
