@@ -23,7 +23,7 @@ namespace mtsv {
 // ------------------------------------------------------------------------------------------
 // small kernels
 // ------------------------------------------------------------------------------------------
-constexpr uint32_t kMaxReadLenDev = 1024;  // longer reads fail the batch (ELIMIT) before any seed work
+constexpr uint32_t kMaxReadLenDev = 4096;  // longer reads fail the batch (ELIMIT) before any seed work
 
 // adds `v` of every thread of the CTA into one of 32 counters with a single global atomic per CTA
 __device__ __forceinline__ void cta_accumulate(unsigned long long* counters32, unsigned int v) {
@@ -663,10 +663,10 @@ struct PairJobs {
   }
 };
 
-template <int W, int NCLS, typename Jobs>
+template <int W, int NCLS, bool SMEM_PEQ, typename Jobs>
 __global__ void __launch_bounds__(kVerifyThreads) verify_kernel(Jobs jobs, uint32_t* __restrict__ out,
                                                                 BatchCounters* __restrict__ ctr) {
-  extern __shared__ uint64_t peq[];  // [NCLS][W][kVerifyThreads]
+  extern __shared__ uint64_t peq[];  // [NCLS][W][kVerifyThreads] when SMEM_PEQ
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= jobs.n) return;
   VerifyJob job = jobs.get(i);
@@ -680,13 +680,16 @@ __global__ void __launch_bounds__(kVerifyThreads) verify_kernel(Jobs jobs, uint3
     return;
   }
   const int last = (int)((L - 1) >> 6);
-  // pattern-match masks straight from the read's bit planes
+  // pattern-match masks straight from the read's bit planes; for reads beyond 1024 bases (W > 16) they do
+  // not fit shared memory and are recomputed from the planes (L1-resident) at every use
+  if (SMEM_PEQ) {
 #pragma unroll
-  for (int w = 0; w < W; ++w) {
-    ReadWord rw{0, 0, ~0ull};
-    if (w <= last) rw = job.enc[w];
+    for (int w = 0; w < W; ++w) {
+      ReadWord rw{0, 0, ~0ull};
+      if (w <= last) rw = job.enc[w];
 #pragma unroll
-    for (int c = 0; c < NCLS; ++c) peq[(c * W + w) * kVerifyThreads + threadIdx.x] = word_peq(rw, c);
+      for (int c = 0; c < NCLS; ++c) peq[(c * W + w) * kVerifyThreads + threadIdx.x] = word_peq(rw, c);
+    }
   }
   // text is read through 8-byte aligned words (the device text has 16 bytes of slack at the end)
   struct TextReader {
@@ -703,7 +706,14 @@ __global__ void __launch_bounds__(kVerifyThreads) verify_kernel(Jobs jobs, uint3
   const uint64_t addr = (uint64_t)job.txt;
   TextReader text{reinterpret_cast<const uint64_t*>(addr & ~7ull), (uint32_t)(addr & 7ull), 0};
   const uint32_t T = job.T;
-  auto peq_f = [&](uint32_t c, int w) -> uint64_t { return peq[(c * W + w) * kVerifyThreads + threadIdx.x]; };
+  const ReadWord* enc = job.enc;
+  auto peq_f = [&](uint32_t c, int w) -> uint64_t {
+    if (SMEM_PEQ) return peq[(c * W + w) * kVerifyThreads + threadIdx.x];
+    ReadWord rw = enc[w];
+    uint64_t base = ~rw.nn;
+    uint64_t lo = (c & 1) ? rw.lo : ~rw.lo, hi = (c & 2) ? rw.hi : ~rw.hi;
+    return c < 4 ? (base & lo & hi) : (rw.nn & ~rw.lo & ~rw.hi);
+  };
   const uint32_t best = myers_bounded<W>(L, T, job.limit, peq_f, text);
   out[job.out] = best <= job.limit ? best : kNoEdit;
 }
@@ -716,8 +726,9 @@ static int launch_verify(const Jobs& jobs, uint32_t max_len, uint32_t* out, Batc
   unsigned grid = (jobs.n + kVerifyThreads - 1) / kVerifyThreads;
 #define MTSV_VERIFY_CASE(WW)                                                                      \
   {                                                                                               \
-    size_t smem = (size_t)NCLS * WW * kVerifyThreads * sizeof(uint64_t);                          \
-    auto kfn = verify_kernel<WW, NCLS, Jobs>;                                                     \
+    constexpr bool kSmem = (WW) <= 16;                                                            \
+    size_t smem = kSmem ? (size_t)NCLS * WW * kVerifyThreads * sizeof(uint64_t) : 0;              \
+    auto kfn = verify_kernel<WW, NCLS, kSmem, Jobs>;                                              \
     if (smem > 48 * 1024)                                                                         \
       MTSV_CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
     MTSV_LAUNCH(kfn, grid, kVerifyThreads, smem, st, jobs, out, ctr);                             \
@@ -728,13 +739,15 @@ static int launch_verify(const Jobs& jobs, uint32_t max_len, uint32_t* out, Batc
   else if (words <= 4) MTSV_VERIFY_CASE(4)
   else if (words <= 8) MTSV_VERIFY_CASE(8)
   else if (words <= 16) MTSV_VERIFY_CASE(16)
-  else return set_error(MTSVGPU_ELIMIT, "pattern of %u bases exceeds the verifier limit of 1024", max_len);
+  else if (words <= 32) MTSV_VERIFY_CASE(32)
+  else if (words <= 64) MTSV_VERIFY_CASE(64)
+  else return set_error(MTSVGPU_ELIMIT, "pattern of %u bases exceeds the verifier limit of 4096", max_len);
 #undef MTSV_VERIFY_CASE
   MTSV_CUDA_TRY(cudaGetLastError());
   return 0;
 }
 
-constexpr uint32_t kMaxReadLen = 1024;
+constexpr uint32_t kMaxReadLen = 4096;
 
 // ------------------------------------------------------------------------------------------
 // select / emit

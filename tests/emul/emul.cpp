@@ -180,10 +180,10 @@ void emul_backward_search(void* p, const uint8_t* pat, uint32_t len, uint32_t* l
 uint32_t emul_edit_distance_k(const uint8_t* pat, uint32_t L, uint32_t rc, const uint8_t* txt, uint32_t T,
                               int ncls, uint32_t k) {
   if (L == 0) return 0;
-  if (L > 1024) return 0xffffffffu;
+  if (L > 4096) return 0xffffffffu;
   // pattern masks from the bit planes, as verify_kernel builds them
   std::vector<ReadWord> q = encode_query(pat, L, rc != 0, ncls == 5);
-  uint64_t peq[5][16];
+  uint64_t peq[5][64];
   memset(peq, 0, sizeof peq);
   for (uint32_t w = 0; w < (L + 63) / 64; ++w)
     for (int c = 0; c < ncls; ++c) peq[c][w] = word_peq(q[w], c);
@@ -192,7 +192,7 @@ uint32_t emul_edit_distance_k(const uint8_t* pat, uint32_t L, uint32_t rc, const
     uint32_t c = text_code(txt[j]);
     return c < (uint32_t)ncls ? c : 7u;
   };
-  return myers_bounded<16>(L, T, k, pf, tf);
+  return L <= 1024 ? myers_bounded<16>(L, T, k, pf, tf) : myers_bounded<64>(L, T, k, pf, tf);
 }
 
 uint32_t emul_edit_distance(const uint8_t* pat, uint32_t L, uint32_t rc, const uint8_t* txt, uint32_t T,
