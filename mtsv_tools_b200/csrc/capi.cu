@@ -153,16 +153,20 @@ static int bin_batch_host(mtsvgpu_index* ix, const uint8_t* seqs, const uint64_t
     MTSV_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     ix->in_events.push_back(e);
   }
-  MTSV_CUDA_TRY(cudaMemcpyAsync(ws.d_seq_off.p, offs, (n_reads + 1) * 8, cudaMemcpyHostToDevice, cin));
   for (uint64_t i = 0; i < n_sub; ++i) {
     uint64_t r0 = i * step, r1 = std::min(n_reads, r0 + step);
     if (r1 < r0 || offs[r1] < offs[r0]) return set_error(MTSVGPU_EINVAL, "seq_off is not monotone");
     uint64_t b0 = offs[r0], nb = offs[r1] - b0;
     if (b0 + nb > bytes) return set_error(MTSVGPU_EINVAL, "seq_off exceeds the reads buffer");
+    // offsets of the slice (r0 .. r1 inclusive) first, then its bases: sub-batch i can start as soon as
+    // its own slice has landed
+    MTSV_CUDA_TRY(cudaMemcpyAsync(ws.d_seq_off.as<uint64_t>() + r0, offs + r0, (r1 - r0 + 1) * 8,
+                                  cudaMemcpyHostToDevice, cin));
     if (nb)
       MTSV_CUDA_TRY(cudaMemcpyAsync(ws.d_seqs.as<uint8_t>() + b0, seqs + base + b0, nb, cudaMemcpyHostToDevice, cin));
     MTSV_CUDA_TRY(cudaEventRecord(ix->in_events[i], cin));
   }
+  if (n_sub == 0) MTSV_CUDA_TRY(cudaMemcpyAsync(ws.d_seq_off.p, offs, 8, cudaMemcpyHostToDevice, cin));
   // ---- compute (each sub-batch waits for its slice) ----
   const mtsvgpu_hit* d_hits = nullptr;
   const uint64_t* d_hit_off = nullptr;

@@ -6,6 +6,8 @@
 // Inputs: n_parts device arrays of mtsvgpu_hit, each with a per-read u32 count array for the same
 // n_reads reads (after the NCCL exchange every rank holds all parts for its own range of reads).
 // All kernels are flat over reads / hits; the per-read sort reuses the binner's segmented sorts.
+#include <mutex>
+
 #include "ctx.h"
 
 namespace mtsv {
@@ -76,17 +78,18 @@ int collapse_device(int device, cudaStream_t st, uint32_t n_parts, const mtsvgpu
   }
   MTSV_CUDA_TRY(cudaSetDevice(device));
   const uint32_t nr = (uint32_t)n_reads;
-  DevBuf offs[16], total, comb_off, keys, scan_tmp, counters, worklist, cnt_out, off_out32;
-  struct Cleanup {
-    DevBuf* a[16 + 9];
-    ~Cleanup() {
-      for (DevBuf* b : a)
-        if (b) b->release();
-    }
-  } cl{};
-  for (int i = 0; i < 16; ++i) cl.a[i] = &offs[i];
-  DevBuf* rest[9] = {&total, &comb_off, &keys, &scan_tmp, &counters, &worklist, &cnt_out, &off_out32, nullptr};
-  for (int i = 0; i < 9; ++i) cl.a[16 + i] = rest[i];
+  // grow-only workspace per device (cudaMalloc / cudaFree per call would cost more than the kernels)
+  struct Workspace {
+    DevBuf offs[16], total, comb_off, keys, scan_tmp, counters, worklist, cnt_out, off_out32;
+  };
+  static Workspace g_ws[16];
+  static std::mutex g_mu;
+  std::lock_guard<std::mutex> lock(g_mu);
+  if (device < 0 || device >= 16) return set_error(MTSVGPU_EINVAL, "device %d out of range", device);
+  Workspace& w = g_ws[device];
+  DevBuf* offs = w.offs;
+  DevBuf &total = w.total, &comb_off = w.comb_off, &keys = w.keys, &scan_tmp = w.scan_tmp,
+         &counters = w.counters, &worklist = w.worklist, &cnt_out = w.cnt_out, &off_out32 = w.off_out32;
 
   PartsView pv{};
   pv.n_parts = n_parts;
