@@ -666,15 +666,17 @@ MTSV_HD uint32_t myers_bounded(uint32_t L, uint32_t T, uint32_t k, PeqF peq, Tex
   uint32_t best = last == nb ? L : k + 1;
   const uint32_t slack = T + k;  // a row i at column j is useful only if i + slack >= L + j
   for (uint32_t j = 0; j < T; ++j) {
-    {
+    // House-keeping every 8th column only: early exit, band advance and (below) block drops merely
+    // prune work, so doing them late is always safe; activation of the next block is checked every column.
+    if ((j & 7) == 0) {
       uint32_t reach = (uint32_t)(last + 1) * 64;  // bottom row of the active region
       if (reach < L && (L - reach) > (T - j) + k) break;
-    }
-    // blocks entirely above the band at column j+1: 64(w+1) + slack < L + j + 1.  The bottom-most
-    // active block is never dropped this way: the activation of the block below needs its bottom cell.
+      // blocks entirely above the band at column j+1: 64(w+1) + slack < L + j + 1.  The bottom-most
+      // active block is never dropped this way: the activation of the block below needs its bottom cell.
 #pragma unroll
-    for (int w = 0; w < W - 1; ++w)
-      if (w == first && w < last && (uint32_t)(w + 1) * 64 + slack < L + j + 1) first = w + 1;
+      for (int w = 0; w < W - 1; ++w)
+        if (w == first && w < last && (uint32_t)(w + 1) * 64 + slack < L + j + 1) first = w + 1;
+    }
     const uint32_t c = text(j);
 #ifdef MTSV_COUNT_BLOCKS
     ++g_myers_cols;
@@ -714,11 +716,13 @@ MTSV_HD uint32_t myers_bounded(uint32_t L, uint32_t T, uint32_t k, PeqF peq, Tex
       }
     }
     // drop blocks that hold only values > k (keep the top-most active one)
+    if ((j & 7) == 7) {
 #pragma unroll
-    for (int w = W - 1; w >= 1; --w) {
-      if (w <= nb && w == last && w > first) {
-        uint32_t rows = w == nb ? L - (uint32_t)w * 64 : 64u;
-        if (bs[w] >= k + rows) last = w - 1;
+      for (int w = W - 1; w >= 1; --w) {
+        if (w <= nb && w == last && w > first) {
+          uint32_t rows = w == nb ? L - (uint32_t)w * 64 : 64u;
+          if (bs[w] >= k + rows) last = w - 1;
+        }
       }
     }
     if (bottom_score < best) best = bottom_score;
