@@ -392,6 +392,26 @@ __global__ void __launch_bounds__(1024) sort_large_kernel(uint64_t* __restrict__
 // hit thousands of loci) is handled by the whole warp so that one heavy read does not serialise 31
 // idle lanes behind it.  Heavy queries are taken one after the other (ballot loop).
 
+// Batcher's odd-even merge sort as a register sorting network (written out: 63 compare-exchanges for 16 keys, verified with the 0-1 principle), the same for every lane, so a warp whose lanes hold
+// differently ordered lists does not diverge (an insertion sort here cost 60 % of coalesce_kernel).
+__device__ __forceinline__ void sort_network16(uint64_t (&v)[16]) {
+#define CE(a, b)                      \
+  {                                   \
+    uint64_t x_ = v[a], y_ = v[b];    \
+    v[a] = x_ < y_ ? x_ : y_;         \
+    v[b] = x_ < y_ ? y_ : x_;         \
+  }
+  CE(0, 1) CE(2, 3) CE(4, 5) CE(6, 7) CE(8, 9) CE(10, 11) CE(12, 13) CE(14, 15)
+  CE(0, 2) CE(1, 3) CE(4, 6) CE(5, 7) CE(8, 10) CE(9, 11) CE(12, 14) CE(13, 15)
+  CE(1, 2) CE(5, 6) CE(9, 10) CE(13, 14) CE(0, 4) CE(1, 5) CE(2, 6) CE(3, 7)
+  CE(8, 12) CE(9, 13) CE(10, 14) CE(11, 15) CE(2, 4) CE(3, 5) CE(10, 12) CE(11, 13)
+  CE(1, 2) CE(3, 4) CE(5, 6) CE(9, 10) CE(11, 12) CE(13, 14) CE(0, 8) CE(1, 9)
+  CE(2, 10) CE(3, 11) CE(4, 12) CE(5, 13) CE(6, 14) CE(7, 15) CE(4, 8) CE(5, 9)
+  CE(6, 10) CE(7, 11) CE(2, 4) CE(3, 5) CE(6, 8) CE(7, 9) CE(10, 12) CE(11, 13)
+  CE(1, 2) CE(3, 4) CE(5, 6) CE(7, 8) CE(9, 10) CE(11, 12) CE(13, 14)
+#undef CE
+}
+
 __device__ __forceinline__ bool carry_valid_or_lane(unsigned lane, bool carry_valid) {
   return lane > 0 || carry_valid;  // lane 0 compares with the previous tile's last hit, if there is one
 }
@@ -518,16 +538,17 @@ __global__ void __launch_bounds__(128) coalesce_kernel(BinsView bv, ReadsView rv
       ms = min_seeds_of(q_nseeds[q], p.min_seed);
       base = hit_off[q];
       if (nh <= kLightItems) {
-        // few hits: this lane orders them itself (they arrive seed by seed, i.e. almost sorted)
+        // few hits: this lane orders them itself with a register sorting network
         uint64_t* kq = hit_keys + base;
-        for (uint32_t i = 1; i < nh; ++i) {
-          uint64_t v = kq[i];
-          uint32_t j = i;
-          while (j > 0 && kq[j - 1] > v) {
-            kq[j] = kq[j - 1];
-            --j;
-          }
-          kq[j] = v;
+        if (nh > 1) {
+          uint64_t v[kLightItems];
+#pragma unroll
+          for (uint32_t i = 0; i < kLightItems; ++i) v[i] = i < nh ? kq[i] : ~0ull;
+          static_assert(kLightItems == 16, "sort_network16 sorts exactly 16 keys");
+          sort_network16(v);
+#pragma unroll
+          for (uint32_t i = 0; i < kLightItems; ++i)
+            if (i < nh) kq[i] = v[i];
         }
         nc = coalesce_item(bv, kq, nh, ms, L, k, cand_sparse + base, rank_keys + base);
       }
