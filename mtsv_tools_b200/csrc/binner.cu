@@ -523,7 +523,9 @@ __global__ void __launch_bounds__(128) coalesce_kernel(BinsView bv, ReadsView rv
                                                        uint64_t* __restrict__ hit_keys,
                                                        CandRec* __restrict__ cand_sparse,
                                                        uint64_t* __restrict__ rank_keys,
-                                                       uint32_t* __restrict__ q_ncand) {
+                                                       uint32_t* __restrict__ q_ncand,
+                                                       uint32_t* __restrict__ heavy_list,
+                                                       BatchCounters* __restrict__ ctr) {
   // one lane per read: its strands are taken one after the other (usually exactly one of them has
   // hits, so lanes carry similar loads); a strand with many hits is handed to the whole warp
   const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
@@ -553,18 +555,40 @@ __global__ void __launch_bounds__(128) coalesce_kernel(BinsView bv, ReadsView rv
         nc = coalesce_item(bv, kq, nh, ms, L, k, cand_sparse + base, rank_keys + base);
       }
     }
+    // strands with many hits go to a work list: coalesce_heavy_kernel gives each of them a warp of its
+    // own, so one warp never has to work through several heavy strands one after the other
     unsigned heavy = __ballot_sync(0xffffffffu, nh > kLightItems);
-    while (heavy) {
-      int src = __ffs(heavy) - 1;
-      heavy &= heavy - 1;
-      uint32_t nh_s = __shfl_sync(0xffffffffu, nh, src), base_s = __shfl_sync(0xffffffffu, base, src);
-      uint32_t L_s = __shfl_sync(0xffffffffu, L, src), k_s = __shfl_sync(0xffffffffu, k, src);
-      uint32_t ms_s = __shfl_sync(0xffffffffu, ms, src);
-      uint32_t rr = coalesce_warp(bv, hit_keys + base_s, nh_s, ms_s, L_s, k_s, cand_sparse + base_s,
-                                  rank_keys + base_s);
-      if ((int)lane == src) nc = rr;
+    if (heavy) {
+      uint32_t slot = 0;
+      if (lane == (unsigned)(__ffs(heavy) - 1)) slot = atomicAdd(&ctr->n_heavy, (unsigned)__popc(heavy));
+      slot = __shfl_sync(0xffffffffu, slot, __ffs(heavy) - 1);
+      if (nh > kLightItems) heavy_list[slot + __popc(heavy & ((1u << lane) - 1))] = q;
     }
-    if (q < nq) q_ncand[q] = nc;
+    if (q < nq && nh <= kLightItems) q_ncand[q] = nc;
+  }
+}
+
+__global__ void __launch_bounds__(128) coalesce_heavy_kernel(BinsView bv, ReadsView rv, Params p,
+                                                             const uint32_t* __restrict__ hit_off,
+                                                             const uint32_t* __restrict__ q_nhits,
+                                                             const uint32_t* __restrict__ q_nseeds,
+                                                             const uint64_t* __restrict__ hit_keys,
+                                                             CandRec* __restrict__ cand_sparse,
+                                                             uint64_t* __restrict__ rank_keys,
+                                                             uint32_t* __restrict__ q_ncand,
+                                                             const uint32_t* __restrict__ heavy_list,
+                                                             const BatchCounters* __restrict__ ctr) {
+  const unsigned lane = threadIdx.x & 31;
+  const uint32_t n_list = ctr->n_heavy;
+  const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t it = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; it < n_list; it += warps) {
+    const uint32_t q = heavy_list[it];
+    const uint32_t L = query_len(rv, p.ns, q);
+    const uint32_t k = edit_budget(L, p.edit_rate);
+    const uint32_t ms = min_seeds_of(q_nseeds[q], p.min_seed);
+    const uint32_t base = hit_off[q];
+    uint32_t nc = coalesce_warp(bv, hit_keys + base, q_nhits[q], ms, L, k, cand_sparse + base, rank_keys + base);
+    if (lane == 0) q_ncand[q] = nc;
   }
 }
 
@@ -1114,10 +1138,15 @@ static int run_sub_batch(mtsvgpu_index* h, const Params& p, const uint8_t* d_seq
     clk.end();
     // ---- coalesce ----
     clk.begin(ST_COALESCE);
+    MTSV_CUDA_TRY(cudaMemsetAsync(&d_ctr->n_heavy, 0, sizeof(unsigned int), st));
     MTSV_LAUNCH(coalesce_kernel, (n_reads + 127) / 128, 128, 0, st, ix.bins_view(), rv, p, nq,
                 ws.hit_off.as<uint32_t>(), ws.q_nhits.as<uint32_t>(), ws.q_nseeds.as<uint32_t>(),
                 ws.hit_keys.as<uint64_t>(), ws.cand_sparse.as<CandRec>(), ws.rank_keys.as<uint64_t>(),
-                ws.q_ncand.as<uint32_t>());
+                ws.q_ncand.as<uint32_t>(), ws.worklist.as<uint32_t>(), d_ctr);
+    MTSV_LAUNCH(coalesce_heavy_kernel, 148 * 8, 128, 0, st, ix.bins_view(), rv, p, ws.hit_off.as<uint32_t>(),
+                ws.q_nhits.as<uint32_t>(), ws.q_nseeds.as<uint32_t>(), ws.hit_keys.as<uint64_t>(),
+                ws.cand_sparse.as<CandRec>(), ws.rank_keys.as<uint64_t>(), ws.q_ncand.as<uint32_t>(),
+                ws.worklist.as<uint32_t>(), d_ctr);
     MTSV_TRY(exclusive_scan_u32(ws.q_ncand.as<uint32_t>(), ws.cand_off.as<uint32_t>(), nq, ws.scan_tmp,
                                 (uint64_t*)&d_ctr->total_cands, st));
     clk.end();
