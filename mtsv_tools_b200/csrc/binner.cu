@@ -577,11 +577,16 @@ __global__ void __launch_bounds__(128) coalesce_heavy_kernel(BinsView bv, ReadsV
                                                              uint64_t* __restrict__ rank_keys,
                                                              uint32_t* __restrict__ q_ncand,
                                                              const uint32_t* __restrict__ heavy_list,
-                                                             const BatchCounters* __restrict__ ctr) {
+                                                             BatchCounters* __restrict__ ctr) {
   const unsigned lane = threadIdx.x & 31;
   const uint32_t n_list = ctr->n_heavy;
-  const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
-  for (uint32_t it = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; it < n_list; it += warps) {
+  // strands differ by orders of magnitude (17 .. tens of thousands of hits): warps take the next strand
+  // from a shared cursor instead of a fixed stride
+  for (;;) {
+    uint32_t it = 0;
+    if (lane == 0) it = atomicAdd(&ctr->heavy_cursor, 1u);
+    it = __shfl_sync(0xffffffffu, it, 0);
+    if (it >= n_list) break;
     const uint32_t q = heavy_list[it];
     const uint32_t L = query_len(rv, p.ns, q);
     const uint32_t k = edit_budget(L, p.edit_rate);
@@ -1138,12 +1143,12 @@ static int run_sub_batch(mtsvgpu_index* h, const Params& p, const uint8_t* d_seq
     clk.end();
     // ---- coalesce ----
     clk.begin(ST_COALESCE);
-    MTSV_CUDA_TRY(cudaMemsetAsync(&d_ctr->n_heavy, 0, sizeof(unsigned int), st));
+    MTSV_CUDA_TRY(cudaMemsetAsync(&d_ctr->n_heavy, 0, 2 * sizeof(unsigned int), st));
     MTSV_LAUNCH(coalesce_kernel, (n_reads + 127) / 128, 128, 0, st, ix.bins_view(), rv, p, nq,
                 ws.hit_off.as<uint32_t>(), ws.q_nhits.as<uint32_t>(), ws.q_nseeds.as<uint32_t>(),
                 ws.hit_keys.as<uint64_t>(), ws.cand_sparse.as<CandRec>(), ws.rank_keys.as<uint64_t>(),
                 ws.q_ncand.as<uint32_t>(), ws.worklist.as<uint32_t>(), d_ctr);
-    MTSV_LAUNCH(coalesce_heavy_kernel, 148 * 8, 128, 0, st, ix.bins_view(), rv, p, ws.hit_off.as<uint32_t>(),
+    MTSV_LAUNCH(coalesce_heavy_kernel, 148 * 16, 128, 0, st, ix.bins_view(), rv, p, ws.hit_off.as<uint32_t>(),
                 ws.q_nhits.as<uint32_t>(), ws.q_nseeds.as<uint32_t>(), ws.hit_keys.as<uint64_t>(),
                 ws.cand_sparse.as<CandRec>(), ws.rank_keys.as<uint64_t>(), ws.q_ncand.as<uint32_t>(),
                 ws.worklist.as<uint32_t>(), d_ctr);

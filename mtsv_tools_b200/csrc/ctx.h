@@ -52,7 +52,7 @@ struct DevBuf {
 
 struct BatchCounters {  // device-side scalars of one sub-batch
   unsigned long long total_slots, total_hits, total_cands, total_out;
-  unsigned int max_len, overflow, n_warp, n_medium, n_large, bad_offsets, n_heavy, reserved1;
+  unsigned int max_len, overflow, n_warp, n_medium, n_large, bad_offsets, n_heavy, heavy_cursor;
   unsigned long long rank_steps[32], window_bytes[32];  // profiling only; spread to avoid one hot address
 };
 
