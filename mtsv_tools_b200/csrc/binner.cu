@@ -428,36 +428,64 @@ __device__ uint32_t coalesce_warp(const BinsView& bv, const uint64_t* __restrict
   CandRec cur{0, 0, 0, 0};
   uint32_t carry_site = 0, carry_bin = 0;  // last hit of the previous tile
   bool carry_valid = false;
-  for (uint32_t t0 = 0; t0 < n_hits; t0 += 32) {
-    uint32_t h = t0 + lane;
-    uint32_t ws = 0, we = 0, b = 0, site = 0;
-    bool some = false;
-    if (h < n_hits) {
-      uint64_t key = keys[h];
-      site = (uint32_t)(key >> 16);
-      uint32_t q_off = (uint32_t)(key & 0xffff);
-      b = find_bin(bv, site);
-      some = candidate_window(site, q_off, ldg(&bv.start[b]), ldg(&bv.end[b]), L, k, &ws, &we);
+  // The automaton itself is cheap; what a long strand waits for is memory (keys, bins).  Four tiles of
+  // 32 hits are therefore fetched together — the four key loads and the four branch-free binary searches
+  // over the bin ends proceed in lock step, i.e. with four loads in flight — and then replayed in order.
+  constexpr int U = 4;
+  uint32_t top = 1;
+  while (top < bv.n) top <<= 1;
+  for (uint32_t g0 = 0; g0 < n_hits; g0 += 32 * U) {
+    uint32_t site[U], qoff[U], b[U], ws[U], we[U];
+    bool some[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      uint32_t h = g0 + u * 32 + lane;
+      uint64_t key = h < n_hits ? keys[h] : 0;
+      site[u] = (uint32_t)(key >> 16);
+      qoff[u] = (uint32_t)(key & 0xffff);
+      b[u] = 0;
     }
-    uint32_t cnt = n_hits - t0 < 32 ? n_hits - t0 : 32;
-    // Fast path.  A hit whose site lies >= 2(L+k) after its predecessor (or in another bin) cannot
-    // overlap any window accumulated so far (windows reach at most L+k either side of their site and
-    // hits are sorted by site), so it certainly starts a new candidate.  If that holds for every hit
-    // of the tile the automaton degenerates: flush the incoming candidate, emit every hit but the last
-    // as a single-seed candidate, carry the last.  Typical for reads whose seeds hit hundreds of
-    // unrelated loci.
-    {
-      uint32_t prev_site = __shfl_up_sync(0xffffffffu, site, 1);
-      uint32_t prev_b = __shfl_up_sync(0xffffffffu, b, 1);
+    // first bin with end > site == number of bins with end <= site (src/index.rs:455-458)
+    for (uint32_t step = top; step >= 1; step >>= 1) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        uint32_t idx = b[u] + step;
+        if (idx <= bv.n && ldg(&bv.end[idx - 1]) <= site[u]) b[u] = idx;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      uint32_t h = g0 + u * 32 + lane;
+      ws[u] = we[u] = 0;
+      some[u] = false;
+      if (h < n_hits) {
+        if (b[u] >= bv.n) b[u] = bv.n - 1;  // cannot happen for a seed hit (it lies before the '$')
+        some[u] = candidate_window(site[u], qoff[u], ldg(&bv.start[b[u]]), ldg(&bv.end[b[u]]), L, k, &ws[u], &we[u]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const uint32_t t0 = g0 + u * 32;
+      if (t0 >= n_hits) break;
+      const uint32_t h = t0 + lane;
+      const uint32_t cnt = n_hits - t0 < 32 ? n_hits - t0 : 32;
+      // Fast path.  A hit whose site lies >= 2(L+k) after its predecessor (or in another bin) cannot
+      // overlap any window accumulated so far (windows reach at most L+k either side of their site and
+      // hits are sorted by site), so it certainly starts a new candidate.  If that holds for every hit
+      // of the tile the automaton degenerates: flush the incoming candidate, emit every hit but the last
+      // as a single-seed candidate, carry the last.  Typical for reads whose seeds hit hundreds of
+      // unrelated loci.
+      uint32_t prev_site = __shfl_up_sync(0xffffffffu, site[u], 1);
+      uint32_t prev_b = __shfl_up_sync(0xffffffffu, b[u], 1);
       if (lane == 0) {
         prev_site = carry_site;
         prev_b = carry_bin;
       }
-      bool brk = h >= n_hits || !carry_valid_or_lane(lane, carry_valid) || b != prev_b ||
-                 (uint64_t)site >= (uint64_t)prev_site + 2ull * ((uint64_t)L + k);
+      bool brk = h >= n_hits || !carry_valid_or_lane(lane, carry_valid) || b[u] != prev_b ||
+                 (uint64_t)site[u] >= (uint64_t)prev_site + 2ull * ((uint64_t)L + k);
       bool all_break = __all_sync(0xffffffffu, brk);
-      uint32_t last_site = __shfl_sync(0xffffffffu, site, cnt - 1), last_b = __shfl_sync(0xffffffffu, b, cnt - 1);
-      carry_site = last_site;
+      const uint32_t last_b = __shfl_sync(0xffffffffu, b[u], cnt - 1);
+      carry_site = __shfl_sync(0xffffffffu, site[u], cnt - 1);
       carry_bin = last_b;
       carry_valid = true;
       if (all_break) {
@@ -468,41 +496,41 @@ __device__ uint32_t coalesce_warp(const BinsView& bv, const uint64_t* __restrict
           }
           ++nc;
         }
-        bool emit = h + 1 < t0 + cnt && some && 1u >= min_seeds;  // every hit of the tile except the last
+        bool emit = h + 1 < t0 + cnt && some[u] && 1u >= min_seeds;  // every hit of the tile except the last
         unsigned em = __ballot_sync(0xffffffffu, emit);
         if (emit) {
           uint32_t pos = nc + __popc(em & ((1u << lane) - 1));
-          cand[pos] = CandRec{ws, we, b, 1};
+          cand[pos] = CandRec{ws[u], we[u], b[u], 1};
           rkey[pos] = make_rank_key(1, pos);
         }
         nc += __popc(em);
-        have = __shfl_sync(0xffffffffu, (int)some, cnt - 1) != 0;
-        cur = CandRec{__shfl_sync(0xffffffffu, ws, cnt - 1), __shfl_sync(0xffffffffu, we, cnt - 1), last_b, 1};
+        have = __shfl_sync(0xffffffffu, (int)some[u], cnt - 1) != 0;
+        cur = CandRec{__shfl_sync(0xffffffffu, ws[u], cnt - 1), __shfl_sync(0xffffffffu, we[u], cnt - 1), last_b, 1};
         continue;
       }
-    }
-    for (uint32_t i = 0; i < cnt; ++i) {
-      uint32_t ws_i = __shfl_sync(0xffffffffu, ws, i), we_i = __shfl_sync(0xffffffffu, we, i);
-      uint32_t b_i = __shfl_sync(0xffffffffu, b, i);
-      bool some_i = __shfl_sync(0xffffffffu, (int)some, i) != 0;
-      bool merged = false;
-      if (have && some_i && b_i == cur.bin &&
-          ((cur.start <= ws_i && ws_i < cur.end) || (cur.start < we_i && we_i <= cur.end))) {
-        cur.start = ws_i < cur.start ? ws_i : cur.start;
-        cur.end = we_i > cur.end ? we_i : cur.end;
-        cur.num_seeds += 1;
-        merged = true;
-      }
-      if (!merged) {
-        if (have && cur.num_seeds >= min_seeds) {
-          if (lane == 0) {
-            cand[nc] = cur;
-            rkey[nc] = make_rank_key(cur.num_seeds, nc);
-          }
-          ++nc;
+      for (uint32_t i = 0; i < cnt; ++i) {
+        uint32_t ws_i = __shfl_sync(0xffffffffu, ws[u], i), we_i = __shfl_sync(0xffffffffu, we[u], i);
+        uint32_t b_i = __shfl_sync(0xffffffffu, b[u], i);
+        bool some_i = __shfl_sync(0xffffffffu, (int)some[u], i) != 0;
+        bool merged = false;
+        if (have && some_i && b_i == cur.bin &&
+            ((cur.start <= ws_i && ws_i < cur.end) || (cur.start < we_i && we_i <= cur.end))) {
+          cur.start = ws_i < cur.start ? ws_i : cur.start;
+          cur.end = we_i > cur.end ? we_i : cur.end;
+          cur.num_seeds += 1;
+          merged = true;
         }
-        have = some_i;
-        if (some_i) cur = CandRec{ws_i, we_i, b_i, 1};
+        if (!merged) {
+          if (have && cur.num_seeds >= min_seeds) {
+            if (lane == 0) {
+              cand[nc] = cur;
+              rkey[nc] = make_rank_key(cur.num_seeds, nc);
+            }
+            ++nc;
+          }
+          have = some_i;
+          if (some_i) cur = CandRec{ws_i, we_i, b_i, 1};
+        }
       }
     }
   }
