@@ -420,8 +420,7 @@ __device__ __forceinline__ bool carry_valid_or_lane(unsigned lane, bool carry_va
 // hits at a time, then every lane replays the (cheap, inherently sequential) merge automaton on the
 // shuffled windows so that control flow stays uniform; lane 0 writes.
 __device__ uint32_t coalesce_warp(const BinsView& bv, const uint64_t* __restrict__ keys, uint32_t n_hits,
-                                  uint32_t min_seeds, uint32_t L, uint32_t k, CandRec* __restrict__ cand,
-                                  uint64_t* __restrict__ rkey) {
+                                  uint32_t min_seeds, uint32_t L, uint32_t k, CandRec* __restrict__ cand) {
   const unsigned lane = threadIdx.x & 31;
   uint32_t nc = 0;
   bool have = false;
@@ -492,7 +491,6 @@ __device__ uint32_t coalesce_warp(const BinsView& bv, const uint64_t* __restrict
         if (have && cur.num_seeds >= min_seeds) {
           if (lane == 0) {
             cand[nc] = cur;
-            rkey[nc] = make_rank_key(cur.num_seeds, nc);
           }
           ++nc;
         }
@@ -501,7 +499,6 @@ __device__ uint32_t coalesce_warp(const BinsView& bv, const uint64_t* __restrict
         if (emit) {
           uint32_t pos = nc + __popc(em & ((1u << lane) - 1));
           cand[pos] = CandRec{ws[u], we[u], b[u], 1};
-          rkey[pos] = make_rank_key(1, pos);
         }
         nc += __popc(em);
         have = __shfl_sync(0xffffffffu, (int)some[u], cnt - 1) != 0;
@@ -524,7 +521,6 @@ __device__ uint32_t coalesce_warp(const BinsView& bv, const uint64_t* __restrict
           if (have && cur.num_seeds >= min_seeds) {
             if (lane == 0) {
               cand[nc] = cur;
-              rkey[nc] = make_rank_key(cur.num_seeds, nc);
             }
             ++nc;
           }
@@ -537,7 +533,6 @@ __device__ uint32_t coalesce_warp(const BinsView& bv, const uint64_t* __restrict
   if (have && cur.num_seeds >= min_seeds) {
     if (lane == 0) {
       cand[nc] = cur;
-      rkey[nc] = make_rank_key(cur.num_seeds, nc);
     }
     ++nc;
   }
@@ -550,7 +545,6 @@ __global__ void __launch_bounds__(128) coalesce_kernel(BinsView bv, ReadsView rv
                                                        const uint32_t* __restrict__ q_nseeds,
                                                        uint64_t* __restrict__ hit_keys,
                                                        CandRec* __restrict__ cand_sparse,
-                                                       uint64_t* __restrict__ rank_keys,
                                                        uint32_t* __restrict__ q_ncand,
                                                        uint32_t* __restrict__ heavy_list,
                                                        BatchCounters* __restrict__ ctr) {
@@ -580,7 +574,7 @@ __global__ void __launch_bounds__(128) coalesce_kernel(BinsView bv, ReadsView rv
           for (uint32_t i = 0; i < kLightItems; ++i)
             if (i < nh) kq[i] = v[i];
         }
-        nc = coalesce_item(bv, kq, nh, ms, L, k, cand_sparse + base, rank_keys + base);
+        nc = coalesce_item(bv, kq, nh, ms, L, k, cand_sparse + base);
       }
     }
     // strands with many hits go to a work list: coalesce_heavy_kernel gives each of them a warp of its
@@ -602,7 +596,6 @@ __global__ void __launch_bounds__(128) coalesce_heavy_kernel(BinsView bv, ReadsV
                                                              const uint32_t* __restrict__ q_nseeds,
                                                              const uint64_t* __restrict__ hit_keys,
                                                              CandRec* __restrict__ cand_sparse,
-                                                             uint64_t* __restrict__ rank_keys,
                                                              uint32_t* __restrict__ q_ncand,
                                                              const uint32_t* __restrict__ heavy_list,
                                                              BatchCounters* __restrict__ ctr) {
@@ -620,15 +613,19 @@ __global__ void __launch_bounds__(128) coalesce_heavy_kernel(BinsView bv, ReadsV
     const uint32_t k = edit_budget(L, p.edit_rate);
     const uint32_t ms = min_seeds_of(q_nseeds[q], p.min_seed);
     const uint32_t base = hit_off[q];
-    uint32_t nc = coalesce_warp(bv, hit_keys + base, q_nhits[q], ms, L, k, cand_sparse + base, rank_keys + base);
+    uint32_t nc = coalesce_warp(bv, hit_keys + base, q_nhits[q], ms, L, k, cand_sparse + base);
     if (lane == 0) q_ncand[q] = nc;
   }
 }
 
+// Candidate ranking (src/index.rs:369: stable sort by num_seeds descending) + compaction into the dense
+// candidate list.  No sort is needed: a lane with a handful of candidates selects them in order; for a
+// strand with many candidates the warp emits, for each distinct num_seeds value from the largest down,
+// the candidates holding it in discovery order (ballot compaction) — the values are few (a chance hit
+// has num_seeds 1) even when the candidates are thousands.
 __global__ void __launch_bounds__(256) rank_emit_kernel(uint32_t nq, const uint32_t* __restrict__ hit_off,
                                                         const uint32_t* __restrict__ q_ncand,
                                                         const uint32_t* __restrict__ cand_off,
-                                                        const uint64_t* __restrict__ rank_keys,
                                                         const CandRec* __restrict__ cand_sparse,
                                                         CandRec* __restrict__ cand_dense,
                                                         uint32_t* __restrict__ cand_q) {
@@ -640,18 +637,15 @@ __global__ void __launch_bounds__(256) rank_emit_kernel(uint32_t nq, const uint3
     src = hit_off[q];
     dst = cand_off[q];
     if (nc <= kLightItems) {
-      // few candidates: emit them in (num_seeds desc, discovery order) by repeated selection — the
-      // rank keys were not sorted for such a segment (src/index.rs:369 is a stable sort)
       uint64_t prev = 0;
       for (uint32_t i = 0; i < nc; ++i) {
         uint64_t best = ~0ull;
         for (uint32_t j = 0; j < nc; ++j) {
-          uint64_t kj = rank_keys[src + j];
+          uint64_t kj = make_rank_key(cand_sparse[src + j].num_seeds, j);
           if ((i == 0 || kj > prev) && kj < best) best = kj;
         }
         prev = best;
-        uint32_t idx = (uint32_t)(best & 0xffffffffu);
-        cand_dense[dst + i] = cand_sparse[src + idx];
+        cand_dense[dst + i] = cand_sparse[src + (uint32_t)(best & 0xffffffffu)];
         cand_q[dst + i] = q;
       }
     }
@@ -660,12 +654,36 @@ __global__ void __launch_bounds__(256) rank_emit_kernel(uint32_t nq, const uint3
   while (heavy) {
     int sl = __ffs(heavy) - 1;
     heavy &= heavy - 1;
-    uint32_t nc_s = __shfl_sync(0xffffffffu, nc, sl), src_s = __shfl_sync(0xffffffffu, src, sl);
-    uint32_t dst_s = __shfl_sync(0xffffffffu, dst, sl), q_s = __shfl_sync(0xffffffffu, q, sl);
-    for (uint32_t i = lane; i < nc_s; i += 32) {
-      uint32_t idx = (uint32_t)(rank_keys[src_s + i] & 0xffffffffu);
-      cand_dense[dst_s + i] = cand_sparse[src_s + idx];
-      cand_q[dst_s + i] = q_s;
+    const uint32_t nc_s = __shfl_sync(0xffffffffu, nc, sl), src_s = __shfl_sync(0xffffffffu, src, sl);
+    const uint32_t dst_s = __shfl_sync(0xffffffffu, dst, sl), q_s = __shfl_sync(0xffffffffu, q, sl);
+    uint32_t out = 0;
+    uint32_t bound = 0xffffffffu;  // emit values strictly below `bound`, largest first
+    while (out < nc_s) {
+      // next value = the largest num_seeds below bound
+      uint32_t v = 0;
+      for (uint32_t i = lane; i < nc_s; i += 32) {
+        uint32_t ns = cand_sparse[src_s + i].num_seeds;
+        if (ns < bound && ns > v) v = ns;
+      }
+      v = __reduce_max_sync(0xffffffffu, v);
+      for (uint32_t t0 = 0; t0 < nc_s; t0 += 32) {
+        uint32_t i = t0 + lane;
+        CandRec c{0, 0, 0, 0};
+        bool take = false;
+        if (i < nc_s) {
+          c = cand_sparse[src_s + i];
+          take = c.num_seeds == v;
+        }
+        unsigned m = __ballot_sync(0xffffffffu, take);
+        if (take) {
+          uint32_t pos = dst_s + out + __popc(m & ((1u << lane) - 1));
+          cand_dense[pos] = c;
+          cand_q[pos] = q_s;
+        }
+        out += __popc(m);
+      }
+      bound = v;
+      if (v == 0) break;  // cannot happen (num_seeds >= 1); guards against an endless loop
     }
   }
 }
@@ -1157,7 +1175,6 @@ static int run_sub_batch(mtsvgpu_index* h, const Params& p, const uint8_t* d_seq
   if (n_hits) {
     MTSV_TRY(ws.hit_keys.reserve((size_t)n_hits * 8));
     MTSV_TRY(ws.cand_sparse.reserve((size_t)n_hits * sizeof(CandRec)));
-    MTSV_TRY(ws.rank_keys.reserve((size_t)n_hits * 8));
     // ---- locate ----
     clk.begin(ST_LOCATE);
     MTSV_LAUNCH(locate_kernel, (n_slots + 255) / 256, 256, 0, st, ix.fm_view(), ix.sa_view(), p, slot_off,
@@ -1174,12 +1191,11 @@ static int run_sub_batch(mtsvgpu_index* h, const Params& p, const uint8_t* d_seq
     MTSV_CUDA_TRY(cudaMemsetAsync(&d_ctr->n_heavy, 0, 2 * sizeof(unsigned int), st));
     MTSV_LAUNCH(coalesce_kernel, (n_reads + 127) / 128, 128, 0, st, ix.bins_view(), rv, p, nq,
                 ws.hit_off.as<uint32_t>(), ws.q_nhits.as<uint32_t>(), ws.q_nseeds.as<uint32_t>(),
-                ws.hit_keys.as<uint64_t>(), ws.cand_sparse.as<CandRec>(), ws.rank_keys.as<uint64_t>(),
-                ws.q_ncand.as<uint32_t>(), ws.worklist.as<uint32_t>(), d_ctr);
+                ws.hit_keys.as<uint64_t>(), ws.cand_sparse.as<CandRec>(), ws.q_ncand.as<uint32_t>(),
+                ws.worklist.as<uint32_t>(), d_ctr);
     MTSV_LAUNCH(coalesce_heavy_kernel, 148 * 16, 128, 0, st, ix.bins_view(), rv, p, ws.hit_off.as<uint32_t>(),
                 ws.q_nhits.as<uint32_t>(), ws.q_nseeds.as<uint32_t>(), ws.hit_keys.as<uint64_t>(),
-                ws.cand_sparse.as<CandRec>(), ws.rank_keys.as<uint64_t>(), ws.q_ncand.as<uint32_t>(),
-                ws.worklist.as<uint32_t>(), d_ctr);
+                ws.cand_sparse.as<CandRec>(), ws.q_ncand.as<uint32_t>(), ws.worklist.as<uint32_t>(), d_ctr);
     MTSV_TRY(exclusive_scan_u32(ws.q_ncand.as<uint32_t>(), ws.cand_off.as<uint32_t>(), nq, ws.scan_tmp,
                                 (uint64_t*)&d_ctr->total_cands, st));
     clk.end();
@@ -1195,11 +1211,9 @@ static int run_sub_batch(mtsvgpu_index* h, const Params& p, const uint8_t* d_seq
     MTSV_TRY(ws.hit_tmp.reserve((size_t)n_cand * sizeof(HitRec)));
     // ---- rank ----
     clk.begin(ST_RANK);
-    MTSV_TRY(run_segmented_sort(st, ws.worklist, ws.rank_keys.as<uint64_t>(), ws.hit_off.as<uint32_t>(),
-                                ws.q_ncand.as<uint32_t>(), nq, kLightItems, d_ctr));
     MTSV_LAUNCH(rank_emit_kernel, qgrid, 256, 0, st, nq, ws.hit_off.as<uint32_t>(),
-                ws.q_ncand.as<uint32_t>(), ws.cand_off.as<uint32_t>(), ws.rank_keys.as<uint64_t>(),
-                ws.cand_sparse.as<CandRec>(), ws.cand_dense.as<CandRec>(), ws.cand_q.as<uint32_t>());
+                ws.q_ncand.as<uint32_t>(), ws.cand_off.as<uint32_t>(), ws.cand_sparse.as<CandRec>(),
+                ws.cand_dense.as<CandRec>(), ws.cand_q.as<uint32_t>());
     clk.end();
     // ---- verify ----
     clk.begin(ST_VERIFY);

@@ -547,16 +547,16 @@ struct CandRec {  // ReferenceCandidate (src/index.rs:158-165), 16 bytes
   uint32_t start, end, bin, num_seeds;
 };
 
-// rank key: ascending sort == `refs.sort_by(|a,b| b.num_seeds.cmp(&a.num_seeds))` (stable)
+// candidate ranking = `refs.sort_by(|a,b| b.num_seeds.cmp(&a.num_seeds))` (stable, src/index.rs:369):
+// by num_seeds descending, ties in discovery order.  Key form of that order (ascending):
 MTSV_HD uint64_t make_rank_key(uint32_t num_seeds, uint32_t idx) {
   return ((uint64_t)(~num_seeds) << 32) | idx;
 }
 
 // coalesce_seed_sites (src/index.rs:435-487) over the query's sorted hit keys.
-// Writes candidates (in discovery order) to cand[0..), their rank keys to rkey[0..); returns count.
+// Writes candidates (in discovery order) to cand[0..); returns their number.
 MTSV_HD uint32_t coalesce_item(const BinsView& bv, const uint64_t* keys, uint32_t n_hits,
-                               uint32_t min_seeds, uint32_t L, uint32_t k, CandRec* cand,
-                               uint64_t* rkey) {
+                               uint32_t min_seeds, uint32_t L, uint32_t k, CandRec* cand) {
   uint32_t nc = 0;
   bool have = false;
   CandRec cur{0, 0, 0, 0};
@@ -584,7 +584,6 @@ MTSV_HD uint32_t coalesce_item(const BinsView& bv, const uint64_t* keys, uint32_
     if (!merged) {
       if (have && cur.num_seeds >= min_seeds) {  // :467-469
         cand[nc] = cur;
-        rkey[nc] = make_rank_key(cur.num_seeds, nc);
         ++nc;
       }
       have = some;  // :472 / :475
@@ -593,7 +592,6 @@ MTSV_HD uint32_t coalesce_item(const BinsView& bv, const uint64_t* keys, uint32_
   }
   if (have && cur.num_seeds >= min_seeds) {  // :481-485
     cand[nc] = cur;
-    rkey[nc] = make_rank_key(cur.num_seeds, nc);
     ++nc;
   }
   return nc;

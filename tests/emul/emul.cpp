@@ -239,10 +239,11 @@ int emul_bin_reads(void* p, const uint8_t* seqs, const uint64_t* seq_off, uint64
     std::sort(keys.begin(), keys.end());
     uint32_t k = edit_budget(L, prm.edit_rate);
     std::vector<CandRec> cand(nhits ? nhits : 1);
-    std::vector<uint64_t> rkeys(nhits ? nhits : 1);
     uint32_t nc = nhits ? coalesce_item(e->bv, keys.data(), nhits, min_seeds_of(nseeds, prm.min_seed), L, k,
-                                        cand.data(), rkeys.data())
+                                        cand.data())
                         : 0;
+    std::vector<uint64_t> rkeys(nc ? nc : 1);
+    for (uint32_t i = 0; i < nc; ++i) rkeys[i] = make_rank_key(cand[i].num_seeds, i);
     std::sort(rkeys.begin(), rkeys.begin() + nc);
     std::vector<CandRec> dense(nc ? nc : 1);
     std::vector<uint32_t> edits(nc ? nc : 1);
