@@ -505,10 +505,16 @@ __device__ uint32_t coalesce_warp(const BinsView& bv, const uint64_t* __restrict
         cur = CandRec{__shfl_sync(0xffffffffu, ws[u], cnt - 1), __shfl_sync(0xffffffffu, we[u], cnt - 1), last_b, 1};
         continue;
       }
-      for (uint32_t i = 0; i < cnt; ++i) {
+      // (fully unrolled so that the shuffles, which do not depend on the automaton's state, are issued
+      //  ahead of the short dependent chain through cur / have)
+      const uint32_t sb = (b[u] << 1) | (some[u] ? 1u : 0u);
+#pragma unroll
+      for (uint32_t i = 0; i < 32; ++i) {
         uint32_t ws_i = __shfl_sync(0xffffffffu, ws[u], i), we_i = __shfl_sync(0xffffffffu, we[u], i);
-        uint32_t b_i = __shfl_sync(0xffffffffu, b[u], i);
-        bool some_i = __shfl_sync(0xffffffffu, (int)some[u], i) != 0;
+        uint32_t sb_i = __shfl_sync(0xffffffffu, sb, i);
+        if (i >= cnt) continue;
+        uint32_t b_i = sb_i >> 1;
+        bool some_i = (sb_i & 1) != 0;
         bool merged = false;
         if (have && some_i && b_i == cur.bin &&
             ((cur.start <= ws_i && ws_i < cur.end) || (cur.start < we_i && we_i <= cur.end))) {
