@@ -236,6 +236,7 @@ __global__ void __launch_bounds__(256) locate_kernel(FmView fm, SaView sv, Param
 // ------------------------------------------------------------------------------------------
 constexpr uint32_t kSortMedium = 4096;
 constexpr uint32_t kLightItems = 16;  // segments this small are ordered by their consumer's own lane
+constexpr uint32_t kMonsterHits = 1024;  // strands with more seed hits than this get a whole CTA in coalesce
 
 __device__ __forceinline__ uint64_t warp_sort_u64(uint64_t v, unsigned lane) {
 #pragma unroll
@@ -553,6 +554,7 @@ __global__ void __launch_bounds__(128) coalesce_kernel(BinsView bv, ReadsView rv
                                                        CandRec* __restrict__ cand_sparse,
                                                        uint32_t* __restrict__ q_ncand,
                                                        uint32_t* __restrict__ heavy_list,
+                                                       uint32_t* __restrict__ monster_list,
                                                        BatchCounters* __restrict__ ctr) {
   // one lane per read: its strands are taken one after the other (usually exactly one of them has
   // hits, so lanes carry similar loads); a strand with many hits is handed to the whole warp
@@ -585,13 +587,14 @@ __global__ void __launch_bounds__(128) coalesce_kernel(BinsView bv, ReadsView rv
     }
     // strands with many hits go to a work list: coalesce_heavy_kernel gives each of them a warp of its
     // own, so one warp never has to work through several heavy strands one after the other
-    unsigned heavy = __ballot_sync(0xffffffffu, nh > kLightItems);
+    unsigned heavy = __ballot_sync(0xffffffffu, nh > kLightItems && nh <= kMonsterHits);
     if (heavy) {
       uint32_t slot = 0;
       if (lane == (unsigned)(__ffs(heavy) - 1)) slot = atomicAdd(&ctr->n_heavy, (unsigned)__popc(heavy));
       slot = __shfl_sync(0xffffffffu, slot, __ffs(heavy) - 1);
-      if (nh > kLightItems) heavy_list[slot + __popc(heavy & ((1u << lane) - 1))] = q;
+      if (nh > kLightItems && nh <= kMonsterHits) heavy_list[slot + __popc(heavy & ((1u << lane) - 1))] = q;
     }
+    if (nh > kMonsterHits) monster_list[atomicAdd(&ctr->n_monster, 1u)] = q;  // a handful per batch
     if (q < nq && nh <= kLightItems) q_ncand[q] = nc;
   }
 }
@@ -621,6 +624,75 @@ __global__ void __launch_bounds__(128) coalesce_heavy_kernel(BinsView bv, ReadsV
     const uint32_t base = hit_off[q];
     uint32_t nc = coalesce_warp(bv, hit_keys + base, q_nhits[q], ms, L, k, cand_sparse + base);
     if (lane == 0) q_ncand[q] = nc;
+  }
+}
+
+// A strand with thousands of hits (several seeds at max-hits) would keep one warp busy long after the
+// rest of the grid has drained.  It gets a CTA of 32 warps instead: the hit list is cut into 32 chunks
+// at positions where a hit provably starts a new candidate (site gap >= 2(L+k), see coalesce_warp), so the
+// chunks are independent sub-problems; every warp runs the ordinary warp automaton on its chunk into a
+// staging buffer, and the chunks' candidates are then packed together in order.
+__global__ void __launch_bounds__(1024) coalesce_monster_kernel(BinsView bv, ReadsView rv, Params p,
+                                                                const uint32_t* __restrict__ hit_off,
+                                                                const uint32_t* __restrict__ q_nhits,
+                                                                const uint32_t* __restrict__ q_nseeds,
+                                                                const uint64_t* __restrict__ hit_keys,
+                                                                CandRec* __restrict__ cand_sparse,
+                                                                CandRec* __restrict__ cand_stage,
+                                                                uint32_t* __restrict__ q_ncand,
+                                                                const uint32_t* __restrict__ monster_list,
+                                                                const BatchCounters* __restrict__ ctr) {
+  __shared__ uint32_t s_start[33], s_cnt[32], s_pre[33];
+  const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const uint32_t n_list = ctr->n_monster;
+  for (uint32_t it = blockIdx.x; it < n_list; it += gridDim.x) {
+    const uint32_t q = monster_list[it];
+    const uint32_t n = q_nhits[q], base = hit_off[q];
+    const uint32_t L = query_len(rv, p.ns, q);
+    const uint32_t k = edit_budget(L, p.edit_rate);
+    const uint32_t ms = min_seeds_of(q_nseeds[q], p.min_seed);
+    const uint64_t* keys = hit_keys + base;
+    // chunk start of warp w: the first guaranteed-break position at or after w * n / 32
+    uint32_t start = (uint32_t)(((uint64_t)n * w) / 32);
+    if (w > 0) {
+      const uint64_t gap = 2ull * ((uint64_t)L + k);
+      for (;;) {
+        uint32_t h = start + lane;
+        bool brk = false;
+        if (h < n && h > 0) brk = (keys[h] >> 16) >= (keys[h - 1] >> 16) + gap;
+        unsigned m = __ballot_sync(0xffffffffu, brk);
+        if (m) {
+          start += __ffs(m) - 1;
+          break;
+        }
+        start += 32;
+        if (start >= n) {
+          start = n;
+          break;
+        }
+      }
+    }
+    if (lane == 0) s_start[w] = start;
+    if (threadIdx.x == 0) s_start[32] = n;
+    __syncthreads();
+    const uint32_t my_start = s_start[w], my_end = s_start[w + 1];
+    uint32_t cnt = 0;
+    if (my_end > my_start)
+      cnt = coalesce_warp(bv, keys + my_start, my_end - my_start, ms, L, k, cand_stage + base + my_start);
+    if (lane == 0) s_cnt[w] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      uint32_t run = 0;
+      for (int i = 0; i < 32; ++i) {
+        s_pre[i] = run;
+        run += s_cnt[i];
+      }
+      s_pre[32] = run;
+      q_ncand[q] = run;
+    }
+    __syncthreads();
+    for (uint32_t i = lane; i < cnt; i += 32) cand_sparse[base + s_pre[w] + i] = cand_stage[base + my_start + i];
+    __syncthreads();
   }
 }
 
@@ -1194,14 +1266,19 @@ static int run_sub_batch(mtsvgpu_index* h, const Params& p, const uint8_t* d_seq
     clk.end();
     // ---- coalesce ----
     clk.begin(ST_COALESCE);
-    MTSV_CUDA_TRY(cudaMemsetAsync(&d_ctr->n_heavy, 0, 2 * sizeof(unsigned int), st));
+    MTSV_TRY(ws.cand_stage.reserve((size_t)n_hits * sizeof(CandRec)));
+    MTSV_CUDA_TRY(cudaMemsetAsync(&d_ctr->n_heavy, 0, 3 * sizeof(unsigned int), st));
     MTSV_LAUNCH(coalesce_kernel, (n_reads + 127) / 128, 128, 0, st, ix.bins_view(), rv, p, nq,
                 ws.hit_off.as<uint32_t>(), ws.q_nhits.as<uint32_t>(), ws.q_nseeds.as<uint32_t>(),
                 ws.hit_keys.as<uint64_t>(), ws.cand_sparse.as<CandRec>(), ws.q_ncand.as<uint32_t>(),
-                ws.worklist.as<uint32_t>(), d_ctr);
+                ws.worklist.as<uint32_t>(), ws.worklist.as<uint32_t>() + nq, d_ctr);
     MTSV_LAUNCH(coalesce_heavy_kernel, 148 * 16, 128, 0, st, ix.bins_view(), rv, p, ws.hit_off.as<uint32_t>(),
                 ws.q_nhits.as<uint32_t>(), ws.q_nseeds.as<uint32_t>(), ws.hit_keys.as<uint64_t>(),
                 ws.cand_sparse.as<CandRec>(), ws.q_ncand.as<uint32_t>(), ws.worklist.as<uint32_t>(), d_ctr);
+    MTSV_LAUNCH(coalesce_monster_kernel, 148, 1024, 0, st, ix.bins_view(), rv, p, ws.hit_off.as<uint32_t>(),
+                ws.q_nhits.as<uint32_t>(), ws.q_nseeds.as<uint32_t>(), ws.hit_keys.as<uint64_t>(),
+                ws.cand_sparse.as<CandRec>(), ws.cand_stage.as<CandRec>(), ws.q_ncand.as<uint32_t>(),
+                ws.worklist.as<uint32_t>() + nq, d_ctr);
     MTSV_TRY(exclusive_scan_u32(ws.q_ncand.as<uint32_t>(), ws.cand_off.as<uint32_t>(), nq, ws.scan_tmp,
                                 (uint64_t*)&d_ctr->total_cands, st));
     clk.end();

@@ -52,7 +52,7 @@ struct DevBuf {
 
 struct BatchCounters {  // device-side scalars of one sub-batch
   unsigned long long total_slots, total_hits, total_cands, total_out;
-  unsigned int max_len, overflow, n_warp, n_medium, n_large, bad_offsets, n_heavy, heavy_cursor;
+  unsigned int max_len, overflow, n_warp, n_medium, n_large, bad_offsets, n_heavy, heavy_cursor, n_monster, reserved2;
   unsigned long long rank_steps[32], window_bytes[32];  // profiling only; spread to avoid one hot address
 };
 
@@ -120,7 +120,7 @@ struct BatchWorkspace {
   // per slot
   DevBuf slot_q, slot_lo, slot_cnt, slot_hoff;
   // per seed hit
-  DevBuf hit_keys, cand_sparse, rank_keys;
+  DevBuf hit_keys, cand_sparse, cand_stage;
   // per candidate (dense)
   DevBuf cand_dense, cand_q, cand_edit, hit_tmp, cand_flag, cand_order;
   // bit-plane encoded reads of the sub-batch
