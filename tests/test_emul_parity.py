@@ -177,3 +177,17 @@ def test_appendix_e_through_emulation(oracle, emul):
         hits, offs = e.bin_reads(cat, off, p)
         assert "".join(results_lines(["r"], hits, offs, False)).strip() == want, name
         assert "".join(results_lines(["r"], hits, offs, True)).strip() == want_long, name
+
+
+def test_randomized_adversarial_cases(oracle, emul):
+    import random
+    from tests.fuzz_cases import rand_case
+    rng = random.Random(20261018)
+    for t in range(120):
+        ix, reads, p = rand_case(rng)
+        h1, o1 = ix.bin_reads(reads, p)
+        cat, off = oracle.pack_seqs(reads)
+        for sa_rate, kk in ((1, rng.randint(0, 6)), (rng.choice([2, 5, 32]), rng.randint(0, 6))):
+            e = emul.EmulIndex(ix, sa_rate=sa_rate, ktab_k=kk)
+            h2, o2 = e.bin_reads(cat, off, p)
+            _same(h1, o1, h2, o2)

@@ -239,6 +239,25 @@ def test_pipeline_reads_longer_than_253(oracle, small_ref, small_index):
             print("read_len %d: reads where the reference's ssw.c changes the outcome: %d of %d" % (read_len, diff, n))
 
 
+def test_randomized_adversarial_cases(oracle):
+    """tests/fuzz_cases.py through the C ABI: 150 random tiny indexes x up to 40 reads with extreme flags."""
+    from tests.fuzz_cases import rand_case
+    rng = random.Random(20261018)
+    for t in range(150):
+        ix, reads, p = rand_case(rng)
+        h1, o1 = ix.bin_reads(reads, p)
+        pg = Params(edit_rate=p.edit_rate, seed_size=p.seed_size, seed_gap=p.seed_gap, min_seed=p.min_seed,
+                    max_hits=p.max_hits, tune_max_hits=p.tune_max_hits,
+                    max_candidates=None if p.max_candidates < 0 else p.max_candidates,
+                    max_assignments=None if p.max_assignments < 0 else p.max_assignments)
+        opts = dict(sa_rate=rng.choice([1, 2, 32]), ktab_k=rng.choice([0, 0xFFFFFFFF, 2, 5]))
+        if opts["sa_rate"] > ix.sa_sample_rate:
+            opts["sa_rate"] = 1
+        with _gpu_index(ix, **opts) as g:
+            h2, o2 = g.bin_reads(reads, pg)
+        _same(h1, o1, h2, o2)
+
+
 def test_appendix_e_vectors_on_gpu(oracle):
     from tests.test_oracle import APPENDIX_E
     for name, refs, read, flags, want, want_long in APPENDIX_E:
