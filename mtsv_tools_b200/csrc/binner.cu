@@ -929,9 +929,11 @@ constexpr uint32_t kMaxReadLen = 4096;
 // The verification loop control of src/index.rs:375-431 with the warp, for queries with many
 // candidates: 32 candidates per step, the (rare) passing ones are taken in rank order; the
 // "TaxID already matched" test scans the accepted list with all lanes.
+constexpr uint32_t kSelectTaxCache = 1024;  // accepted TaxIDs of a heavy strand kept in shared memory
+
 __device__ uint32_t select_warp(const BinsView& bv, const Params& p, const CandRec* __restrict__ cand,
                                 const uint32_t* __restrict__ edits, uint32_t n_cand, uint32_t k,
-                                HitRec* __restrict__ out) {
+                                HitRec* __restrict__ out, uint32_t* __restrict__ s_tax) {
   const unsigned lane = threadIdx.x & 31;
   uint32_t n_out = 0;
   if (p.max_candidates >= 0 && (uint64_t)n_cand > (uint64_t)p.max_candidates) n_cand = (uint32_t)p.max_candidates;
@@ -950,8 +952,12 @@ __device__ uint32_t select_warp(const BinsView& bv, const Params& p, const CandR
       int i = __ffs(m) - 1;
       m &= m - 1;
       uint32_t tax_i = __shfl_sync(0xffffffffu, tax, i);
+      // "TaxID already matched" (src/index.rs:393-396): the first kSelectTaxCache accepted TaxIDs are
+      // scanned in shared memory, any beyond that in the output records
       bool seen = false;
-      for (uint32_t j = lane; j < n_out; j += 32) seen |= out[j].tax_id == tax_i;
+      const uint32_t n_cached = n_out < kSelectTaxCache ? n_out : kSelectTaxCache;
+      for (uint32_t j = lane; j < n_cached; j += 32) seen |= s_tax[j] == tax_i;
+      for (uint32_t j = kSelectTaxCache + lane; j < n_out; j += 32) seen |= out[j].tax_id == tax_i;
       if (__any_sync(0xffffffffu, seen)) continue;
       if ((int)lane == i) {
         HitRec h;
@@ -962,6 +968,7 @@ __device__ uint32_t select_warp(const BinsView& bv, const Params& p, const CandR
         h.edit = e;
         h.reserved = 0;
         out[n_out] = h;
+        if (n_out < kSelectTaxCache) s_tax[n_out] = tax;
       }
       __syncwarp();
       ++n_out;
@@ -977,6 +984,7 @@ __global__ void __launch_bounds__(128) select_kernel(BinsView bv, ReadsView rv, 
                                                      const uint32_t* __restrict__ cand_edit,
                                                      HitRec* __restrict__ hit_tmp,
                                                      uint32_t* __restrict__ q_nout) {
+  __shared__ uint32_t s_tax[4][kSelectTaxCache];
   uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
   const unsigned lane = threadIdx.x & 31;
   uint32_t b = 0, nc = 0, k = 0, n = 0;
@@ -995,7 +1003,8 @@ __global__ void __launch_bounds__(128) select_kernel(BinsView bv, ReadsView rv, 
     heavy &= heavy - 1;
     uint32_t nc_s = __shfl_sync(0xffffffffu, nc, sl), b_s = __shfl_sync(0xffffffffu, b, sl);
     uint32_t k_s = __shfl_sync(0xffffffffu, k, sl);
-    uint32_t r = select_warp(bv, p, cand_dense + b_s, cand_edit + b_s, nc_s, k_s, hit_tmp + b_s);
+    uint32_t r = select_warp(bv, p, cand_dense + b_s, cand_edit + b_s, nc_s, k_s, hit_tmp + b_s,
+                             s_tax[threadIdx.x >> 5]);
     if ((int)lane == sl) n = r;
   }
   if (q < nq) q_nout[q] = n;

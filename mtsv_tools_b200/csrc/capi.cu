@@ -3,6 +3,8 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
+#include <stdio.h>
 
 #include "ctx.h"
 
@@ -131,6 +133,9 @@ static int bin_batch_host(mtsvgpu_index* ix, const uint8_t* seqs, const uint64_t
   *hit_off = nullptr;
   MTSV_CUDA_TRY(cudaSetDevice(ix->ix.device));
   cudaStream_t st = ix->stream, cin = ix->copy_in_stream;
+  static const bool trace = getenv("MTSV_B200_TRACE") != nullptr;  // host-side phase times on stderr
+  auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double t_begin = trace ? now() : 0;
   const uint64_t base = seq_off[0];
   if (seq_off[n_reads] < base) return set_error(MTSVGPU_EINVAL, "seq_off is not monotone");
   const uint64_t bytes = seq_off[n_reads] - base;
@@ -167,6 +172,7 @@ static int bin_batch_host(mtsvgpu_index* ix, const uint8_t* seqs, const uint64_t
     MTSV_CUDA_TRY(cudaEventRecord(ix->in_events[i], cin));
   }
   if (n_sub == 0) MTSV_CUDA_TRY(cudaMemcpyAsync(ws.d_seq_off.p, offs, 8, cudaMemcpyHostToDevice, cin));
+  const double t_enq = trace ? now() : 0;
   // ---- compute (each sub-batch waits for its slice) ----
   const mtsvgpu_hit* d_hits = nullptr;
   const uint64_t* d_hit_off = nullptr;
@@ -188,6 +194,7 @@ static int bin_batch_host(mtsvgpu_index* ix, const uint8_t* seqs, const uint64_t
     cudaStreamSynchronize(ix->copy_out_stream);
     return rc;
   }
+  const double t_comp = trace ? now() : 0;
   MTSV_CUDA_TRY(cudaStreamSynchronize(cin));
   // ---- D2H ----
   mtsvgpu_hit* h_hits = nullptr;
@@ -227,6 +234,10 @@ static int bin_batch_host(mtsvgpu_index* ix, const uint8_t* seqs, const uint64_t
   *hits = h_hits;
   *hit_off = h_off;
   if (n_hits_out) *n_hits_out = n_hits;
+  if (trace)
+    fprintf(stderr, "[mtsv_b200 trace] bin_batch_host: enqueue H2D %.2f ms, compute %.2f ms, tail (D2H rest) %.2f ms, "
+                    "overlapped D2H %s\n", t_enq - t_begin, t_comp - t_enq, now() - t_comp,
+            ix->out_overlap_ok ? "yes" : "no");
   return 0;
 }
 
