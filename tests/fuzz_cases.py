@@ -45,7 +45,7 @@ def rand_case(rng):
             s = bytes(rng.choice(b"ACGTN") for _ in range(L))
         reads.append(s)
     p = po.default_params(edit_rate=rng.choice([0.0, 0.05, 0.13, 0.2, 0.34, 0.5, 0.7, 1.0]),
-                          seed_size=rng.randint(3, 24), seed_gap=rng.randint(1, 20),
+                          seed_size=rng.choice([rng.randint(3, 24)] * 6 + [40, 64, 65, 70, 100]), seed_gap=rng.randint(1, 20),
                           min_seed=rng.choice([0.015, 0.2, 0.5, 1.0]), max_hits=rng.choice([1, 3, 20, 2000]),
                           tune_max_hits=rng.choice([0, 1, 2, 10, 200]),
                           max_candidates=rng.choice([-1, -1, 0, 1, 3]), max_assignments=rng.choice([-1, -1, 0, 1, 2]))
