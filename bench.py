@@ -309,11 +309,20 @@ def run_gpu_arm(args, cfg, rank, world, local_rank):
         t0 = time.time()
         oix = pyoracle.Index.from_parts(parts["text"], parts["bins"], parts["bwt"], parts["sa_sample"], 32)
         sub = (h_reads.numpy()[:ns * L], h_off.numpy()[:ns + 1].astype(np.uint64))
-        want_h, want_o = oix.bin_reads(sub, pyoracle.default_params(**cfg["flags"]), threads=os.cpu_count())
+        octr = pyoracle.Counters()
+        want_h, want_o = oix.bin_reads(sub, pyoracle.default_params(**cfg["flags"]), threads=os.cpu_count(),
+                                       counters=octr)
         got_h, got_o = gix.bin_reads(sub, params)
+        gst = gix.last_batch_stats()
         ok = np.array_equal(want_o, got_o) and all(np.array_equal(want_h[f], got_h[f])
                                                    for f in ("tax_id", "gi", "offset", "edit"))
-        parity = {"reads": ns, "hits": int(len(want_h)), "bit_exact": bool(ok)}
+        oc = octr.as_dict()
+        # work cross-check: the GPU path locates the same rows as the reference algorithm; it builds at least
+        # the reference's candidates (it verifies all of them concurrently, the reference stops early)
+        parity = {"reads": ns, "hits": int(len(want_h)), "bit_exact": bool(ok),
+                  "rows_located": {"oracle": int(oc["rows_located"]), "gpu": gst["n_seed_hits"]},
+                  "candidates": {"oracle_built": int(oc["candidates"]), "oracle_verified": int(oc["sw_calls"]),
+                                 "gpu_verified": gst["n_candidates"]}}
         log("parity gate: %s (%.1fs)" % (parity, time.time() - t0))
         if not ok:
             raise SystemExit("bench.py: GPU results differ from the oracle — refusing to report a number")

@@ -51,13 +51,20 @@ __global__ void count_slots_kernel(ReadsView rv, Params p, uint32_t nq, uint32_t
     q_nslots[q] = L <= kMaxReadLenDev ? seed_slots(L, p.S, p.G) : 0;
   }
   // block max of L -> one atomic per block
-  __shared__ unsigned int smax;
-  if (threadIdx.x == 0) smax = 0;
+  __shared__ unsigned int smax, simin;
+  if (threadIdx.x == 0) smax = simin = 0;
   __syncthreads();
   unsigned int wmax = __reduce_max_sync(0xffffffffu, L);
-  if ((threadIdx.x & 31) == 0) atomicMax(&smax, wmax);
+  unsigned int wimin = __reduce_max_sync(0xffffffffu, q < nq ? ~L : 0u);  // ~(shortest read)
+  if ((threadIdx.x & 31) == 0) {
+    atomicMax(&smax, wmax);
+    atomicMax(&simin, wimin);
+  }
   __syncthreads();
-  if (threadIdx.x == 0) atomicMax(&ctr->max_len, smax);
+  if (threadIdx.x == 0) {
+    atomicMax(&ctr->max_len, smax);
+    atomicMax(&ctr->inv_min_len, simin);
+  }
 }
 
 __global__ void expand_slots_kernel(const uint32_t* __restrict__ slot_off, uint32_t nq,
@@ -171,14 +178,21 @@ __global__ void __launch_bounds__(256) seed_search_kernel(FmView fm, KtabView kt
   if (count_ranks) cta_accumulate(ctr->rank_steps, steps);
 }
 
-__global__ void seed_select_kernel(Params p, const uint32_t* __restrict__ slot_off, uint32_t nq,
-                                   const uint32_t* __restrict__ slot_cnt, uint32_t* __restrict__ slot_hoff,
-                                   uint32_t* __restrict__ q_nseeds, uint32_t* __restrict__ q_nhits,
-                                   BatchCounters* __restrict__ ctr) {
+__global__ void seed_select_kernel(ReadsView rv, EncView ev, Params p, const uint32_t* __restrict__ slot_off,
+                                   uint32_t nq, const uint32_t* __restrict__ slot_cnt,
+                                   uint32_t* __restrict__ slot_hoff, uint32_t* __restrict__ q_nseeds,
+                                   uint32_t* __restrict__ q_nhits, BatchCounters* __restrict__ ctr) {
   uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= nq) return;
   uint32_t b = slot_off[q], e = slot_off[q + 1];
   uint32_t ns = 0, nh = 0, ovf = 0;
+  const uint32_t L = query_len(rv, p.ns, q);
+  if (e > b && query_hopeless(ev.words + query_word_off(rv, ev, p.ns, q), L, edit_budget(L, p.edit_rate))) {
+    for (uint32_t j = b; j < e; ++j) slot_hoff[j] = kUnused;
+    q_nseeds[q] = 0;
+    q_nhits[q] = 0;
+    return;
+  }
   seed_select_item(p, e - b, slot_cnt + b, slot_hoff + b, &ns, &nh, &ovf);
   q_nseeds[q] = ns;
   q_nhits[q] = nh;
@@ -921,6 +935,104 @@ static int launch_verify(const Jobs& jobs, uint32_t max_len, uint32_t* out, Batc
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------
+// The binner's fast path: reads of at most 256 bases (W <= 4 words).  Same jobs, same results as
+// verify_kernel, but the block range of the recurrence is kept per warp (core.cuh::myers_warp), the
+// text comes as 4-bit match classes, 16 columns per load, and with all reads of one length (UNIFORM)
+// block scores follow the carries.  Shared memory: [5 classes][W][thread] masks, class 4 = zero.
+// ------------------------------------------------------------------------------------------
+struct WarpVote {
+  __device__ __forceinline__ bool any(bool x) const { return __any_sync(0xffffffffu, x); }
+  __device__ __forceinline__ bool all(bool x) const { return __all_sync(0xffffffffu, x); }
+  __device__ __forceinline__ uint32_t umax(uint32_t x) const { return __reduce_max_sync(0xffffffffu, x); }
+};
+
+template <int W, bool UNIFORM>
+__global__ void __launch_bounds__(kVerifyThreads) verify_warp_kernel(BinnerJobs jobs, const uint64_t* __restrict__ text4,
+                                                                     uint64_t text4_last_word,
+                                                                     uint32_t* __restrict__ out) {
+  extern __shared__ uint64_t peq[];  // [5][W][kVerifyThreads]
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  VerifyJob job;
+  job.skip = 1;
+  job.L = 0;
+  job.T = 0;
+  job.limit = 0;
+  job.out = 0;
+  job.enc = nullptr;
+  uint32_t start = 0;
+  if (i < jobs.n) {
+    job = jobs.get(i);
+    start = (uint32_t)(job.txt - jobs.text);
+  }
+  bool live = i < jobs.n && !job.skip && job.L != 0;
+  if (i < jobs.n && !live) out[job.out] = job.skip ? kNoEdit : 0u;  // L == 0: src/align.rs test_empty
+  const uint32_t L = job.L;
+  const int nb = live ? (int)((L - 1) >> 6) : -1;
+#pragma unroll
+  for (int w = 0; w < W; ++w) {
+    ReadWord rw{0, 0, ~0ull};
+    if (w <= nb) rw = job.enc[w];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) peq[(c * W + w) * kVerifyThreads + threadIdx.x] = word_peq(rw, c);
+    peq[(4 * W + w) * kVerifyThreads + threadIdx.x] = 0;
+  }
+  // (each thread reads back only what it wrote: no barrier needed)
+  const uint64_t* my_peq = peq + threadIdx.x;
+  auto peq_f = [&](uint32_t c, int w) -> uint64_t { return my_peq[(c * W + w) * kVerifyThreads]; };
+  // 16 columns of text per call, realigned to the window start; one word of look-ahead is carried over
+  struct Text16 {
+    const uint64_t* t4;
+    uint64_t wi, last_word;
+    uint32_t sh;
+    mutable uint64_t cur;
+    __device__ __forceinline__ uint64_t operator()(uint32_t j0) const {
+      uint64_t idx = wi + (j0 >> 4) + 1;
+      uint64_t nxt = __ldg(t4 + (idx < last_word ? idx : last_word));
+      uint64_t v = sh ? (cur >> sh) | (nxt << (64 - sh)) : cur;
+      cur = nxt;
+      return v;
+    }
+  };
+  Text16 text16{text4, start >> 4, text4_last_word, (start & 15u) * 4u, 0};
+  text16.cur = __ldg(text4 + text16.wi);
+  const uint32_t best = myers_warp<W, UNIFORM>(L, job.T, job.limit, live, peq_f, text16, WarpVote());
+  if (live) out[job.out] = best <= job.limit ? best : kNoEdit;
+}
+
+// A/B knob for measurements: MTSV_B200_VERIFIER=legacy routes short reads through verify_kernel as well
+static bool legacy_verifier() {  // read per sub-batch so that a test can flip it in-process
+  const char* e = getenv("MTSV_B200_VERIFIER");
+  return e && strcmp(e, "legacy") == 0;
+}
+
+static int launch_verify_warp(const BinnerJobs& jobs, const DeviceIndex& ix, uint32_t max_len, bool uniform,
+                              uint32_t* out, cudaStream_t st) {
+  if (jobs.n == 0) return 0;
+  const uint32_t words = (max_len + 63) / 64;
+  const unsigned grid = (jobs.n + kVerifyThreads - 1) / kVerifyThreads;
+#define MTSV_VW_CASE(WW, UU)                                                                     \
+  {                                                                                              \
+    size_t smem = (size_t)5 * WW * kVerifyThreads * sizeof(uint64_t);                            \
+    MTSV_LAUNCH((verify_warp_kernel<WW, UU>), grid, kVerifyThreads, smem, st, jobs, ix.text4,    \
+                ix.text4_words - 1, out);                                                        \
+  }
+#define MTSV_VW_CASES(UU)                 \
+  if (words <= 1) MTSV_VW_CASE(1, UU)     \
+  else if (words == 2) MTSV_VW_CASE(2, UU) \
+  else if (words == 3) MTSV_VW_CASE(3, UU) \
+  else MTSV_VW_CASE(4, UU)
+  if (uniform) {
+    MTSV_VW_CASES(true)
+  } else {
+    MTSV_VW_CASES(false)
+  }
+#undef MTSV_VW_CASES
+#undef MTSV_VW_CASE
+  MTSV_CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
 constexpr uint32_t kMaxReadLen = 4096;
 
 // ------------------------------------------------------------------------------------------
@@ -1214,6 +1326,7 @@ static int run_sub_batch(mtsvgpu_index* h, const Params& p, const uint8_t* d_seq
                      hc.total_slots, (unsigned long long)slot_bound, (unsigned long long)read0, n_reads,
                      (unsigned long long)sub_bytes);
   const uint32_t n_slots = (uint32_t)hc.total_slots;
+  const uint32_t min_len = ~hc.inv_min_len;  // == max_len: every read of the sub-batch has the same length
   h->stats.n_seed_slots += n_slots;
   // (only now that the slot count is known to fit the buffers)
   clk.begin(ST_PREP);
@@ -1237,7 +1350,7 @@ static int run_sub_batch(mtsvgpu_index* h, const Params& p, const uint8_t* d_seq
 
   // ---- replay the seed rule, hit offsets ----
   clk.begin(ST_SELECT);
-  MTSV_LAUNCH(seed_select_kernel, qgrid, 256, 0, st, p, slot_off, nq, ws.slot_cnt.as<uint32_t>(),
+  MTSV_LAUNCH(seed_select_kernel, qgrid, 256, 0, st, rv, ev, p, slot_off, nq, ws.slot_cnt.as<uint32_t>(),
               ws.slot_hoff.as<uint32_t>(), ws.q_nseeds.as<uint32_t>(), ws.q_nhits.as<uint32_t>(), d_ctr);
   MTSV_TRY(exclusive_scan_u32(ws.q_nhits.as<uint32_t>(), ws.hit_off.as<uint32_t>(), nq, ws.scan_tmp,
                               (uint64_t*)&d_ctr->total_hits, st));
@@ -1319,8 +1432,12 @@ static int run_sub_batch(mtsvgpu_index* h, const Params& p, const uint8_t* d_seq
                 ws.cand_flag.as<uint32_t>(), n_cand, ws.cand_order.as<uint32_t>());
     BinnerJobs jobs{rv, ev, p, ws.cand_dense.as<CandRec>(), ws.cand_q.as<uint32_t>(),
                     ws.cand_off.as<uint32_t>(), ws.cand_order.as<uint32_t>(), ix.text, n_cand};
-    MTSV_TRY(launch_verify<4>(jobs, hc.max_len, ws.cand_edit.as<uint32_t>(),
-                              h->profiling ? d_ctr : nullptr, st));
+    if (hc.max_len <= 256 && !legacy_verifier())
+      MTSV_TRY(launch_verify_warp(jobs, ix, std::max(hc.max_len, 1u), min_len == hc.max_len,
+                                  ws.cand_edit.as<uint32_t>(), st));
+    else
+      MTSV_TRY(launch_verify<4>(jobs, hc.max_len, ws.cand_edit.as<uint32_t>(),
+                                h->profiling ? d_ctr : nullptr, st));
     clk.end();
     // ---- select ----
     clk.begin(ST_EMIT);

@@ -490,6 +490,25 @@ MTSV_HD void seed_select_item(const Params& p, uint32_t nslots, const uint32_t* 
   *n_hits = (uint32_t)total;
 }
 
+// A read-strand that cannot produce a hit whatever its seeds find (result-preserving shortcut):
+//  * every N of the read is compared as '.' (src/index.rs:272-279), which equals no reference byte, so each
+//    N costs at least one edit in any alignment: more than k of them => min_edit_distance > k (:410);
+//  * 2k > L: the SW threshold L - 2k wraps (:406) and nothing is ever accepted.
+// Such strands skip locate / coalesce / verify altogether.  (Typical source: reads sampled across an
+// N run of the reference, whose N-rich seeds match hundreds of other N runs.)
+MTSV_HD bool query_hopeless(const ReadWord* qw, uint32_t L, uint32_t k) {
+  if (2ull * k > (uint64_t)L) return true;
+  uint32_t n_n = 0;
+  for (uint32_t w = 0; w * 64 < L; ++w) {
+#ifdef __CUDA_ARCH__
+    n_n += (uint32_t)__popcll(qw[w].nn);
+#else
+    n_n += (uint32_t)__builtin_popcountll(qw[w].nn);
+#endif
+  }
+  return n_n > k;
+}
+
 // hit key: (reference_offset << 16) | query_offset — sorts as the derived Ord of SeedHit
 // (src/index.rs:109-113, :443)
 MTSV_HD uint64_t make_hit_key(uint32_t pos, uint32_t q_off) { return ((uint64_t)pos << 16) | q_off; }
@@ -724,6 +743,118 @@ MTSV_HD uint32_t myers_bounded(uint32_t L, uint32_t T, uint32_t k, PeqF peq, Tex
       }
     }
     if (bottom_score < best) best = bottom_score;
+  }
+  return best;
+}
+
+// ---------------------------------------------------------------------------------------------
+// The same bounded recurrence with WARP-UNIFORM control, for reads of at most W <= 4 words (the
+// verifier's fast path).  Lanes of a warp run in lock step anyway, so the set of computed blocks
+// [first, last] is kept per warp instead of per lane: every decision that only prunes work is taken by
+// a vote — a block is activated as soon as ANY lane needs it, dropped / banded out / the loop left only
+// when ALL lanes agree.  For a lane this means blocks are activated earlier and dropped later than it
+// would on its own, both of which are exact (a block activated early holds true values > k or the
+// +1-per-row over-estimate of them; a block kept longer holds exact values).  What this buys: no
+// per-lane activity predicates, no divergent sections, and with all reads of one length (UNIFORM)
+// the score of every block but the last is tracked with the carry bits the recurrence produces anyway.
+//
+// Text arrives 16 columns at a time as 4-bit codes (0..3 = A,C,G,T, 4 = matches nothing): text16(j0)
+// returns the codes of columns j0 .. j0+15, and may be asked for columns beyond the lane's own T (up to the
+// warp's longest window); those columns are computed but never scored.
+// Vote: any(bool), all(bool), umax(u32) over the warp (tests/emul supplies a one-lane version that
+// perturbs the votes to exercise early activation and late drops).
+// ---------------------------------------------------------------------------------------------
+template <int W, bool UNIFORM, typename Vote, typename PeqF, typename Text16F>
+MTSV_HD uint32_t myers_warp(uint32_t L, uint32_t T, uint32_t k, bool live, PeqF peq, Text16F text16,
+                            Vote vote) {
+  if (!live) {
+    L = 0;
+    T = 0;
+    k = 0;
+  }
+  const uint32_t Lw = vote.umax(L);
+  if (Lw == 0) return 0;
+  if (!live) L = Lw;  // idle lanes borrow a length so that their (unused) state stays well defined
+  if (k > L) k = L;
+  const int nb = UNIFORM ? W - 1 : (int)((L - 1) >> 6);
+  const uint32_t sbit = (L - 1) & 63;
+  const uint32_t rows_nb = L - (uint32_t)nb * 64;
+  uint64_t Pv[W], Mv[W];
+  uint32_t bs[W];
+#pragma unroll
+  for (int w = 0; w < W; ++w) {
+    Pv[w] = ~0ull;
+    Mv[w] = 0;
+    uint32_t bottom = (uint32_t)(w + 1) * 64;
+    bs[w] = bottom < L ? bottom : L;
+  }
+  int lane_last = k ? (int)((k - 1) >> 6) : 0;
+  if (lane_last > nb) lane_last = nb;
+  int last = (int)vote.umax((uint32_t)lane_last), first = 0;
+  uint32_t best = L < k + 1 ? L : k + 1;
+  const uint32_t slack = T + k;
+  const uint32_t Tw = vote.umax(T);
+  for (uint32_t j0 = 0; j0 < Tw; j0 += 16) {
+    // ---- pruning votes, once per 16 columns (late pruning is always exact) ----
+    const uint32_t reach = (uint32_t)(last + 1) * 64;
+    const bool done = !live || j0 >= T || (reach < L && (L - reach) > (T - j0) + k);
+    if (vote.all(done)) break;
+    if (first < last) {  // top block entirely above the band: 64(first+1) + slack < L + j0 + 1
+      bool can = done || ((uint32_t)(first + 1) * 64 + slack < L + j0 + 1);
+      if (vote.all(can)) ++first;
+    }
+    if (last > first) {  // bottom block holds only values > k
+      uint32_t rows = last == nb ? rows_nb : 64u;
+      uint32_t bl = bs[0];
+#pragma unroll
+      for (int w = 1; w < W; ++w)
+        if (w == last) bl = bs[w];
+      bool can = done || last > nb || bl >= k + rows;
+      if (vote.all(can)) --last;
+    }
+    const uint64_t tw = text16(j0);
+    const uint32_t ncols = Tw - j0 < 16u ? Tw - j0 : 16u;
+#pragma unroll
+    for (uint32_t jj = 0; jj < 16; ++jj) {
+      if (jj >= ncols) break;
+      const uint32_t c = (uint32_t)(tw >> (4 * jj)) & 7u;
+      uint32_t phin = first > 0 ? 1u : 0u, mhin = 0;
+#pragma unroll
+      for (int w = 0; w < W; ++w) {
+        if (w >= first && w <= last) {  // warp-uniform
+          uint64_t Eq = peq(c, w);
+          const uint32_t prev_old = bs[w];
+          uint64_t Ph, Mh;
+          myers_block(Eq, Pv[w], Mv[w], phin, mhin, Ph, Mh);  // leaves the carries in phin / mhin
+          if (UNIFORM && w < W - 1) {
+            bs[w] += phin;
+            bs[w] -= mhin;
+          } else {
+            const uint32_t bit = (UNIFORM || w == nb) ? sbit : 63u;
+            bs[w] += (uint32_t)(Ph >> bit) & 1u;
+            bs[w] -= (uint32_t)(Mh >> bit) & 1u;
+          }
+          if (w < W - 1 && w == last) {  // the bottom cell of the last block is <= k here or one column ago
+            bool want = live && !done && w < nb && (prev_old <= k || bs[w] <= k);
+            if (vote.any(want)) {
+              Pv[w + 1] = ~0ull;
+              Mv[w + 1] = 0;
+              bs[w + 1] = prev_old + (w + 1 == nb ? rows_nb : 64u);
+              last = w + 1;
+            }
+          }
+        }
+      }
+      if (last >= nb && j0 + jj < T) {
+        uint32_t v = bs[W - 1];
+        if (!UNIFORM) {
+#pragma unroll
+          for (int w = 0; w < W - 1; ++w)
+            if (w == nb) v = bs[w];
+        }
+        if (v < best) best = v;
+      }
+    }
   }
   return best;
 }

@@ -52,7 +52,8 @@ struct DevBuf {
 
 struct BatchCounters {  // device-side scalars of one sub-batch
   unsigned long long total_slots, total_hits, total_cands, total_out;
-  unsigned int max_len, overflow, n_warp, n_medium, n_large, bad_offsets, n_heavy, heavy_cursor, n_monster, reserved2;
+  unsigned int max_len, overflow, n_warp, n_medium, n_large, bad_offsets, n_heavy, heavy_cursor, n_monster;
+  unsigned int inv_min_len;  // ~(shortest read) so that a zeroed struct means "no read seen"
   unsigned long long rank_steps[32], window_bytes[32];  // profiling only; spread to avoid one hot address
 };
 
@@ -79,6 +80,8 @@ struct DeviceIndex {
   uint32_t ktab_k = 0;
   // reference text (bytes, as in the file) and bins (SoA)
   uint8_t* text = nullptr;
+  uint64_t* text4 = nullptr;  // the same text as 4-bit match classes (0..3 = A,C,G,T, 4 = anything else), 16 per word
+  uint64_t text4_words = 0;
   uint32_t *bin_start = nullptr, *bin_end = nullptr, *bin_tax = nullptr, *bin_gi = nullptr;
   uint64_t n_bins = 0;
   uint64_t device_bytes = 0;

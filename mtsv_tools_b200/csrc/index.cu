@@ -226,6 +226,24 @@ static int dev_alloc(T** p, uint64_t count, uint64_t* acc) {
   return 0;
 }
 
+// reference text -> 4-bit match classes, 16 symbols per 64-bit word (symbol i of a word in bits 4i..4i+3)
+__global__ void text_pack4_kernel(const uint8_t* __restrict__ text, uint64_t n, uint64_t* __restrict__ text4,
+                                  uint64_t n_words) {
+  uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= n_words) return;
+  uint64_t v = 0;
+  for (uint32_t i = 0; i < 16; ++i) {
+    uint64_t pos = w * 16 + i;
+    uint32_t c = 4;
+    if (pos < n) {
+      c = upper_acgtn_code(text[pos]);
+      if (c > 3) c = 4;  // N, '$' and any other byte match nothing (src/index.rs:272-279: read N became '.')
+    }
+    v |= (uint64_t)c << (4 * i);
+  }
+  text4[w] = v;
+}
+
 void index_destroy(mtsvgpu_index* h) {
   if (!h) return;
   cudaSetDevice(h->ix.device);
@@ -237,6 +255,7 @@ void index_destroy(mtsvgpu_index* h) {
   cudaFree(d.sa);
   cudaFree(d.ktab);
   cudaFree(d.text);
+  cudaFree(d.text4);
   cudaFree(d.bin_start);
   cudaFree(d.bin_end);
   cudaFree(d.bin_tax);
@@ -337,6 +356,12 @@ int index_from_host_parts(const uint8_t* text, uint64_t n, const mtsvgpu_bin* bi
   // ---- text and bins ----
   MTSV_TRY(dev_alloc(&d.text, n + 16, &d.device_bytes));
   MTSV_CUDA_TRY(cudaMemcpyAsync(d.text, text, n, cudaMemcpyHostToDevice, st));
+  MTSV_CUDA_TRY(cudaMemsetAsync(d.text + n, 0, 16, st));
+  // 4-bit match classes for the verifier's fast path (+ 2 words of slack: it reads one word ahead)
+  d.text4_words = (n + 15) / 16 + 2;
+  MTSV_TRY(dev_alloc(&d.text4, d.text4_words, &d.device_bytes));
+  MTSV_LAUNCH(text_pack4_kernel, (unsigned)((d.text4_words + 255) / 256), 256, 0, st, d.text, n, d.text4,
+              d.text4_words);
   {
     std::vector<uint32_t> bs(n_bins), be(n_bins), bt(n_bins), bg(n_bins);
     for (uint64_t i = 0; i < n_bins; ++i) {

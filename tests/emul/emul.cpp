@@ -195,6 +195,98 @@ uint32_t emul_edit_distance_k(const uint8_t* pat, uint32_t L, uint32_t rc, const
   return L <= 1024 ? myers_bounded<16>(L, T, k, pf, tf) : myers_bounded<64>(L, T, k, pf, tf);
 }
 
+// The warp-uniform fast path (core.cuh::myers_warp) as one lane.  The votes of the other 31 lanes are
+// played by a PRNG: with probability `noise`/256 an `any` vote succeeds although this lane did not ask
+// (early activation) and an `all` vote fails although this lane agreed (late drop / late exit).
+struct NoisyVote {
+  mutable uint64_t s;
+  uint32_t noise;
+  uint32_t other_T;  // a longer window of "another lane": this lane computes columns beyond its own T
+  bool flip() const {
+    s = s * 6364136223846793005ull + 1442695040888963407ull;
+    return ((s >> 33) & 255) < noise;
+  }
+  bool any(bool x) const { return x || flip(); }
+  bool all(bool x) const { return x && !flip(); }
+  uint32_t umax(uint32_t x) const { return x; }
+};
+struct NoisyVoteT : NoisyVote {  // myers_warp takes three maxima: L, the initial last block, T
+  mutable int calls = 0;
+  uint32_t max_last = 0;
+  uint32_t umax(uint32_t x) const {
+    ++calls;
+    if (calls == 2 && x < max_last && flip()) return x + 1;  // another lane starts with one more block
+    if (calls == 3 && other_T > x) return other_T;           // another lane has a longer window
+    return x;
+  }
+};
+
+uint32_t emul_edit_distance_warp(const uint8_t* pat, uint32_t L, uint32_t rc, const uint8_t* txt, uint32_t T,
+                                 uint32_t k, int uniform, uint32_t noise, uint64_t seed, uint32_t other_T) {
+  if (L == 0) return 0;
+  if (L > 256) return 0xffffffffu;
+  std::vector<ReadWord> q = encode_query(pat, L, rc != 0, false);
+  uint64_t peq[5][4];
+  memset(peq, 0, sizeof peq);
+  const uint32_t words = (L + 63) / 64;
+  for (uint32_t w = 0; w < words; ++w)
+    for (int c = 0; c < 4; ++c) peq[c][w] = word_peq(q[w], c);
+  auto pf = [&](uint32_t c, int w) { return peq[c][w]; };
+  // 4-bit codes of the window, followed by arbitrary codes (what another lane's longer window would make
+  // this lane read)
+  auto t16 = [&](uint32_t j0) {
+    uint64_t v = 0;
+    for (uint32_t i = 0; i < 16; ++i) {
+      uint32_t j = j0 + i;
+      uint32_t c = j < T ? upper_acgtn_code(txt[j]) : (j * 2654435761u >> 7) % 5;
+      if (c > 4) c = 4;
+      v |= (uint64_t)c << (4 * i);
+    }
+    return v;
+  };
+  NoisyVoteT vote;
+  vote.s = seed;
+  vote.noise = noise;
+  vote.other_T = other_T;
+  vote.max_last = words - 1;
+#define CASE(WW)                                                                                     \
+  if (words == WW)                                                                                   \
+    return uniform ? myers_warp<WW, true>(L, T, k, true, pf, t16, vote)                              \
+                   : myers_warp<WW, false>(L, T, k, true, pf, t16, vote);
+  CASE(1) CASE(2) CASE(3) CASE(4)
+#undef CASE
+  // non-uniform lanes may sit in a wider kernel than they need
+  return 0xffffffffu;
+}
+
+// a short read in a kernel instantiated for longer ones (ragged batch): words < W
+uint32_t emul_edit_distance_warp_wide(const uint8_t* pat, uint32_t L, const uint8_t* txt, uint32_t T, uint32_t k,
+                                      uint32_t noise, uint64_t seed, uint32_t other_T) {
+  if (L == 0 || L > 256) return 0xffffffffu;
+  std::vector<ReadWord> q = encode_query(pat, L, false, false);
+  uint64_t peq[5][4];
+  memset(peq, 0, sizeof peq);
+  for (uint32_t w = 0; w < (L + 63) / 64; ++w)
+    for (int c = 0; c < 4; ++c) peq[c][w] = word_peq(q[w], c);
+  auto pf = [&](uint32_t c, int w) { return peq[c][w]; };
+  auto t16 = [&](uint32_t j0) {
+    uint64_t v = 0;
+    for (uint32_t i = 0; i < 16; ++i) {
+      uint32_t j = j0 + i;
+      uint32_t c = j < T ? upper_acgtn_code(txt[j]) : (j * 2654435761u >> 7) % 5;
+      if (c > 4) c = 4;
+      v |= (uint64_t)c << (4 * i);
+    }
+    return v;
+  };
+  NoisyVoteT vote;
+  vote.s = seed;
+  vote.noise = noise;
+  vote.other_T = other_T;
+  vote.max_last = 3;
+  return myers_warp<4, false>(L, T, k, true, pf, t16, vote);
+}
+
 uint32_t emul_edit_distance(const uint8_t* pat, uint32_t L, uint32_t rc, const uint8_t* txt, uint32_t T,
                             int ncls) {
   return emul_edit_distance_k(pat, L, rc, txt, T, ncls, 0xfffffffeu);
@@ -229,7 +321,11 @@ int emul_bin_reads(void* p, const uint8_t* seqs, const uint64_t* seq_off, uint64
     for (uint32_t j = 0; j < nslots; ++j)
       seed_search_item(e->fm, e->kt, qwords.data(), L, prm.S, j * prm.G, &lo[j], &cnt[j], nullptr);
     uint32_t nseeds = 0, nhits = 0, ovf = 0;
-    seed_select_item(prm, nslots, cnt.data(), hoff.data(), &nseeds, &nhits, &ovf);
+    if (nslots && query_hopeless(qwords.data(), L, edit_budget(L, prm.edit_rate))) {
+      for (uint32_t j = 0; j < nslots; ++j) hoff[j] = kUnused;
+    } else {
+      seed_select_item(prm, nslots, cnt.data(), hoff.data(), &nseeds, &nhits, &ovf);
+    }
     if (ovf) return -7;
     std::vector<uint64_t> keys(nhits);
     for (uint32_t j = 0; j < nslots; ++j)

@@ -54,6 +54,12 @@ def lib():
     L.emul_edit_distance_k.restype = C.c_uint32
     L.emul_edit_distance_k.argtypes = [C.c_char_p, C.c_uint32, C.c_uint32, C.c_char_p, C.c_uint32, C.c_int,
                                        C.c_uint32]
+    L.emul_edit_distance_warp.restype = C.c_uint32
+    L.emul_edit_distance_warp.argtypes = [C.c_char_p, C.c_uint32, C.c_uint32, C.c_char_p, C.c_uint32, C.c_uint32,
+                                          C.c_int, C.c_uint32, C.c_uint64, C.c_uint32]
+    L.emul_edit_distance_warp_wide.restype = C.c_uint32
+    L.emul_edit_distance_warp_wide.argtypes = [C.c_char_p, C.c_uint32, C.c_char_p, C.c_uint32, C.c_uint32,
+                                               C.c_uint32, C.c_uint64, C.c_uint32]
     L.emul_bin_reads.argtypes = [vp, vp, vp, C.c_uint64, C.POINTER(Params), C.POINTER(vp), C.POINTER(vp)]
     L.emul_free.argtypes = [vp]
     _LIB = L
@@ -118,3 +124,13 @@ def edit_distance(pat, txt, rc=0, ncls=5, k=None):
     if k is None:
         return int(lib().emul_edit_distance(bytes(pat), len(pat), rc, bytes(txt), len(txt), ncls))
     return int(lib().emul_edit_distance_k(bytes(pat), len(pat), rc, bytes(txt), len(txt), ncls, k))
+
+
+def edit_distance_warp(pat, txt, k, rc=0, uniform=True, noise=0, seed=1, other_T=0, wide=False):
+    """core.cuh::myers_warp (the verifier's fast path, reads <= 256 bases, binner match rule) as one lane
+    whose warp votes are perturbed with probability noise/256; exact when the result is <= k."""
+    if wide:
+        return int(lib().emul_edit_distance_warp_wide(bytes(pat), len(pat), bytes(txt), len(txt), k, noise, seed,
+                                                      other_T))
+    return int(lib().emul_edit_distance_warp(bytes(pat), len(pat), rc, bytes(txt), len(txt), k, int(uniform),
+                                             noise, seed, other_T))

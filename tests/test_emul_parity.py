@@ -93,6 +93,46 @@ def test_edit_distance_fuzz(oracle, emul):
         assert oracle.min_edit_distance(p.replace(b"N", b"."), tx) == emul.edit_distance(p, tx, 0, 4)
 
 
+def test_edit_distance_warp_fuzz(oracle, emul):
+    """The warp-uniform verifier recurrence (core.cuh::myers_warp) against the full DP: exact whenever the
+    distance is within the budget, above the budget otherwise — with the votes of the other lanes perturbed
+    (early activation, late drops, a longer window elsewhere in the warp) and for ragged lengths."""
+    rng = random.Random(11)
+    n_within = 0
+    for it in range(4000):
+        L = rng.randint(1, 256)
+        alpha = b"ACGTN" if rng.random() < 0.3 else b"ACGT"
+        p = bytes(rng.choice(alpha) for _ in range(L))
+        mode = rng.random()
+        if mode < 0.7:
+            s = list(p)
+            for _ in range(rng.randint(0, 30)):
+                i = rng.randrange(len(s))
+                r = rng.random()
+                if r < 0.4:
+                    s[i] = rng.choice(b"ACGTN")
+                elif r < 0.7:
+                    s.insert(i, rng.choice(b"ACGT"))
+                elif len(s) > 1:
+                    del s[i]
+            tx = bytes(rng.choice(b"ACGT") for _ in range(rng.randint(0, 60))) + bytes(s) + \
+                bytes(rng.choice(b"ACGT") for _ in range(rng.randint(0, 60)))
+        else:
+            tx = bytes(rng.choice(alpha) for _ in range(rng.randint(0, 500)))
+        k = rng.choice([0, 1, 3, 10, 20, 33, 50, 64, 65, 100, 128, 129, 255, 400])
+        want = oracle.min_edit_distance(p.replace(b"N", b"."), tx) if tx else L
+        n_within += want <= k
+        for uniform in (True, False):
+            noise = rng.choice([0, 0, 8, 64, 200])
+            other_T = rng.choice([0, 0, len(tx) + rng.randint(1, 100)])
+            got = emul.edit_distance_warp(p, tx, k, 0, uniform, noise, rng.getrandbits(60), other_T)
+            assert (got == want) if want <= k else (got > k), (it, L, len(tx), k, uniform, noise, other_T, got, want)
+        got = emul.edit_distance_warp(p, tx, k, wide=True, noise=rng.choice([0, 16, 128]), seed=rng.getrandbits(60),
+                                      other_T=rng.choice([0, len(tx) + 37]))
+        assert (got == want) if want <= k else (got > k), (it, "wide", L, len(tx), k, got, want)
+    assert n_within > 1000
+
+
 CASES = [
     ("defaults dense+ktab", {}, 1, 8),
     ("sa_rate 4, no table", {}, 4, 0),
@@ -132,6 +172,30 @@ def test_pipeline_redundant_reference(oracle, emul):
         h2, o2 = e.bin_reads(reads[0], reads[1], p)
         _same(h1, o1, h2, o2)
         assert len(h1) > 3000
+
+
+def _n_rich_case(seed=41):
+    """Reference with 3 % of its bases in N runs of 10-50 and reads sampled across them: N-rich seeds match
+    other N runs (many spurious candidates), reads with more N than the edit budget can never be accepted
+    (core.cuh::query_hopeless), reads with fewer still can."""
+    ref = synth.make_reference(6, 30000, seed=seed, n_frac=0.03, shared_frac=0.1)
+    reads = synth.make_reads(ref[0], ref[1], 1500, 150, seed=seed + 1, frac_n_reads=0.2)
+    return ref, reads
+
+
+def test_pipeline_n_rich_reference(oracle, emul):
+    ref, reads = _n_rich_case()
+    ix = oracle.Index.build((ref[0], ref[1]), ref[2], ref[3], 64, 32)
+    cat = reads[0].reshape(-1, 150)
+    n_per_read = (cat == ord("N")).sum(axis=1)
+    assert (n_per_read > 20).sum() > 50 and ((n_per_read > 0) & (n_per_read <= 20)).sum() > 100
+    for flags in ({}, dict(edit_rate=0.05), dict(edit_rate=0.3, max_hits=100000, tune_max_hits=100000)):
+        p = oracle.default_params(**flags)
+        h1, o1 = ix.bin_reads(reads, p, threads=4)
+        e = emul.EmulIndex(ix, sa_rate=1, ktab_k=6)
+        h2, o2 = e.bin_reads(reads[0], reads[1], p)
+        _same(h1, o1, h2, o2)
+        assert len(h1) > 500
 
 
 def test_pipeline_long_reads_high_edit(oracle, emul, small_ref, small_index):

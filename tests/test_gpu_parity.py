@@ -215,6 +215,57 @@ def test_pipeline_ragged_and_garbage(oracle, small_ref, small_index):
             assert [tuple(h) for h in got] == want
 
 
+def test_pipeline_n_rich_reference(oracle):
+    """N runs in the reference and reads sampled across them (see tests/test_emul_parity.py::_n_rich_case)."""
+    from tests.test_emul_parity import _n_rich_case
+    ref, reads = _n_rich_case()
+    ix = oracle.Index.build((ref[0], ref[1]), ref[2], ref[3], 64, 32)
+    with _gpu_index(ix) as g:
+        for flags in ({}, dict(edit_rate=0.05), dict(edit_rate=0.3, max_hits=100000, tune_max_hits=100000)):
+            po, pg = _params(oracle, **flags)
+            h1, o1 = ix.bin_reads(reads, po, threads=8)
+            h2, o2 = g.bin_reads(reads, pg)
+            _same(h1, o1, h2, o2)
+            assert len(h1) > 500
+
+
+def test_verifier_fast_and_legacy_paths_agree(oracle, small_ref, small_index):
+    """Reads <= 256 bases go through verify_warp_kernel (warp-uniform block range, 4-bit text); the
+    per-lane verify_kernel stays for longer reads.  Both must give the oracle's hits on uniform and on
+    ragged batches (mutated reads of 1..256 bases so that the edit budget is actually used)."""
+    rng = np.random.default_rng(21)
+    ref = small_ref[0]
+    batches = {"uniform_150": synth.make_reads(small_ref[0], small_ref[1], 4000, 150, seed=31, sub=0.05),
+               "uniform_64": synth.make_reads(small_ref[0], small_ref[1], 3000, 64, seed=32, sub=0.04),
+               "uniform_256": synth.make_reads(small_ref[0], small_ref[1], 2000, 256, seed=33, sub=0.06)}
+    rl = []
+    for _ in range(4000):
+        L = int(rng.integers(1, 257))
+        st = int(rng.integers(0, len(ref) - 300))
+        s = bytearray(ref[st:st + L])
+        for _ in range(int(rng.integers(0, max(1, L // 12)))):
+            s[int(rng.integers(0, L))] = b"ACGTN"[int(rng.integers(0, 5))]
+        rl.append(bytes(s))
+    batches["ragged"] = oracle.pack_seqs(rl)
+    old = os.environ.get("MTSV_B200_VERIFIER")
+    try:
+        with _gpu_index(small_index) as g:
+            for name, reads in batches.items():
+                for flags in ({}, dict(edit_rate=0.2, seed_gap=5), dict(edit_rate=0.05)):
+                    po, pg = _params(oracle, **flags)
+                    h1, o1 = small_index.bin_reads(reads, po, threads=8)
+                    assert len(h1) > 100, name
+                    for mode in ("warp", "legacy"):
+                        os.environ["MTSV_B200_VERIFIER"] = mode
+                        h2, o2 = g.bin_reads(reads, pg)
+                        _same(h1, o1, h2, o2)
+    finally:
+        if old is None:
+            os.environ.pop("MTSV_B200_VERIFIER", None)
+        else:
+            os.environ["MTSV_B200_VERIFIER"] = old
+
+
 def test_pipeline_reads_longer_than_253(oracle, small_ref, small_index):
     """Reads of 300-3000 bp (verifier with 8-64 words).  For reads >= 254 bp the reference's SSW pre-filter
     may fall to its 16-bit kernel, which is not exactly textbook SW; the comparison here is
