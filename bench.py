@@ -317,8 +317,9 @@ def run_gpu_arm(args, cfg, rank, world, local_rank):
         ok = np.array_equal(want_o, got_o) and all(np.array_equal(want_h[f], got_h[f])
                                                    for f in ("tax_id", "gi", "offset", "edit"))
         oc = octr.as_dict()
-        # work cross-check: the GPU path locates the same rows as the reference algorithm; it builds at least
-        # the reference's candidates (it verifies all of them concurrently, the reference stops early)
+        # work cross-check against the reference algorithm's own counters: rows located and candidates verified
+        # (the GPU path verifies all candidates of a strand concurrently where the reference stops early, and
+        # skips strands that cannot be accepted: more N than the edit budget, core.cuh::query_hopeless)
         parity = {"reads": ns, "hits": int(len(want_h)), "bit_exact": bool(ok),
                   "rows_located": {"oracle": int(oc["rows_located"]), "gpu": gst["n_seed_hits"]},
                   "candidates": {"oracle_built": int(oc["candidates"]), "oracle_verified": int(oc["sw_calls"]),
@@ -417,11 +418,16 @@ def run_gpu_arm(args, cfg, rank, world, local_rank):
         except Exception:
             traffic = {}
 
+    # the verifier has two kernels: verify_warp_kernel for reads <= 256 bases, verify_kernel beyond
+    kernel_of = {"verify": "verify_warp_kernel" if L <= 256 and os.environ.get("MTSV_B200_VERIFIER") != "legacy"
+                 else "verify_kernel"}
+
     def roof(stage, extra):
         ms_k = per_step.get(stage, 0.0)
         ach = alg_bytes[stage] / (ms_k * 1e-3) / 1e9 if ms_k > 0 else 0.0
-        t = traffic.get(stage + "_kernel", {})
-        r = {"bound": "hbm", "kernel": stage + "_kernel", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+        kname = kernel_of.get(stage, stage + "_kernel")
+        t = traffic.get(kname, {})
+        r = {"bound": "hbm", "kernel": kname, "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
              "frac": ach / peaks["hbm_gbs"], "traffic": t.get("dram_bytes_per_launch"),
              "peak_source": "%s MEASURED_PEAKS.json hbm_gbs (streaming copy)" % peak_kind,
              "algorithmic_bytes_per_launch": alg_bytes[stage] / n_sub, "launches_per_step": n_sub,
@@ -429,7 +435,8 @@ def run_gpu_arm(args, cfg, rank, world, local_rank):
         if t:
             r["ncu"] = {"dram_throughput_pct_of_peak": t.get("dram_throughput_pct_of_peak"),
                         "alu_pipe_pct_of_peak": t.get("alu_pipe_pct_of_peak"),
-                        "issue_active_pct": t.get("issue_active_pct"), "source": "profiles/r01_%s_kernel.txt" % stage}
+                        "fma_pipe_pct_of_peak": t.get("fma_pipe_pct_of_peak"),
+                        "issue_active_pct": t.get("issue_active_pct"), "source": "profiles/r01_%s.txt" % kname}
         r.update(extra)
         return r
 

@@ -764,9 +764,57 @@ MTSV_HD uint32_t myers_bounded(uint32_t L, uint32_t T, uint32_t k, PeqF peq, Tex
 // Vote: any(bool), all(bool), umax(u32) over the warp (tests/emul supplies a one-lane version that
 // perturbs the votes to exercise early activation and late drops).
 // ---------------------------------------------------------------------------------------------
+// four columns of the recurrence over the blocks F..Z (compile time), straight-line
+template <int W, bool UNIFORM, int F, int Z, typename PeqF>
+MTSV_HD void myers_cols4(uint32_t codes, uint32_t ncols, uint64_t (&Pv)[W], uint64_t (&Mv)[W], uint32_t (&bs)[W],
+                         uint32_t& best, PeqF peq, int nb, uint32_t sbit, uint32_t j, uint32_t T) {
+#pragma unroll
+  for (uint32_t jj = 0; jj < 4; ++jj) {
+    if (jj >= ncols) break;  // warp-uniform
+    const uint32_t c = (codes >> (4 * jj)) & 7u;
+    uint32_t phin = F > 0 ? 1u : 0u, mhin = 0;
+#pragma unroll
+    for (int w = F; w <= Z; ++w) {
+      uint64_t Ph, Mh;
+      myers_block(peq(c, w), Pv[w], Mv[w], phin, mhin, Ph, Mh);  // leaves the carries in phin / mhin
+      if (UNIFORM && w < W - 1) {
+        bs[w] += phin;
+        bs[w] -= mhin;
+      } else {
+        const uint32_t bit = (UNIFORM || w == nb) ? sbit : 63u;
+        bs[w] += (uint32_t)(Ph >> bit) & 1u;
+        bs[w] -= (uint32_t)(Mh >> bit) & 1u;
+      }
+    }
+    if (UNIFORM) {
+      if (Z == W - 1 && j + jj < T && bs[W - 1] < best) best = bs[W - 1];
+    } else if (Z >= nb && F <= nb && j + jj < T) {
+      uint32_t v = bs[W - 1];
+#pragma unroll
+      for (int w = 0; w < W - 1; ++w)
+        if (w == nb) v = bs[w];
+      if (v < best) best = v;
+    }
+  }
+}
+
+template <int W, bool UNIFORM, int F, typename PeqF>
+MTSV_HD void myers_cols4_z(int last, uint32_t codes, uint32_t ncols, uint64_t (&Pv)[W], uint64_t (&Mv)[W],
+                           uint32_t (&bs)[W], uint32_t& best, PeqF peq, int nb, uint32_t sbit, uint32_t j,
+                           uint32_t T) {
+  if (last == F) myers_cols4<W, UNIFORM, F, F>(codes, ncols, Pv, Mv, bs, best, peq, nb, sbit, j, T);
+  if (W > F + 1 && last == F + 1)
+    myers_cols4<W, UNIFORM, F, (F + 1 < W ? F + 1 : F)>(codes, ncols, Pv, Mv, bs, best, peq, nb, sbit, j, T);
+  if (W > F + 2 && last == F + 2)
+    myers_cols4<W, UNIFORM, F, (F + 2 < W ? F + 2 : F)>(codes, ncols, Pv, Mv, bs, best, peq, nb, sbit, j, T);
+  if (W > F + 3 && last == F + 3)
+    myers_cols4<W, UNIFORM, F, (F + 3 < W ? F + 3 : F)>(codes, ncols, Pv, Mv, bs, best, peq, nb, sbit, j, T);
+}
+
 template <int W, bool UNIFORM, typename Vote, typename PeqF, typename Text16F>
 MTSV_HD uint32_t myers_warp(uint32_t L, uint32_t T, uint32_t k, bool live, PeqF peq, Text16F text16,
                             Vote vote) {
+  static_assert(W >= 1 && W <= 4, "fast path: at most 4 words");
   if (!live) {
     L = 0;
     T = 0;
@@ -788,6 +836,7 @@ MTSV_HD uint32_t myers_warp(uint32_t L, uint32_t T, uint32_t k, bool live, PeqF 
     uint32_t bottom = (uint32_t)(w + 1) * 64;
     bs[w] = bottom < L ? bottom : L;
   }
+  // column 0: D[i][0] = i, so the blocks holding rows <= k start active
   int lane_last = k ? (int)((k - 1) >> 6) : 0;
   if (lane_last > nb) lane_last = nb;
   int last = (int)vote.umax((uint32_t)lane_last), first = 0;
@@ -803,57 +852,51 @@ MTSV_HD uint32_t myers_warp(uint32_t L, uint32_t T, uint32_t k, bool live, PeqF 
       bool can = done || ((uint32_t)(first + 1) * 64 + slack < L + j0 + 1);
       if (vote.all(can)) ++first;
     }
-    if (last > first) {  // bottom block holds only values > k
+    if (last > first) {  // bottom block holds only values > k (with the margin of the activation rule below)
       uint32_t rows = last == nb ? rows_nb : 64u;
-      uint32_t bl = bs[0];
+      uint32_t bl = bs[0], bp = bs[0];
 #pragma unroll
-      for (int w = 1; w < W; ++w)
+      for (int w = 1; w < W; ++w) {
         if (w == last) bl = bs[w];
-      bool can = done || last > nb || bl >= k + rows;
+        if (w == last - 1) bp = bs[w];
+      }
+      bool can = done || last > nb || (bl >= k + rows && bp > k + 4 + 16);
       if (vote.all(can)) --last;
     }
     const uint64_t tw = text16(j0);
-    const uint32_t ncols = Tw - j0 < 16u ? Tw - j0 : 16u;
+    const uint32_t ncols16 = Tw - j0 < 16u ? Tw - j0 : 16u;
+    for (uint32_t j4 = 0; j4 < ncols16; j4 += 4) {
+      // ---- activation, every 4 columns: the bottom cell of block `last` moves by at most 1 per column, so
+      //      block last+1 cannot hold a value <= k within the next 4 columns unless that cell is <= k + 4 now.
+      //      The new block starts from the +1-per-row over-estimate below that cell (state of column j-1). ----
+      if (last < W - 1) {
+        uint32_t bl = bs[0];
 #pragma unroll
-    for (uint32_t jj = 0; jj < 16; ++jj) {
-      if (jj >= ncols) break;
-      const uint32_t c = (uint32_t)(tw >> (4 * jj)) & 7u;
-      uint32_t phin = first > 0 ? 1u : 0u, mhin = 0;
+        for (int w = 1; w < W - 1; ++w)
+          if (w == last) bl = bs[w];
+        bool want = live && !done && last < nb && bl <= k + 4;
+        if (vote.any(want)) {
+          ++last;
+          const uint32_t init = bl + (last == nb ? rows_nb : 64u);
 #pragma unroll
-      for (int w = 0; w < W; ++w) {
-        if (w >= first && w <= last) {  // warp-uniform
-          uint64_t Eq = peq(c, w);
-          const uint32_t prev_old = bs[w];
-          uint64_t Ph, Mh;
-          myers_block(Eq, Pv[w], Mv[w], phin, mhin, Ph, Mh);  // leaves the carries in phin / mhin
-          if (UNIFORM && w < W - 1) {
-            bs[w] += phin;
-            bs[w] -= mhin;
-          } else {
-            const uint32_t bit = (UNIFORM || w == nb) ? sbit : 63u;
-            bs[w] += (uint32_t)(Ph >> bit) & 1u;
-            bs[w] -= (uint32_t)(Mh >> bit) & 1u;
-          }
-          if (w < W - 1 && w == last) {  // the bottom cell of the last block is <= k here or one column ago
-            bool want = live && !done && w < nb && (prev_old <= k || bs[w] <= k);
-            if (vote.any(want)) {
-              Pv[w + 1] = ~0ull;
-              Mv[w + 1] = 0;
-              bs[w + 1] = prev_old + (w + 1 == nb ? rows_nb : 64u);
-              last = w + 1;
+          for (int w = 1; w < W; ++w)
+            if (w == last) {
+              Pv[w] = ~0ull;
+              Mv[w] = 0;
+              bs[w] = init;
             }
-          }
         }
       }
-      if (last >= nb && j0 + jj < T) {
-        uint32_t v = bs[W - 1];
-        if (!UNIFORM) {
-#pragma unroll
-          for (int w = 0; w < W - 1; ++w)
-            if (w == nb) v = bs[w];
-        }
-        if (v < best) best = v;
-      }
+      const uint32_t codes = (uint32_t)(tw >> (4 * j4)) & 0xffffu;
+      const uint32_t ncols = ncols16 - j4 < 4u ? ncols16 - j4 : 4u;
+      const uint32_t j = j0 + j4;
+      if (first == 0) myers_cols4_z<W, UNIFORM, 0>(last, codes, ncols, Pv, Mv, bs, best, peq, nb, sbit, j, T);
+      if (W > 1 && first == 1)
+        myers_cols4_z<W, UNIFORM, (W > 1 ? 1 : 0)>(last, codes, ncols, Pv, Mv, bs, best, peq, nb, sbit, j, T);
+      if (W > 2 && first == 2)
+        myers_cols4_z<W, UNIFORM, (W > 2 ? 2 : 0)>(last, codes, ncols, Pv, Mv, bs, best, peq, nb, sbit, j, T);
+      if (W > 3 && first == 3)
+        myers_cols4_z<W, UNIFORM, (W > 3 ? 3 : 0)>(last, codes, ncols, Pv, Mv, bs, best, peq, nb, sbit, j, T);
     }
   }
   return best;
