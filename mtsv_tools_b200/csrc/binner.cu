@@ -1268,6 +1268,27 @@ static int grow_preserve(DevBuf& buf, size_t used_bytes, size_t need_bytes, cuda
   return 0;
 }
 
+// The host reads the sub-batch scalars between stages.  They are pushed into page-locked mapped host memory
+// by a tiny kernel instead of a cudaMemcpy: a D2H copy would queue on the copy engine behind the result
+// slices of the previous sub-batch that the host API streams out concurrently.
+__global__ void publish_counters_kernel(const BatchCounters* __restrict__ d, BatchCounters* __restrict__ h) {
+  const uint32_t* src = reinterpret_cast<const uint32_t*>(d);
+  volatile uint32_t* dst = reinterpret_cast<volatile uint32_t*>(h);
+  for (uint32_t i = threadIdx.x; i < sizeof(BatchCounters) / 4; i += blockDim.x) dst[i] = src[i];
+  __threadfence_system();
+}
+
+static int fetch_counters(mtsvgpu_index* h, const BatchCounters* d_ctr, BatchCounters* out, cudaStream_t st) {
+  if (!h->h_ctr) {
+    MTSV_CUDA_TRY(cudaHostAlloc((void**)&h->h_ctr, sizeof(BatchCounters), cudaHostAllocMapped));
+    MTSV_CUDA_TRY(cudaHostGetDevicePointer((void**)&h->h_ctr_dev, h->h_ctr, 0));
+  }
+  MTSV_LAUNCH(publish_counters_kernel, 1, 160, 0, st, d_ctr, h->h_ctr_dev);
+  MTSV_CUDA_TRY(cudaStreamSynchronize(st));
+  memcpy(out, h->h_ctr, sizeof(BatchCounters));
+  return 0;
+}
+
 // One device sub-batch: reads [read0, read0 + n_reads).  Returns 1 when the seed hits exceed the
 // in-flight cap and the caller must split the range (nothing was emitted in that case).
 static int run_sub_batch(mtsvgpu_index* h, const Params& p, const uint8_t* d_seqs,
@@ -1315,8 +1336,7 @@ static int run_sub_batch(mtsvgpu_index* h, const Params& p, const uint8_t* d_seq
   MTSV_LAUNCH(count_slots_kernel, qgrid, 256, 0, st, rv, p, nq, slot_off, d_ctr);
   MTSV_TRY(exclusive_scan_u32(slot_off, slot_off, nq, ws.scan_tmp, (uint64_t*)&d_ctr->total_slots, st));
   clk.end();
-  MTSV_CUDA_TRY(cudaMemcpyAsync(&hc, d_ctr, sizeof hc, cudaMemcpyDeviceToHost, st));
-  MTSV_CUDA_TRY(cudaStreamSynchronize(st));
+  MTSV_TRY(fetch_counters(h, d_ctr, &hc, st));
   if (hc.bad_offsets) return set_error(MTSVGPU_EINVAL, "seq_off is not monotone");
   if (hc.max_len > kMaxReadLen)
     return set_error(MTSVGPU_ELIMIT, "a read of %u bases exceeds this build's limit of %u", hc.max_len,
@@ -1355,8 +1375,7 @@ static int run_sub_batch(mtsvgpu_index* h, const Params& p, const uint8_t* d_seq
   MTSV_TRY(exclusive_scan_u32(ws.q_nhits.as<uint32_t>(), ws.hit_off.as<uint32_t>(), nq, ws.scan_tmp,
                               (uint64_t*)&d_ctr->total_hits, st));
   clk.end();
-  MTSV_CUDA_TRY(cudaMemcpyAsync(&hc, d_ctr, sizeof hc, cudaMemcpyDeviceToHost, st));
-  MTSV_CUDA_TRY(cudaStreamSynchronize(st));
+  MTSV_TRY(fetch_counters(h, d_ctr, &hc, st));
   if (hc.overflow)
     return set_error(MTSVGPU_ELIMIT, "a single read-strand produced more than %u seed hits; lower max_hits",
                      kMaxQueryHits);
@@ -1404,8 +1423,7 @@ static int run_sub_batch(mtsvgpu_index* h, const Params& p, const uint8_t* d_seq
     MTSV_TRY(exclusive_scan_u32(ws.q_ncand.as<uint32_t>(), ws.cand_off.as<uint32_t>(), nq, ws.scan_tmp,
                                 (uint64_t*)&d_ctr->total_cands, st));
     clk.end();
-    MTSV_CUDA_TRY(cudaMemcpyAsync(&hc, d_ctr, sizeof hc, cudaMemcpyDeviceToHost, st));
-    MTSV_CUDA_TRY(cudaStreamSynchronize(st));
+    MTSV_TRY(fetch_counters(h, d_ctr, &hc, st));
     n_cand = (uint32_t)hc.total_cands;
     h->stats.n_candidates += n_cand;
   }
@@ -1447,8 +1465,7 @@ static int run_sub_batch(mtsvgpu_index* h, const Params& p, const uint8_t* d_seq
     MTSV_TRY(exclusive_scan_u32(ws.q_nout.as<uint32_t>(), ws.out_off.as<uint32_t>(), nq, ws.scan_tmp,
                                 (uint64_t*)&d_ctr->total_out, st));
     clk.end();
-    MTSV_CUDA_TRY(cudaMemcpyAsync(&hc, d_ctr, sizeof hc, cudaMemcpyDeviceToHost, st));
-    MTSV_CUDA_TRY(cudaStreamSynchronize(st));
+    MTSV_TRY(fetch_counters(h, d_ctr, &hc, st));
     sub_out = hc.total_out;
     for (int i = 0; i < 32; ++i) h->stats.window_bytes += hc.window_bytes[i];
   } else {
@@ -1527,23 +1544,24 @@ int bin_batch_device(mtsvgpu_index* h, const uint8_t* d_seqs, const uint64_t* d_
     MTSV_TRY(grow_preserve(ws.out_hits, 0, sizeof(HitRec), st));
   }
   // sub-batch boundaries of seq_off: one strided gather instead of copying 8 B per read
-  const uint64_t n_sub = (n_reads + step - 1) / step;
+  // the host API (sub_batch_hook set) uploads slice by slice: short first slices fill the pipeline
+  const std::vector<uint64_t> rb = sub_batch_bounds(n_reads, step, h->sub_batch_hook != nullptr);
+  const uint64_t n_sub = rb.size() - 1;
   std::vector<uint64_t> bounds(n_sub + 1, 0);
   OffsetSource offs{h_seq_off_or_null, d_seq_off, st};
   if (n_reads) {
     if (h_seq_off_or_null) {
-      for (uint64_t i = 0; i < n_sub; ++i) bounds[i] = h_seq_off_or_null[i * step];
-      bounds[n_sub] = h_seq_off_or_null[n_reads];
+      for (uint64_t i = 0; i <= n_sub; ++i) bounds[i] = h_seq_off_or_null[rb[i]];
     } else {
+      // (no ramp without the host API: boundaries are multiples of step)
       MTSV_CUDA_TRY(cudaMemcpy2DAsync(bounds.data(), 8, d_seq_off, step * 8, 8, n_sub, cudaMemcpyDeviceToHost, st));
       MTSV_CUDA_TRY(cudaMemcpyAsync(&bounds[n_sub], d_seq_off + n_reads, 8, cudaMemcpyDeviceToHost, st));
       MTSV_CUDA_TRY(cudaStreamSynchronize(st));
     }
   }
   for (uint64_t i = 0; i < n_sub; ++i) {
-    uint64_t r0 = i * step, nr = std::min(step, n_reads - r0);
     if (h->sub_batch_hook) MTSV_TRY(h->sub_batch_hook(h, i));
-    MTSV_TRY(run_range(h, p, d_seqs, d_seq_off, offs, r0, nr, bounds[i], bounds[i + 1], &total));
+    MTSV_TRY(run_range(h, p, d_seqs, d_seq_off, offs, rb[i], rb[i + 1] - rb[i], bounds[i], bounds[i + 1], &total));
   }
   MTSV_CUDA_TRY(cudaStreamSynchronize(st));
   if (d_hits) *d_hits = reinterpret_cast<const mtsvgpu_hit*>(ws.out_hits.p);

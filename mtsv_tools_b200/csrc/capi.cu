@@ -152,14 +152,15 @@ static int bin_batch_host(mtsvgpu_index* ix, const uint8_t* seqs, const uint64_t
   }
   // ---- H2D, pipelined per device sub-batch ----
   const uint64_t step = ix->opts.batch_reads ? ix->opts.batch_reads : (1u << 20);
-  const uint64_t n_sub = (n_reads + step - 1) / step;
+  const std::vector<uint64_t> rb = sub_batch_bounds(n_reads, step, true);
+  const uint64_t n_sub = n_reads ? rb.size() - 1 : 0;
   while (ix->in_events.size() < n_sub) {
     cudaEvent_t e;
     MTSV_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     ix->in_events.push_back(e);
   }
   for (uint64_t i = 0; i < n_sub; ++i) {
-    uint64_t r0 = i * step, r1 = std::min(n_reads, r0 + step);
+    uint64_t r0 = rb[i], r1 = rb[i + 1];
     if (r1 < r0 || offs[r1] < offs[r0]) return set_error(MTSVGPU_EINVAL, "seq_off is not monotone");
     uint64_t b0 = offs[r0], nb = offs[r1] - b0;
     if (b0 + nb > bytes) return set_error(MTSVGPU_EINVAL, "seq_off exceeds the reads buffer");

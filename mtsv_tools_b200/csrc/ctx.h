@@ -5,6 +5,7 @@
 #include <stdarg.h>
 #include <stdint.h>
 
+#include <algorithm>
 #include <atomic>
 #include <string>
 #include <vector>
@@ -148,6 +149,8 @@ struct mtsvgpu_index {
   cudaStream_t stream = nullptr;
   bool profiling = false;
   mtsv::BatchWorkspace ws;
+  mtsv::BatchCounters* h_ctr = nullptr;      // page-locked, mapped: sub-batch scalars published by the device
+  mtsv::BatchCounters* h_ctr_dev = nullptr;  // its device alias
   mtsvgpu_batch_stats stats{};
   // host API: copy streams, per-sub-batch "input landed" events, pinned result buffers
   cudaStream_t copy_in_stream = nullptr;
@@ -170,6 +173,25 @@ struct mtsvgpu_index {
 };
 
 namespace mtsv {
+// Read boundaries of the device sub-batches of one batch call.  The host API uploads slice by slice while
+// earlier slices compute, so the first slices are short (step/8, step/4, step/2) to fill the pipeline quickly;
+// the rest have `step` reads.  Shared by capi.cu (uploads) and binner.cu (compute) so that they agree.
+inline std::vector<uint64_t> sub_batch_bounds(uint64_t n_reads, uint64_t step, bool ramp) {
+  std::vector<uint64_t> b{0};
+  uint64_t r = 0;
+  if (ramp && n_reads > 2 * step && step >= 64) {
+    for (uint64_t d = 8; d >= 2; d /= 2) {
+      r += step / d;
+      b.push_back(r);
+    }
+  }
+  while (r < n_reads) {
+    r = std::min(n_reads, r + step);
+    b.push_back(r);
+  }
+  return b;
+}
+
 // index.cu
 int index_from_host_parts(const uint8_t* text, uint64_t n, const mtsvgpu_bin* bins, uint64_t n_bins,
                           const uint8_t* bwt, const uint64_t* sa_sample, uint64_t sa_sample_len,

@@ -261,6 +261,7 @@ void index_destroy(mtsvgpu_index* h) {
   cudaFree(d.bin_tax);
   cudaFree(d.bin_gi);
   h->ws.release_all();
+  if (h->h_ctr) cudaFreeHost(h->h_ctr);
   if (h->pin_hits) cudaFreeHost(h->pin_hits);
   if (h->pin_off) cudaFreeHost(h->pin_off);
   for (cudaEvent_t e : h->in_events) cudaEventDestroy(e);
