@@ -853,6 +853,7 @@ struct PairJobs {
 
 template <int W, int NCLS, bool SMEM_PEQ, typename Jobs>
 __global__ void __launch_bounds__(kVerifyThreads) verify_kernel(Jobs jobs, uint32_t* __restrict__ out,
+                                                                uint32_t* __restrict__ end_out,
                                                                 BatchCounters* __restrict__ ctr) {
   extern __shared__ uint64_t peq[];  // [NCLS][W][kVerifyThreads] when SMEM_PEQ
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -902,12 +903,14 @@ __global__ void __launch_bounds__(kVerifyThreads) verify_kernel(Jobs jobs, uint3
     uint64_t lo = (c & 1) ? rw.lo : ~rw.lo, hi = (c & 2) ? rw.hi : ~rw.hi;
     return c < 4 ? (base & lo & hi) : (rw.nn & ~rw.lo & ~rw.hi);
   };
-  const uint32_t best = myers_bounded<W>(L, T, job.limit, peq_f, text);
+  uint32_t end_col = 0;
+  const uint32_t best = myers_bounded<W>(L, T, job.limit, peq_f, text, end_out ? &end_col : nullptr);
   out[job.out] = best <= job.limit ? best : kNoEdit;
+  if (end_out) end_out[job.out] = end_col;  // text columns consumed by the best alignment (for the SW check)
 }
 
 template <int NCLS, typename Jobs>
-static int launch_verify(const Jobs& jobs, uint32_t max_len, uint32_t* out, BatchCounters* ctr,
+static int launch_verify(const Jobs& jobs, uint32_t max_len, uint32_t* out, uint32_t* end_out, BatchCounters* ctr,
                          cudaStream_t st) {
   if (jobs.n == 0) return 0;
   uint32_t words = (max_len + 63) / 64;
@@ -919,7 +922,7 @@ static int launch_verify(const Jobs& jobs, uint32_t max_len, uint32_t* out, Batc
     auto kfn = verify_kernel<WW, NCLS, kSmem, Jobs>;                                              \
     if (smem > 48 * 1024)                                                                         \
       MTSV_CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    MTSV_LAUNCH(kfn, grid, kVerifyThreads, smem, st, jobs, out, ctr);                             \
+    MTSV_LAUNCH(kfn, grid, kVerifyThreads, smem, st, jobs, out, end_out, ctr);                    \
   }
   if (words <= 1) MTSV_VERIFY_CASE(1)
   else if (words <= 2) MTSV_VERIFY_CASE(2)
@@ -998,6 +1001,61 @@ __global__ void __launch_bounds__(kVerifyThreads) verify_warp_kernel(BinnerJobs 
   text16.cur = __ldg(text4 + text16.wi);
   const uint32_t best = myers_warp<W, UNIFORM>(L, job.T, job.limit, live, peq_f, text16, WarpVote());
   if (live) out[job.out] = best <= job.limit ? best : kNoEdit;
+}
+
+// ------------------------------------------------------------------------------------------
+// Reads of 254 bases and more: the SW pre-filter of src/index.rs:402-406 is no longer implied by the edit
+// distance (core.cuh, "The SW pre-filter ... for reads of 254 bases and more").  Candidates that passed the
+// edit-distance test are re-checked against an exact emulation of ssw_align's 16-bit kernel:
+//   ssw_band_kernel  thread per passing candidate: lower bound from the cells within edit+1 of the diagonal
+//                    on which the edit alignment ends; settles nearly every candidate;
+//   ssw_full_kernel  the few that stay below the threshold (or whose band would not fit its 256-row ring): both full
+//                    matrices (textbook SW decides whether the 8-bit kernel overflowed), thread per candidate,
+//                    scratch rows in global memory.
+// A rejected candidate gets kNoEdit, exactly as if it had failed :406.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) ssw_band_kernel(BinnerJobs jobs, const uint32_t* __restrict__ cand_end,
+                                                       const uint32_t* __restrict__ cand_edit,
+                                                       uint32_t* __restrict__ list, unsigned int* __restrict__ n_list) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= jobs.n) return;
+  VerifyJob job = jobs.get(i);
+  if (job.skip || job.L < 254) return;
+  const uint32_t edit = cand_edit[job.out];
+  if (edit == kNoEdit) return;
+  const uint32_t L = job.L, thr = L - 2 * job.limit;  // 2k <= L here (job.skip otherwise)
+  if (thr == 0) return;
+  const uint32_t w = edit + 1;
+  bool ok = false;
+  if (w <= kSswBandMaxW) {
+    uint16_t H[kSswBandCap], E[kSswBandCap];
+    const ReadWord* enc = job.enc;
+    const uint8_t* txt = job.txt;
+    auto rcode = [&](uint32_t q) { return plane_code(enc, q); };
+    auto tcode = [&](uint32_t c) { return dna5_code(__ldg(txt + c)); };
+    ok = ssw_word_band(L, job.T, rcode, tcode, (int64_t)cand_end[job.out] - (int64_t)L, w, thr, H, E) >= thr;
+  }
+  if (!ok) list[atomicAdd(n_list, 1u)] = i;
+}
+
+__global__ void __launch_bounds__(128) ssw_full_kernel(BinnerJobs jobs, const uint32_t* __restrict__ list,
+                                                       const unsigned int* __restrict__ n_list,
+                                                       uint32_t* __restrict__ cand_edit, uint16_t* __restrict__ scratch,
+                                                       uint32_t max_len) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+  uint16_t* H = scratch + (size_t)t * 4 * max_len;
+  const uint32_t n = *n_list;
+  for (uint32_t x = t; x < n; x += nt) {
+    VerifyJob job = jobs.get(list[x]);
+    const uint32_t L = job.L;
+    const ReadWord* enc = job.enc;
+    const uint8_t* txt = job.txt;
+    auto rcode = [&](uint32_t q) { return plane_code(enc, q); };
+    auto tcode = [&](uint32_t c) { return dna5_code(__ldg(txt + c)); };
+    if (!ssw_accepts_full(L, job.T, rcode, tcode, L - 2 * job.limit, H, H + max_len, H + 2 * (size_t)max_len,
+                          H + 3 * (size_t)max_len))
+      cand_edit[job.out] = kNoEdit;
+  }
 }
 
 // A/B knob for measurements: MTSV_B200_VERIFIER=legacy routes short reads through verify_kernel as well
@@ -1450,12 +1508,32 @@ static int run_sub_batch(mtsvgpu_index* h, const Params& p, const uint8_t* d_seq
                 ws.cand_flag.as<uint32_t>(), n_cand, ws.cand_order.as<uint32_t>());
     BinnerJobs jobs{rv, ev, p, ws.cand_dense.as<CandRec>(), ws.cand_q.as<uint32_t>(),
                     ws.cand_off.as<uint32_t>(), ws.cand_order.as<uint32_t>(), ix.text, n_cand};
-    if (hc.max_len <= 256 && !legacy_verifier())
+    const bool need_ssw = hc.max_len >= 254;  // reads the SW pre-filter is not implied for
+    if (!need_ssw && !legacy_verifier()) {
       MTSV_TRY(launch_verify_warp(jobs, ix, std::max(hc.max_len, 1u), min_len == hc.max_len,
                                   ws.cand_edit.as<uint32_t>(), st));
-    else
-      MTSV_TRY(launch_verify<4>(jobs, hc.max_len, ws.cand_edit.as<uint32_t>(),
+    } else {
+      uint32_t* cand_end = nullptr;
+      if (need_ssw) {
+        MTSV_TRY(ws.cand_end.reserve((size_t)n_cand * 4));
+        MTSV_TRY(ws.ssw_list.reserve((size_t)n_cand * 4));
+        cand_end = ws.cand_end.as<uint32_t>();
+      }
+      MTSV_TRY(launch_verify<4>(jobs, hc.max_len, ws.cand_edit.as<uint32_t>(), cand_end,
                                 h->profiling ? d_ctr : nullptr, st));
+      if (need_ssw) {
+        // scratch of the full-matrix pass: 4 rows of max_len u16 per thread, about 64 MB in all
+        const uint32_t full_threads =
+            (uint32_t)std::min<size_t>(8192, std::max<size_t>(256, ((size_t)64 << 20) / ((size_t)hc.max_len * 8))) /
+            128 * 128;
+        MTSV_TRY(ws.ssw_scratch.reserve((size_t)full_threads * 4 * hc.max_len * sizeof(uint16_t)));
+        MTSV_CUDA_TRY(cudaMemsetAsync(&d_ctr->n_ssw_full, 0, sizeof(unsigned int), st));
+        MTSV_LAUNCH(ssw_band_kernel, (n_cand + 127) / 128, 128, 0, st, jobs, cand_end, ws.cand_edit.as<uint32_t>(),
+                    ws.ssw_list.as<uint32_t>(), &d_ctr->n_ssw_full);
+        MTSV_LAUNCH(ssw_full_kernel, full_threads / 128, 128, 0, st, jobs, ws.ssw_list.as<uint32_t>(),
+                    &d_ctr->n_ssw_full, ws.cand_edit.as<uint32_t>(), ws.ssw_scratch.as<uint16_t>(), hc.max_len);
+      }
+    }
     clk.end();
     // ---- select ----
     clk.begin(ST_EMIT);
@@ -1695,7 +1773,7 @@ int edit_distance_batch(int device, const uint8_t* pats, const uint64_t* pat_off
     const uint64_t threads = n_pairs * w_max;
     MTSV_LAUNCH(encode_fwd_kernel, (unsigned)((threads * 32 + 255) / 256), 256, 0, 0, pv, dw.as<ReadWord>(), w_max, 1);
     PairJobs jobs{pv, ev, dt.as<uint8_t>(), dto.as<uint64_t>(), (uint32_t)n_pairs};
-    if ((rc = launch_verify<5>(jobs, std::max(max_len, 1u), de.as<uint32_t>(), nullptr, 0))) break;
+    if ((rc = launch_verify<5>(jobs, std::max(max_len, 1u), de.as<uint32_t>(), nullptr, nullptr, 0))) break;
     cudaError_t e = cudaMemcpy(edits, de.p, n_pairs * 4, cudaMemcpyDeviceToHost);
     if (e != cudaSuccess) rc = set_error(MTSVGPU_ECUDA, "edit_distance: %s", cudaGetErrorString(e));
   } while (0);

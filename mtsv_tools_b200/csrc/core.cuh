@@ -662,7 +662,10 @@ static unsigned long long g_myers_blocks = 0, g_myers_cols = 0;  // test-only in
 #endif
 
 template <int W, typename PeqF, typename TextF>
-MTSV_HD uint32_t myers_bounded(uint32_t L, uint32_t T, uint32_t k, PeqF peq, TextF text) {
+MTSV_HD uint32_t myers_bounded(uint32_t L, uint32_t T, uint32_t k, PeqF peq, TextF text,
+                               uint32_t* end_col = nullptr) {
+  // end_col (optional): number of text columns consumed by the first best alignment found (0 = D[L][0])
+  if (end_col) *end_col = 0;
   if (L == 0) return 0;
   if (k > L) k = L;  // D[L][0] = L bounds the answer; also keeps k + rows small
   uint64_t Pv[W], Mv[W];
@@ -742,7 +745,10 @@ MTSV_HD uint32_t myers_bounded(uint32_t L, uint32_t T, uint32_t k, PeqF peq, Tex
         }
       }
     }
-    if (bottom_score < best) best = bottom_score;
+    if (bottom_score < best) {
+      best = bottom_score;
+      if (end_col) *end_col = j + 1;
+    }
   }
   return best;
 }
@@ -900,6 +906,138 @@ MTSV_HD uint32_t myers_warp(uint32_t L, uint32_t T, uint32_t k, bool live, PeqF 
     }
   }
   return best;
+}
+
+// ---------------------------------------------------------------------------------------------
+// The SW pre-filter of src/index.rs:402-406 for reads of 254 bases and more.
+//
+// For shorter reads the test `score >= L - 2k` is implied by `min_edit_distance <= k`:
+// ssw_align's 8-bit kernel is textbook local SW.  Once the true SW score reaches 254 the 8-bit kernel
+// overflows (ssw.c:271,302) and ssw_align re-runs sw_sse2_word (ssw.c:789-792, :354-530), which is NOT
+// textbook SW: with gap open == gap extend (the reference passes 1, 1: src/index.rs:402) its lazy-F loop
+// (ssw.c:444-455) always leaves after its first vector — after `vH = max(vH, vF)` the exit test
+// `vF - gapE > vH - gapO` can never hold.  In scalar terms (query row q sits in SIMD lane q / segLen at
+// position q % segLen, segLen = ceil(L / 8)): the vertical-gap value F restarts from 0 at every lane
+// boundary row (q % segLen == 0); the F that arrives there from the row above only lifts the STORED H of
+// that one row (used as the next column's diagonal and for the maximum), while E and the F of the rows
+// below continue from the uncorrected H.  Scores come out up to a few points lower than SW, which can
+// push a candidate with edit distance <= k under the threshold.  The functions below reproduce the kernel
+// cell for cell (16-bit saturation never triggers: scores < 32767).
+//
+// Codes: 0..3 = A,C,G,T, 4 = anything else; 4 matches 4 (ssw/src/lib.rs:11-16,93-99).
+// ---------------------------------------------------------------------------------------------
+MTSV_HD int32_t ssw_sub(uint32_t rc, uint32_t tc) { return rc == tc ? 1 : -1; }
+
+// One column of sw_sse2_word over rows [q_lo, q_hi]; H/E are indexed through `slot(q)`.  diag_in = stored H of
+// row q_lo - 1 in the previous column (0 above the matrix / outside a band).  Returns the column maximum.
+template <typename ReadF, typename SlotF>
+MTSV_HD uint32_t ssw_word_column(uint32_t q_lo, uint32_t q_hi, uint32_t seg_len, uint32_t tc, ReadF rcode,
+                                 uint16_t* H, uint16_t* E, SlotF slot, uint32_t diag_in) {
+  uint32_t colmax = 0, F = 0, diag = diag_in;
+  for (uint32_t q = q_lo; q <= q_hi; ++q) {
+    const uint32_t sl = slot(q);
+    const uint32_t e = E[sl];
+    int32_t h = (int32_t)diag + ssw_sub(rcode(q), tc);  // _mm_adds_epi16(vH, profile)
+    if (h < (int32_t)e) h = (int32_t)e;                  // e >= 0, so h >= 0 from here on
+    uint32_t carry = 0;
+    if (q % seg_len == 0) {  // first row of a SIMD lane: F restarts; the carry only corrects the stored H
+      carry = q == q_lo ? 0 : F;
+      F = 0;
+    }
+    if ((uint32_t)h < F) h = (int32_t)F;
+    const uint32_t t = h > 0 ? (uint32_t)h - 1 : 0;  // _mm_subs_epu16(vH, vGapO)
+    const uint32_t e1 = e > 0 ? e - 1 : 0;
+    E[sl] = (uint16_t)(e1 > t ? e1 : t);
+    const uint32_t f1 = F > 0 ? F - 1 : 0;
+    F = f1 > t ? f1 : t;
+    uint32_t hst = (uint32_t)h > carry ? (uint32_t)h : carry;  // lazy-F, j == 0 of every lane only
+    diag = H[sl];
+    H[sl] = (uint16_t)hst;
+    if (hst > colmax) colmax = hst;
+  }
+  return colmax;
+}
+
+// Lower bound of the sw_sse2_word score from the cells within `w` of the diagonal text_col - row == d0
+// (cells outside count as 0; every operation of the kernel is monotone, so restricting it can only lower the
+// result).  Stops as soon as `thr` is reached.  H/E: 2 x kSswBandCap entries, used circularly.
+constexpr uint32_t kSswBandCap = 256;
+constexpr uint32_t kSswBandMaxW = kSswBandCap / 2 - 1;  // rows q_lo-1 .. q_hi of a column must fit the ring
+template <typename ReadF, typename TextF>
+MTSV_HD uint32_t ssw_word_band(uint32_t L, uint32_t T, ReadF rcode, TextF tcode, int64_t d0, uint32_t w,
+                               uint32_t thr, uint16_t* H, uint16_t* E) {
+  const uint32_t seg_len = (L + 7) / 8;
+  for (uint32_t x = 0; x < kSswBandCap; ++x) H[x] = E[x] = 0;
+  int64_t i_lo = d0 - (int64_t)w, i_hi = d0 + (int64_t)(L - 1) + (int64_t)w;
+  if (i_lo < 0) i_lo = 0;
+  if (i_hi > (int64_t)T - 1) i_hi = (int64_t)T - 1;
+  uint32_t best = 0;
+  auto slot = [](uint32_t q) { return q & (kSswBandCap - 1); };
+  for (int64_t i = i_lo; i <= i_hi; ++i) {
+    int64_t ql = i - d0 - (int64_t)w, qh = i - d0 + (int64_t)w;
+    if (qh < 0 || ql > (int64_t)L - 1) continue;
+    if (qh <= (int64_t)L - 1 && i > i_lo) H[slot((uint32_t)qh)] = E[slot((uint32_t)qh)] = 0;  // row enters the band
+    if (ql < 0) ql = 0;
+    if (qh > (int64_t)L - 1) qh = (int64_t)L - 1;
+    uint32_t diag_in = 0;
+    if (ql > 0 && i > i_lo) diag_in = H[slot((uint32_t)ql - 1)];  // top row of the previous column's band
+    uint32_t m = ssw_word_column((uint32_t)ql, (uint32_t)qh, seg_len, tcode((uint32_t)i), rcode, H, E, slot, diag_in);
+    if (m > best) best = m;
+    if (best >= thr) return best;
+  }
+  return best;
+}
+
+// The reference's decision at src/index.rs:406 from the full matrices: textbook SW (what the 8-bit kernel
+// returns while it does not overflow) and the 16-bit kernel, in one pass.  H/E/H2/E2: L entries each.
+template <typename ReadF, typename TextF>
+MTSV_HD bool ssw_accepts_full(uint32_t L, uint32_t T, ReadF rcode, TextF tcode, uint32_t thr, uint16_t* H,
+                              uint16_t* E, uint16_t* H2, uint16_t* E2, uint32_t* word_out = nullptr,
+                              uint32_t* exact_out = nullptr) {  // (scores are only complete when thr is unreachable)
+  const uint32_t seg_len = (L + 7) / 8;
+  for (uint32_t q = 0; q < L; ++q) H[q] = E[q] = H2[q] = E2[q] = 0;
+  uint32_t word_best = 0, exact_best = 0;
+  auto slot = [](uint32_t q) { return q; };
+  for (uint32_t i = 0; i < T; ++i) {
+    const uint32_t tc = tcode(i);
+    uint32_t m = ssw_word_column(0, L - 1, seg_len, tc, rcode, H, E, slot, 0);
+    if (m > word_best) word_best = m;
+    if (word_best >= thr) return true;  // (and if the 8-bit kernel did not overflow, SW itself is >= this)
+    // textbook SW, linear gap 1 (== sw_sse2_byte below its overflow point)
+    uint32_t diag = 0, F = 0;
+    for (uint32_t q = 0; q < L; ++q) {
+      int32_t h = (int32_t)diag + ssw_sub(rcode(q), tc);
+      const uint32_t e = E2[q];
+      if (h < (int32_t)e) h = (int32_t)e;
+      if ((uint32_t)h < F) h = (int32_t)F;
+      const uint32_t t = h > 0 ? (uint32_t)h - 1 : 0;
+      const uint32_t e1 = e > 0 ? e - 1 : 0;
+      E2[q] = (uint16_t)(e1 > t ? e1 : t);
+      const uint32_t f1 = F > 0 ? F - 1 : 0;
+      F = f1 > t ? f1 : t;
+      diag = H2[q];
+      H2[q] = (uint16_t)h;
+      if ((uint32_t)h > exact_best) exact_best = (uint32_t)h;
+    }
+  }
+  // ssw_align: the 8-bit result unless it overflowed (max + bias >= 255, bias = 1), then the 16-bit kernel's
+  if (word_out) *word_out = word_best;
+  if (exact_out) *exact_out = exact_best;
+  const uint32_t score = exact_best >= 254 ? word_best : exact_best;
+  return score >= thr;
+}
+
+// read code of row q from the bit planes: 0..3, N -> 4
+MTSV_HD uint32_t plane_code(const ReadWord* qw, uint32_t q) {
+  const ReadWord& w = qw[q >> 6];
+  const uint32_t b = q & 63;
+  if ((w.nn >> b) & 1) return 4;
+  return (uint32_t)((w.lo >> b) & 1) | ((uint32_t)((w.hi >> b) & 1) << 1);
+}
+// reference byte -> dna5 code (ssw/src/lib.rs:93-99)
+MTSV_HD uint32_t dna5_code(uint8_t b) {
+  uint32_t c = upper_acgtn_code(b);
+  return c < 4 ? c : 4;
 }
 
 // ---------------------------------------------------------------------------------------------

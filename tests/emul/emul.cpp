@@ -177,8 +177,58 @@ void emul_backward_search(void* p, const uint8_t* pat, uint32_t len, uint32_t* l
 }
 
 // Myers recurrence exactly as verify_kernel evaluates it (ncls = 4: binner rule, 5: raw bytes)
+static uint32_t edit_distance_k_end(const uint8_t* pat, uint32_t L, uint32_t rc, const uint8_t* txt, uint32_t T,
+                                    int ncls, uint32_t k, uint32_t* end_col);
+
 uint32_t emul_edit_distance_k(const uint8_t* pat, uint32_t L, uint32_t rc, const uint8_t* txt, uint32_t T,
                               int ncls, uint32_t k) {
+  return edit_distance_k_end(pat, L, rc, txt, T, ncls, k, nullptr);
+}
+
+// The decision of src/index.rs:406 for reads >= 254 bases, as the device takes it (binner.cu ssw_band_kernel /
+// ssw_full_kernel): banded lower bound of the 16-bit kernel around the edit alignment first, full matrices if
+// that is not enough.  which: 0 = as the device, 1 = full matrices only, 2 = band only (lower-bound score).
+uint32_t emul_ssw_accepts(const uint8_t* read, uint32_t L, const uint8_t* txt, uint32_t T, uint32_t k,
+                          uint32_t edit, uint32_t end_col, int which) {
+  std::vector<ReadWord> q = encode_query(read, L, false, false);
+  auto rcode = [&](uint32_t x) { return plane_code(q.data(), x); };
+  auto tcode = [&](uint32_t i) { return dna5_code(txt[i]); };
+  const uint32_t thr = L - 2 * k;
+  const uint32_t w = edit + 1;
+  if (which != 1 && w <= kSswBandMaxW) {
+    uint16_t H[kSswBandCap], E[kSswBandCap];
+    uint32_t b = ssw_word_band(L, T, rcode, tcode, (int64_t)end_col - (int64_t)L, w, thr, H, E);
+    if (which == 2) return b;
+    if (b >= thr) return 1;
+  }
+  if (which == 2) return 0;
+  std::vector<uint16_t> buf(4 * (size_t)L);
+  return ssw_accepts_full(L, T, rcode, tcode, thr, buf.data(), buf.data() + L, buf.data() + 2 * L,
+                          buf.data() + 3 * L)
+             ? 1
+             : 0;
+}
+
+// bounded edit distance (binner match rule, forward strand) + the end column of the first best alignment
+uint32_t emul_edit_distance_end(const uint8_t* pat, uint32_t L, const uint8_t* txt, uint32_t T, uint32_t k,
+                                uint32_t* end_col) {
+  return edit_distance_k_end(pat, L, 0, txt, T, 4, k, end_col);
+}
+
+// both scores of the full matrices: the emulated sw_sse2_word and textbook SW
+void emul_ssw_scores(const uint8_t* read, uint32_t L, const uint8_t* txt, uint32_t T, uint32_t* word,
+                     uint32_t* exact) {
+  std::vector<ReadWord> q = encode_query(read, L, false, false);
+  auto rcode = [&](uint32_t x) { return plane_code(q.data(), x); };
+  auto tcode = [&](uint32_t i) { return dna5_code(txt[i]); };
+  std::vector<uint16_t> buf(4 * (size_t)L);
+  ssw_accepts_full(L, T, rcode, tcode, 0xffffffffu, buf.data(), buf.data() + L, buf.data() + 2 * L,
+                   buf.data() + 3 * L, word, exact);
+}
+
+static uint32_t edit_distance_k_end(const uint8_t* pat, uint32_t L, uint32_t rc, const uint8_t* txt, uint32_t T,
+                                    int ncls, uint32_t k, uint32_t* end_col) {
+  if (end_col) *end_col = 0;
   if (L == 0) return 0;
   if (L > 4096) return 0xffffffffu;
   // pattern masks from the bit planes, as verify_kernel builds them
@@ -192,7 +242,7 @@ uint32_t emul_edit_distance_k(const uint8_t* pat, uint32_t L, uint32_t rc, const
     uint32_t c = text_code(txt[j]);
     return c < (uint32_t)ncls ? c : 7u;
   };
-  return L <= 1024 ? myers_bounded<16>(L, T, k, pf, tf) : myers_bounded<64>(L, T, k, pf, tf);
+  return L <= 1024 ? myers_bounded<16>(L, T, k, pf, tf, end_col) : myers_bounded<64>(L, T, k, pf, tf, end_col);
 }
 
 // The warp-uniform fast path (core.cuh::myers_warp) as one lane.  The votes of the other 31 lanes are
@@ -349,8 +399,27 @@ int emul_bin_reads(void* p, const uint8_t* seqs, const uint64_t* seq_off, uint64
                   2ull * k > (uint64_t)L || L == 0;
       uint32_t ed = kNoEdit;
       if (!skip) {
-        ed = emul_edit_distance_k(seq, L, rc, e->text.data() + dense[i].start, dense[i].end - dense[i].start, 4, k);
+        const uint8_t* win = e->text.data() + dense[i].start;
+        const uint32_t T = dense[i].end - dense[i].start;
+        uint32_t end_col = 0;
+        ed = edit_distance_k_end(seq, L, rc, win, T, 4, k, &end_col);
         if (ed > k) ed = kNoEdit;
+        if (ed != kNoEdit && L >= 254) {  // the SW pre-filter is no longer implied (core.cuh, ssw_word_*)
+          auto rcode = [&](uint32_t x) { return plane_code(qwords.data(), x); };
+          auto tcode = [&](uint32_t c) { return dna5_code(win[c]); };
+          const uint32_t thr = L - 2 * k, w = ed + 1;
+          bool ok = false;
+          if (w <= kSswBandMaxW) {
+            uint16_t Hb[kSswBandCap], Eb[kSswBandCap];
+            ok = ssw_word_band(L, T, rcode, tcode, (int64_t)end_col - (int64_t)L, w, thr, Hb, Eb) >= thr;
+          }
+          if (!ok) {
+            std::vector<uint16_t> buf(4 * (size_t)L);
+            ok = ssw_accepts_full(L, T, rcode, tcode, thr, buf.data(), buf.data() + L, buf.data() + 2 * L,
+                                  buf.data() + 3 * L);
+          }
+          if (!ok) ed = kNoEdit;
+        }
       }
       edits[i] = ed;
     }

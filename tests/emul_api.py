@@ -60,6 +60,14 @@ def lib():
     L.emul_edit_distance_warp_wide.restype = C.c_uint32
     L.emul_edit_distance_warp_wide.argtypes = [C.c_char_p, C.c_uint32, C.c_char_p, C.c_uint32, C.c_uint32,
                                                C.c_uint32, C.c_uint64, C.c_uint32]
+    L.emul_ssw_scores.argtypes = [C.c_char_p, C.c_uint32, C.c_char_p, C.c_uint32, C.POINTER(C.c_uint32),
+                                  C.POINTER(C.c_uint32)]
+    L.emul_edit_distance_end.restype = C.c_uint32
+    L.emul_edit_distance_end.argtypes = [C.c_char_p, C.c_uint32, C.c_char_p, C.c_uint32, C.c_uint32,
+                                         C.POINTER(C.c_uint32)]
+    L.emul_ssw_accepts.restype = C.c_uint32
+    L.emul_ssw_accepts.argtypes = [C.c_char_p, C.c_uint32, C.c_char_p, C.c_uint32, C.c_uint32, C.c_uint32,
+                                   C.c_uint32, C.c_int]
     L.emul_bin_reads.argtypes = [vp, vp, vp, C.c_uint64, C.POINTER(Params), C.POINTER(vp), C.POINTER(vp)]
     L.emul_free.argtypes = [vp]
     _LIB = L
@@ -134,3 +142,23 @@ def edit_distance_warp(pat, txt, k, rc=0, uniform=True, noise=0, seed=1, other_T
                                                       other_T))
     return int(lib().emul_edit_distance_warp(bytes(pat), len(pat), rc, bytes(txt), len(txt), k, int(uniform),
                                              noise, seed, other_T))
+
+
+def ssw_accepts(read, txt, k, edit, end_col, which=0):
+    """src/index.rs:406 for reads >= 254 bases as the device decides it (core.cuh ssw_word_band /
+    ssw_accepts_full).  which: 0 = band then full, 1 = full only, 2 = the band's lower-bound score."""
+    return int(lib().emul_ssw_accepts(bytes(read), len(read), bytes(txt), len(txt), k, edit, end_col, which))
+
+
+def ssw_scores(read, txt):
+    """(emulated sw_sse2_word score, textbook SW score) over the full matrices."""
+    w, e = C.c_uint32(), C.c_uint32()
+    lib().emul_ssw_scores(bytes(read), len(read), bytes(txt), len(txt), C.byref(w), C.byref(e))
+    return w.value, e.value
+
+
+def edit_distance_end(pat, txt, k):
+    """(bounded edit distance, number of text columns consumed by the first best alignment)."""
+    ec = C.c_uint32()
+    e = lib().emul_edit_distance_end(bytes(pat), len(pat), bytes(txt), len(txt), k, C.byref(ec))
+    return int(e), ec.value

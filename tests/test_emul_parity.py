@@ -133,6 +133,154 @@ def test_edit_distance_warp_fuzz(oracle, emul):
     assert n_within > 1000
 
 
+def _long_pair(rng, max_edits=40):
+    L = rng.randint(254, 520)
+    read = [rng.choice(b"ACGT") for _ in range(L)]
+    if rng.random() < 0.2:
+        for _ in range(rng.randint(1, 5)):
+            read[rng.randrange(L)] = ord("N")
+    s = list(read)
+    for _ in range(rng.randint(0, max_edits)):
+        i = rng.randrange(len(s))
+        r = rng.random()
+        if r < 0.3:
+            s[i] = rng.choice(b"ACGTN")
+        elif r < 0.65:  # runs of inserted reference bases / deleted read bases: gaps that cross SIMD lane rows
+            for _ in range(rng.randint(1, 4)):
+                s.insert(i, rng.choice(b"ACGT"))
+        else:
+            for _ in range(rng.randint(1, 4)):
+                if len(s) > 1 and i < len(s):
+                    del s[i]
+    tx = bytes(rng.choice(b"ACGT") for _ in range(rng.randint(0, 50))) + bytes(s) + \
+        bytes(rng.choice(b"ACGT") for _ in range(rng.randint(0, 50)))
+    return bytes(read), tx
+
+
+def test_ssw_word_kernel_emulation(oracle, emul):
+    """Reads >= 254 bases: ssw_align falls to sw_sse2_word once SW reaches 254, and that kernel is not textbook
+    SW (core.cuh).  The cell-for-cell emulation must reproduce the reference's own ssw.c (oracle/_ref) score;
+    the banded lower bound must never exceed it; the device's accept decision must equal `score >= L - 2k`."""
+    if not oracle.ssw_ref_available():
+        pytest.skip("oracle/_ref/libssw_ref.so not built")
+    rng = random.Random(7)
+    n_word = n_diff = n_band_ok = n_band_short = 0
+    for it in range(1200):
+        read, tx = _long_pair(rng)
+        L = len(read)
+        ref_score = oracle.ssw_score(read, tx, 1)
+        w, e = emul.ssw_scores(read, tx)
+        assert (w if e >= 254 else e) == ref_score, (it, L, len(tx), ref_score, w, e)
+        assert w <= e
+        n_word += e >= 254
+        n_diff += w != e
+        # decision as the device takes it, for budgets around the candidate's own edit distance
+        ed, end_col = emul.edit_distance_end(read, tx, L)
+        for k in {ed, ed + 1, ed + 3, (L - ref_score) // 2, (L - ref_score + 1) // 2, int(L * 0.13) + 1}:
+            if ed > k or 2 * k > L:
+                continue
+            want = ref_score >= L - 2 * k
+            assert bool(emul.ssw_accepts(read, tx, k, ed, end_col, 0)) == want, (it, L, k, ed, ref_score)
+            assert bool(emul.ssw_accepts(read, tx, k, ed, end_col, 1)) == want
+            if ed + 1 <= 127:
+                b = emul.ssw_accepts(read, tx, 0, ed, end_col, 2)  # k = 0: threshold L, never reached early
+                assert b <= w, (it, b, w)
+                n_band_ok += b >= L - 2 * ed
+                n_band_short += b < L - 2 * ed
+    assert n_word > 500 and n_diff > 20
+    assert n_band_ok > 10 * max(1, n_band_short)  # the band settles nearly every case without the full matrices
+
+
+def _long_reads(ref_cat, n, read_len, seed, edit_frac):
+    """Reads of `read_len` bases sampled from the reference and edited at about edit_frac per base with
+    substitutions and RUNS of inserted / deleted bases (what trips sw_sse2_word), half reverse-complemented."""
+    rng = random.Random(seed)
+    out = []
+    text = bytes(ref_cat)
+    for _ in range(n):
+        st = rng.randrange(0, len(text) - 2 * read_len)
+        s = list(text[st:st + read_len + 60])
+        n_ed = max(0, int(rng.gauss(edit_frac * read_len, 0.25 * edit_frac * read_len)))
+        done = 0
+        while done < n_ed:
+            i = rng.randrange(5, read_len - 5)
+            r = rng.random()
+            if r < 0.4:
+                s[i] = rng.choice(b"ACGT")
+                done += 1
+            elif r < 0.7:
+                run = rng.randint(1, 4)
+                for _ in range(run):
+                    s.insert(i, rng.choice(b"ACGT"))
+                done += run
+            else:
+                run = rng.randint(1, 4)
+                del s[i:i + run]
+                done += run
+        read = bytes(s[:read_len])
+        if rng.random() < 0.5:
+            read = synth.revcomp(read)
+        out.append(read)
+    return out
+
+
+def _borderline_long_reads(ref_cat, n, read_len, k, seed):
+    """Reads built to sit on the SW threshold: exactly k or k-1 edits, none of them a deleted reference base
+    (SW = L - 2*edits then), with a run of 2-4 inserted bases laid across a SIMD lane boundary row of
+    sw_sse2_word (row l * ceil(L/8)) — the alignments its truncated lazy-F loop under-scores."""
+    rng = random.Random(seed)
+    text = bytes(ref_cat)
+    seg = (read_len + 7) // 8
+    out = []
+    other = {65: b"CGT", 67: b"AGT", 71: b"ACT", 84: b"ACG"}
+    while len(out) < n:
+        a = rng.randint(2, 4)
+        st = rng.randrange(0, len(text) - 2 * read_len)
+        base = list(text[st:st + read_len - a])
+        if any(c not in other for c in base):
+            continue
+        lane = rng.randint(1, 7)
+        pos = lane * seg - rng.randint(1, a - 1)  # the run covers rows pos .. pos+a-1, crossing row lane*seg
+        ins = [rng.choice(b"ACGT") for _ in range(a)]
+        s = base[:pos] + ins + base[pos:]
+        assert len(s) == read_len
+        n_sub = k - a - rng.randint(0, 1)
+        for i in rng.sample([i for i in range(3, read_len - 3) if not pos - 2 <= i < pos + a + 2], max(0, n_sub)):
+            s[i] = rng.choice(other[s[i]])
+        read = bytes(s)
+        if rng.random() < 0.5:
+            read = synth.revcomp(read)
+        out.append(read)
+    return out
+
+
+def test_pipeline_reads_of_254_bases_and_more(oracle, emul, small_ref, small_index):
+    """The oracle runs the reference's own ssw.c (16-bit kernel for these reads); the per-item device logic
+    must reject exactly the candidates it rejects (edit distance within budget but SSW score below L - 2k)."""
+    if not oracle.ssw_ref_available():
+        pytest.skip("oracle/_ref/libssw_ref.so not built")
+    L = oracle.lib()
+    n_changed = 0
+    for read_len, rate, frac in ((254, 0.13, 0.11), (300, 0.13, 0.12), (300, 0.05, 0.045), (420, 0.10, 0.09)):
+        rl = _long_reads(small_ref[0], 150, read_len, seed=read_len + int(rate * 100), edit_frac=frac)
+        k = int(np.ceil(read_len * rate))
+        rl += _borderline_long_reads(small_ref[0], 150, read_len, k, seed=read_len)
+        reads = oracle.pack_seqs(rl)
+        p = oracle.default_params(edit_rate=rate)
+        h1, o1 = small_index.bin_reads(reads, p, threads=4)  # real ssw.c
+        e = emul.EmulIndex(small_index, sa_rate=1, ktab_k=6)
+        h2, o2 = e.bin_reads(reads[0], reads[1], p)
+        _same(h1, o1, h2, o2)
+        assert len(h1) > 40
+        L.orc_set_ssw_kind(2)  # textbook SW: "edit <= k" alone
+        try:
+            h3, o3 = small_index.bin_reads(reads, p, threads=4)
+        finally:
+            L.orc_set_ssw_kind(0)
+        n_changed += int(np.sum((o3[1:] - o3[:-1]) != (o1[1:] - o1[:-1])))
+    assert n_changed > 0, "no read exercised the 16-bit kernel's deviation; make the cases harder"
+
+
 CASES = [
     ("defaults dense+ktab", {}, 1, 8),
     ("sa_rate 4, no table", {}, 4, 0),
