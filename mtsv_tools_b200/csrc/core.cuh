@@ -852,10 +852,21 @@ MTSV_HD uint32_t myers_warp(uint32_t L, uint32_t T, uint32_t k, bool live, PeqF 
   for (uint32_t j0 = 0; j0 < Tw; j0 += 16) {
     // ---- pruning votes, once per 16 columns (late pruning is always exact) ----
     const uint32_t reach = (uint32_t)(last + 1) * 64;
-    const bool done = !live || j0 >= T || (reach < L && (L - reach) > (T - j0) + k);
+    // Value-based pruning of the top block: a cell (i, j) with value D lies on an alignment of cost <= k only if
+    // D + (L - i) - (T - j) <= k (the rows still to come need that many vertical moves).  Inside a block
+    // D[i] >= D[bottom] - (bottom - i), so D[bottom] + L + j > k + bottom + T rules out every cell of the block
+    // at this column; once row 0 can no longer start an alignment (j + L > T + k) everything that enters the
+    // block later descends from such cells.
+    uint32_t bf = bs[0];
+#pragma unroll
+    for (int w = 1; w < W; ++w)
+      if (w == first) bf = bs[w];
+    const uint32_t bottom_f = (uint32_t)(first + 1) * 64 < L ? (uint32_t)(first + 1) * 64 : L;
+    const bool top_useless = j0 + L > T + k && bf + L + j0 > k + bottom_f + T;
+    const bool done = !live || j0 >= T || (reach < L && (L - reach) > (T - j0) + k) || (first == last && top_useless);
     if (vote.all(done)) break;
     if (first < last) {  // top block entirely above the band: 64(first+1) + slack < L + j0 + 1
-      bool can = done || ((uint32_t)(first + 1) * 64 + slack < L + j0 + 1);
+      bool can = done || ((uint32_t)(first + 1) * 64 + slack < L + j0 + 1) || top_useless;
       if (vote.all(can)) ++first;
     }
     if (last > first) {  // bottom block holds only values > k (with the margin of the activation rule below)
