@@ -400,7 +400,7 @@ def run_gpu_arm(args, cfg, rank, world, local_rank):
     # algorithmic bytes = per-unit figure of DESIGN.md §3 x units counted by the kernels themselves.
     peaks, peak_kind = measured_peaks()
     S = params.seed_size
-    n_sub = max(1, -(-n_reads // (args.batch_reads or (1 << 20))))
+    n_sub = max(1, int(stats.get("n_sub_batches", 0)) or -(-n_reads // (args.batch_reads or (1 << 22))))
     per_step = {k: v / args.steps for k, v in stage_ms.items()}
     alg_bytes = {
         # index sectors needed (k-mer table + FmBlock sectors, counted in-kernel) + 2 plane words in + 8 B out
@@ -484,7 +484,7 @@ def run_gpu_arm(args, cfg, rank, world, local_rank):
         "data": "synthetic",
         "config": {"workload": cfg["label"], "reads_per_gpu_per_step": n_reads, "index_mbp": info["text_len"] / 1e6,
                    "index_replicated": True, "device_sa_rate": info["device_sa_rate"], "ktab_k": info["ktab_k"],
-                   "index_hbm_gb": info["device_bytes"] / 1e9, "batch_reads": args.batch_reads or (1 << 20),
+                   "index_hbm_gb": info["device_bytes"] / 1e9, "batch_reads": args.batch_reads or "default (1<<22 device-resident; host input: ramped slices up to 1<<20 on two lanes)",
                    "l2_note": "index (>= 1 GB at cfg2) and per-step read batch exceed the 126 MB L2",
                    "hits_per_step": int(stats["n_hits"]), "profiling_events": not args.no_profile},
         "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": int(hr.nbytes + ho.nbytes),

@@ -84,7 +84,8 @@ typedef struct {
                              fits the memory budget), otherwise a divisor of the file's rate          */
   uint32_t ktab_k;        /* k-mer interval table order: 0 = auto, 1..16; 0xFFFFFFFF = none           */
   uint64_t max_batch_hits;/* cap on seed hits in flight per device sub-batch (0 = default 1<<27)      */
-  uint32_t batch_reads;   /* reads per device sub-batch (0 = default 1<<20)                            */
+  uint32_t batch_reads;   /* reads per device sub-batch (0 = default: 1<<22 for device-resident input,
+                             1<<20 with ramped first/last slices for host input)                       */
   uint32_t reserved;
 } mtsvgpu_index_opts;
 
@@ -113,6 +114,7 @@ typedef struct {
   uint64_t n_hits;         /* hits returned */
   uint64_t window_bytes;   /* reference bytes read by the verifier */
   uint64_t rank_queries;   /* 32-byte index sectors touched by seed search: FM blocks + k-mer table (0 unless profiling) */
+  uint64_t n_sub_batches;  /* device sub-batches the call was processed in (= launches of every stage kernel) */
 } mtsvgpu_batch_stats;
 
 /* ---- index lifetime: replaces from_file::<MGIndex> (src/io.rs:115-122, src/binner.rs:63-67) ---- */

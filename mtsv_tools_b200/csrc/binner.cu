@@ -15,6 +15,7 @@
 //
 // All per-item arithmetic lives in core.cuh (shared with the CPU emulation tests).
 #include <algorithm>
+#include <thread>
 
 #include "ctx.h"
 
@@ -1257,35 +1258,36 @@ static int validate_params(const mtsvgpu_params* in, Params* p) {
 
 struct StageClock {
   mtsvgpu_index* h;
-  explicit StageClock(mtsvgpu_index* hh) : h(hh) {}
+  Lane& ln;
+  StageClock(mtsvgpu_index* hh, Lane& l) : h(hh), ln(l) {}
   cudaEvent_t next_event() {
-    if (h->ev_next == h->ev_pool.size()) {
+    if (ln.ev_next == ln.ev_pool.size()) {
       cudaEvent_t e;
       cudaEventCreate(&e);
-      h->ev_pool.push_back(e);
+      ln.ev_pool.push_back(e);
     }
-    return h->ev_pool[h->ev_next++];
+    return ln.ev_pool[ln.ev_next++];
   }
   void begin(int stage) {
     if (!h->profiling) return;
     cudaEvent_t a = next_event(), b = next_event();
-    cudaEventRecord(a, h->stream);
-    h->ev_used.push_back({stage, {a, b}});
+    cudaEventRecord(a, ln.stream);
+    ln.ev_used.push_back({stage, {a, b}});
   }
   void end() {
     if (!h->profiling) return;
-    cudaEventRecord(h->ev_used.back().second.second, h->stream);
+    cudaEventRecord(ln.ev_used.back().second.second, ln.stream);
   }
   void resolve() {
     if (!h->profiling) return;
-    cudaStreamSynchronize(h->stream);
-    for (auto& e : h->ev_used) {
+    cudaStreamSynchronize(ln.stream);
+    for (auto& e : ln.ev_used) {
       float ms = 0;
       cudaEventElapsedTime(&ms, e.second.first, e.second.second);
-      h->stats.ms[e.first] += ms;
+      ln.stats.ms[e.first] += ms;
     }
-    h->ev_used.clear();
-    h->ev_next = 0;
+    ln.ev_used.clear();
+    ln.ev_next = 0;
   }
 };
 
@@ -1336,27 +1338,53 @@ __global__ void publish_counters_kernel(const BatchCounters* __restrict__ d, Bat
   __threadfence_system();
 }
 
-static int fetch_counters(mtsvgpu_index* h, const BatchCounters* d_ctr, BatchCounters* out, cudaStream_t st) {
-  if (!h->h_ctr) {
-    MTSV_CUDA_TRY(cudaHostAlloc((void**)&h->h_ctr, sizeof(BatchCounters), cudaHostAllocMapped));
-    MTSV_CUDA_TRY(cudaHostGetDevicePointer((void**)&h->h_ctr_dev, h->h_ctr, 0));
+static int fetch_counters(Lane& ln, const BatchCounters* d_ctr, BatchCounters* out, cudaStream_t st) {
+  if (!ln.h_ctr) {
+    MTSV_CUDA_TRY(cudaHostAlloc((void**)&ln.h_ctr, sizeof(BatchCounters), cudaHostAllocMapped));
+    MTSV_CUDA_TRY(cudaHostGetDevicePointer((void**)&ln.h_ctr_dev, ln.h_ctr, 0));
   }
-  MTSV_LAUNCH(publish_counters_kernel, 1, 160, 0, st, d_ctr, h->h_ctr_dev);
+  MTSV_LAUNCH(publish_counters_kernel, 1, 160, 0, st, d_ctr, ln.h_ctr_dev);
   MTSV_CUDA_TRY(cudaStreamSynchronize(st));
-  memcpy(out, h->h_ctr, sizeof(BatchCounters));
+  memcpy(out, ln.h_ctr, sizeof(BatchCounters));
   return 0;
+}
+
+// ---- ordered output: slices append to the batch result in slice order ----
+static int emit_acquire(mtsvgpu_index* h, Lane& ln) {
+  if (ln.has_turn) return 0;
+  std::unique_lock<std::mutex> lk(h->emit_mu);
+  h->emit_cv.wait(lk, [&] { return h->abort_rc != 0 || h->emit_turn == ln.slice; });
+  if (h->abort_rc != 0) return set_error(h->abort_rc, "%s", h->abort_msg.c_str());
+  ln.has_turn = true;
+  return 0;
+}
+static void emit_release(mtsvgpu_index* h, Lane& ln) {  // the slice is complete
+  std::lock_guard<std::mutex> lk(h->emit_mu);
+  if (ln.has_turn) h->emit_turn = ln.slice + 1;
+  ln.has_turn = false;
+  h->emit_cv.notify_all();
+}
+const char* last_error_cstr();
+static void emit_abort(mtsvgpu_index* h, int rc) {
+  std::lock_guard<std::mutex> lk(h->emit_mu);
+  if (h->abort_rc == 0) {
+    h->abort_rc = rc;
+    h->abort_msg = last_error_cstr();
+  }
+  h->emit_cv.notify_all();
 }
 
 // One device sub-batch: reads [read0, read0 + n_reads).  Returns 1 when the seed hits exceed the
 // in-flight cap and the caller must split the range (nothing was emitted in that case).
-static int run_sub_batch(mtsvgpu_index* h, const Params& p, const uint8_t* d_seqs,
+static int run_sub_batch(mtsvgpu_index* h, Lane& ln, const Params& p, const uint8_t* d_seqs,
                          const uint64_t* d_seq_off, uint64_t read0, uint32_t n_reads,
                          uint64_t slot_bound, uint64_t sub_bytes, uint64_t* out_total) {
   const uint64_t batch_read0 = 0;
   DeviceIndex& ix = h->ix;
-  BatchWorkspace& ws = h->ws;
-  cudaStream_t st = h->stream;
-  StageClock clk(h);
+  BatchWorkspace& ws = *ln.ws;  // scratch of this lane
+  BatchWorkspace& res = h->ws;  // batch results (shared, appended in slice order)
+  cudaStream_t st = ln.stream;
+  StageClock clk(h, ln);
   const uint32_t nq = n_reads * p.ns;
   ReadsView rv{d_seqs, d_seq_off, read0, n_reads};
   const uint64_t hit_cap = h->opts.max_batch_hits ? h->opts.max_batch_hits : (1ull << 27);
@@ -1394,7 +1422,7 @@ static int run_sub_batch(mtsvgpu_index* h, const Params& p, const uint8_t* d_seq
   MTSV_LAUNCH(count_slots_kernel, qgrid, 256, 0, st, rv, p, nq, slot_off, d_ctr);
   MTSV_TRY(exclusive_scan_u32(slot_off, slot_off, nq, ws.scan_tmp, (uint64_t*)&d_ctr->total_slots, st));
   clk.end();
-  MTSV_TRY(fetch_counters(h, d_ctr, &hc, st));
+  MTSV_TRY(fetch_counters(ln, d_ctr, &hc, st));
   if (hc.bad_offsets) return set_error(MTSVGPU_EINVAL, "seq_off is not monotone");
   if (hc.max_len > kMaxReadLen)
     return set_error(MTSVGPU_ELIMIT, "a read of %u bases exceeds this build's limit of %u", hc.max_len,
@@ -1405,7 +1433,7 @@ static int run_sub_batch(mtsvgpu_index* h, const Params& p, const uint8_t* d_seq
                      (unsigned long long)sub_bytes);
   const uint32_t n_slots = (uint32_t)hc.total_slots;
   const uint32_t min_len = ~hc.inv_min_len;  // == max_len: every read of the sub-batch has the same length
-  h->stats.n_seed_slots += n_slots;
+  ln.stats.n_seed_slots += n_slots;
   // (only now that the slot count is known to fit the buffers)
   clk.begin(ST_PREP);
   MTSV_LAUNCH(expand_slots_kernel, qgrid, 256, 0, st, slot_off, nq, ws.slot_q.as<uint32_t>());
@@ -1433,7 +1461,7 @@ static int run_sub_batch(mtsvgpu_index* h, const Params& p, const uint8_t* d_seq
   MTSV_TRY(exclusive_scan_u32(ws.q_nhits.as<uint32_t>(), ws.hit_off.as<uint32_t>(), nq, ws.scan_tmp,
                               (uint64_t*)&d_ctr->total_hits, st));
   clk.end();
-  MTSV_TRY(fetch_counters(h, d_ctr, &hc, st));
+  MTSV_TRY(fetch_counters(ln, d_ctr, &hc, st));
   if (hc.overflow)
     return set_error(MTSVGPU_ELIMIT, "a single read-strand produced more than %u seed hits; lower max_hits",
                      kMaxQueryHits);
@@ -1444,8 +1472,8 @@ static int run_sub_batch(mtsvgpu_index* h, const Params& p, const uint8_t* d_seq
     return 1;  // caller splits
   }
   const uint32_t n_hits = (uint32_t)hc.total_hits;
-  h->stats.n_seed_hits += n_hits;
-  for (int i = 0; i < 32; ++i) h->stats.rank_queries += hc.rank_steps[i];  // sectors touched by seed search
+  ln.stats.n_seed_hits += n_hits;
+  for (int i = 0; i < 32; ++i) ln.stats.rank_queries += hc.rank_steps[i];  // sectors touched by seed search
 
   uint64_t sub_out = 0;
   uint32_t n_cand = 0;
@@ -1481,9 +1509,9 @@ static int run_sub_batch(mtsvgpu_index* h, const Params& p, const uint8_t* d_seq
     MTSV_TRY(exclusive_scan_u32(ws.q_ncand.as<uint32_t>(), ws.cand_off.as<uint32_t>(), nq, ws.scan_tmp,
                                 (uint64_t*)&d_ctr->total_cands, st));
     clk.end();
-    MTSV_TRY(fetch_counters(h, d_ctr, &hc, st));
+    MTSV_TRY(fetch_counters(ln, d_ctr, &hc, st));
     n_cand = (uint32_t)hc.total_cands;
-    h->stats.n_candidates += n_cand;
+    ln.stats.n_candidates += n_cand;
   }
   if (n_cand) {
     MTSV_TRY(ws.cand_dense.reserve((size_t)n_cand * sizeof(CandRec)));
@@ -1543,28 +1571,33 @@ static int run_sub_batch(mtsvgpu_index* h, const Params& p, const uint8_t* d_seq
     MTSV_TRY(exclusive_scan_u32(ws.q_nout.as<uint32_t>(), ws.out_off.as<uint32_t>(), nq, ws.scan_tmp,
                                 (uint64_t*)&d_ctr->total_out, st));
     clk.end();
-    MTSV_TRY(fetch_counters(h, d_ctr, &hc, st));
+    MTSV_TRY(fetch_counters(ln, d_ctr, &hc, st));
     sub_out = hc.total_out;
-    for (int i = 0; i < 32; ++i) h->stats.window_bytes += hc.window_bytes[i];
+    for (int i = 0; i < 32; ++i) ln.stats.window_bytes += hc.window_bytes[i];
   } else {
     MTSV_CUDA_TRY(cudaMemsetAsync(ws.out_off.p, 0, qn * 4, st));
     MTSV_CUDA_TRY(cudaMemsetAsync(ws.cand_off.p, 0, qn * 4, st));
   }
-  // ---- append to the batch output ----
-  MTSV_TRY(grow_preserve(ws.out_hits, *out_total * sizeof(HitRec), (*out_total + sub_out + 1) * sizeof(HitRec),
+  // ---- append to the batch output: in slice order, after the other lane's previous append ----
+  MTSV_TRY(emit_acquire(h, ln));
+  Lane& other = h->lanes[&ln == &h->lanes[0] ? 1 : 0];
+  if (other.emit_event) MTSV_CUDA_TRY(cudaStreamWaitEvent(st, other.emit_event, 0));
+  MTSV_TRY(grow_preserve(res.out_hits, *out_total * sizeof(HitRec), (*out_total + sub_out + 1) * sizeof(HitRec),
                          st));
   clk.begin(ST_EMIT);
   MTSV_LAUNCH(gather_hits_kernel, (nq + 1 + 255) / 256, 256, 0, st, nq, p.ns, ws.cand_off.as<uint32_t>(),
-              ws.out_off.as<uint32_t>(), ws.hit_tmp.as<HitRec>(), ws.out_hits.as<HitRec>(), *out_total,
-              ws.out_hit_off.as<uint64_t>(), read0 - batch_read0);
+              ws.out_off.as<uint32_t>(), ws.hit_tmp.as<HitRec>(), res.out_hits.as<HitRec>(), *out_total,
+              res.out_hit_off.as<uint64_t>(), read0 - batch_read0);
   clk.end();
   MTSV_CUDA_TRY(cudaGetLastError());
+  if (!ln.emit_event) MTSV_CUDA_TRY(cudaEventCreateWithFlags(&ln.emit_event, cudaEventDisableTiming));
+  MTSV_CUDA_TRY(cudaEventRecord(ln.emit_event, st));
   // host API: start copying this sub-batch's results out while the next one computes
-  if (h->results_hook) MTSV_TRY(h->results_hook(h, *out_total, sub_out, read0 - batch_read0, n_reads));
+  if (h->results_hook) MTSV_TRY(h->results_hook(h, *out_total, sub_out, read0 - batch_read0, n_reads, st));
   clk.resolve();
   *out_total += sub_out;
-  h->stats.n_hits += sub_out;
-  h->stats.n_queries += nq;
+  ln.stats.n_hits += sub_out;
+  ln.stats.n_queries += nq;
   return 0;
 }
 
@@ -1584,23 +1617,36 @@ struct OffsetSource {
   }
 };
 
-static int run_range(mtsvgpu_index* h, const Params& p, const uint8_t* d_seqs, const uint64_t* d_seq_off,
+// One uploaded slice [read0, read0 + n_reads): processed in groups of ln.chunk_reads reads.  A group whose seed
+// hits overflow the in-flight cap (run_sub_batch returns 1, nothing emitted) is retried at half the size, and
+// the smaller size is kept for what follows (repetitive references: hundreds of hits per read).
+static int run_range(mtsvgpu_index* h, Lane& ln, const Params& p, const uint8_t* d_seqs, const uint64_t* d_seq_off,
                      const OffsetSource& offs, uint64_t read0, uint64_t n_reads, uint64_t off_lo,
                      uint64_t off_hi, uint64_t* out_total) {
-  // bound on seed slots from the byte count: slots(L) <= L/G + 1 per strand
   if (off_hi < off_lo) return set_error(MTSVGPU_EINVAL, "seq_off is not monotone");
-  uint64_t bytes = off_hi - off_lo;
-  uint64_t slot_bound = (bytes / p.G + n_reads) * p.ns + 1;
-  bool split = slot_bound > 0xfffffff0ull || n_reads * p.ns > 0x7ffffff0ull;
-  if (!split) {
-    int rc = run_sub_batch(h, p, d_seqs, d_seq_off, read0, (uint32_t)n_reads, slot_bound, bytes, out_total);
-    if (rc != 1) return rc;
+  uint64_t r = read0, off_r = off_lo;
+  const uint64_t r_end = read0 + n_reads;
+  while (r < r_end) {
+    uint64_t nr = std::min(r_end - r, std::max<uint64_t>(ln.chunk_reads, 1));
+    uint64_t off_e = off_hi;
+    if (r + nr < r_end) MTSV_TRY(offs.get(r + nr, &off_e));
+    if (off_e < off_r) return set_error(MTSVGPU_EINVAL, "seq_off is not monotone");
+    // bound on seed slots from the byte count: slots(L) <= L/G + 1 per strand
+    const uint64_t bytes = off_e - off_r;
+    const uint64_t slot_bound = (bytes / p.G + nr) * p.ns + 1;
+    const bool too_big = slot_bound > 0xfffffff0ull || nr * p.ns > 0x7ffffff0ull;
+    int rc = too_big ? 1 : run_sub_batch(h, ln, p, d_seqs, d_seq_off, r, (uint32_t)nr, slot_bound, bytes, out_total);
+    if (rc == 1) {
+      if (nr == 1) return set_error(MTSVGPU_ELIMIT, "a single read exceeds the device batch limits");
+      ln.chunk_reads = std::max<uint64_t>(1, nr / 2);
+      continue;
+    }
+    if (rc != 0) return rc;
+    ln.stats.n_sub_batches += 1;
+    r += nr;
+    off_r = off_e;
   }
-  if (n_reads == 1) return set_error(MTSVGPU_ELIMIT, "a single read exceeds the device batch limits");
-  uint64_t half = n_reads / 2, off_mid = 0;
-  MTSV_TRY(offs.get(read0 + half, &off_mid));
-  MTSV_TRY(run_range(h, p, d_seqs, d_seq_off, offs, read0, half, off_lo, off_mid, out_total));
-  return run_range(h, p, d_seqs, d_seq_off, offs, read0 + half, n_reads - half, off_mid, off_hi, out_total);
+  return 0;
 }
 
 int bin_batch_device(mtsvgpu_index* h, const uint8_t* d_seqs, const uint64_t* d_seq_off, uint64_t n_reads,
@@ -1616,17 +1662,17 @@ int bin_batch_device(mtsvgpu_index* h, const uint8_t* d_seqs, const uint64_t* d_
   BatchWorkspace& ws = h->ws;
   MTSV_TRY(ws.out_hit_off.reserve((n_reads + 1) * 8));
   uint64_t total = 0;
-  const uint64_t step = h->opts.batch_reads ? h->opts.batch_reads : (1u << 20);
+  const bool host_path = h->sub_batch_hook != nullptr;
+  const uint64_t step = h->opts.batch_reads ? h->opts.batch_reads : (host_path ? kDefaultStepHost : kDefaultStepDevice);
   if (n_reads == 0) {
     MTSV_CUDA_TRY(cudaMemsetAsync(ws.out_hit_off.p, 0, 8, st));
     MTSV_TRY(grow_preserve(ws.out_hits, 0, sizeof(HitRec), st));
   }
   // sub-batch boundaries of seq_off: one strided gather instead of copying 8 B per read
   // the host API (sub_batch_hook set) uploads slice by slice: short first slices fill the pipeline
-  const std::vector<uint64_t> rb = sub_batch_bounds(n_reads, step, h->sub_batch_hook != nullptr);
+  const std::vector<uint64_t> rb = sub_batch_bounds(n_reads, step, host_path);
   const uint64_t n_sub = rb.size() - 1;
   std::vector<uint64_t> bounds(n_sub + 1, 0);
-  OffsetSource offs{h_seq_off_or_null, d_seq_off, st};
   if (n_reads) {
     if (h_seq_off_or_null) {
       for (uint64_t i = 0; i <= n_sub; ++i) bounds[i] = h_seq_off_or_null[rb[i]];
@@ -1637,9 +1683,84 @@ int bin_batch_device(mtsvgpu_index* h, const uint8_t* d_seqs, const uint64_t* d_
       MTSV_CUDA_TRY(cudaStreamSynchronize(st));
     }
   }
-  for (uint64_t i = 0; i < n_sub; ++i) {
-    if (h->sub_batch_hook) MTSV_TRY(h->sub_batch_hook(h, i));
-    MTSV_TRY(run_range(h, p, d_seqs, d_seq_off, offs, rb[i], rb[i + 1] - rb[i], bounds[i], bounds[i + 1], &total));
+  // ---- lanes: with host input the slices alternate between two lanes (the sync bubbles and kernel tails of
+  // one slice are filled by the other: ~10 % on small slices, which is what keeps the compute ahead of the
+  // upload); device-resident input uses large slices on one lane, so that the per-stage event timers of the
+  // profiling mode measure kernels that run alone.  MTSV_B200_LANES=1|2 overrides. ----
+  const char* lanes_env = getenv("MTSV_B200_LANES");
+  int want_lanes = host_path ? 2 : 1;
+  if (lanes_env && (atoi(lanes_env) == 1 || atoi(lanes_env) == 2)) want_lanes = atoi(lanes_env);
+  const int n_lanes = n_sub >= 2 ? want_lanes : 1;
+  h->lanes[0].stream = st;
+  h->lanes[0].ws = &h->ws;
+  h->lanes[1].ws = &h->ws1;
+  if (n_lanes == 2) {
+    if (!h->lane1_stream) MTSV_CUDA_TRY(cudaStreamCreateWithFlags(&h->lane1_stream, cudaStreamNonBlocking));
+    if (!h->fork_event) MTSV_CUDA_TRY(cudaEventCreateWithFlags(&h->fork_event, cudaEventDisableTiming));
+    if (!h->join_event) MTSV_CUDA_TRY(cudaEventCreateWithFlags(&h->join_event, cudaEventDisableTiming));
+    h->lanes[1].stream = h->lane1_stream;
+    // lane 1 starts after whatever the caller queued on the handle's stream (its inputs)
+    MTSV_CUDA_TRY(cudaEventRecord(h->fork_event, st));
+    MTSV_CUDA_TRY(cudaStreamWaitEvent(h->lane1_stream, h->fork_event, 0));
+  }
+  h->emit_turn = 0;
+  h->abort_rc = 0;
+  h->abort_msg.clear();
+  for (Lane& ln : h->lanes) {
+    ln.has_turn = false;
+    ln.chunk_reads = step;
+    memset(&ln.stats, 0, sizeof ln.stats);
+  }
+  const int device = h->ix.device;
+  auto lane_main = [&](int li) {
+    Lane& ln = h->lanes[li];
+    if (li != 0) cudaSetDevice(device);
+    OffsetSource offs{h_seq_off_or_null, d_seq_off, ln.stream};
+    for (uint64_t i = (uint64_t)li; i < n_sub; i += (uint64_t)n_lanes) {
+      {
+        std::lock_guard<std::mutex> lk(h->emit_mu);
+        if (h->abort_rc != 0) return;
+      }
+      ln.slice = i;
+      int rc = 0;
+      if (h->sub_batch_hook) rc = h->sub_batch_hook(h, i, ln.stream);
+      if (rc == 0)
+        rc = run_range(h, ln, p, d_seqs, d_seq_off, offs, rb[i], rb[i + 1] - rb[i], bounds[i], bounds[i + 1], &total);
+      if (rc != 0) {
+        emit_abort(h, rc);
+        return;
+      }
+      emit_release(h, ln);
+    }
+  };
+  if (n_lanes == 2) {
+    std::thread helper(lane_main, 1);
+    lane_main(0);
+    helper.join();
+    // everything lane 1 did is ordered before what follows on the handle's stream
+    MTSV_CUDA_TRY(cudaEventRecord(h->join_event, h->lane1_stream));
+    MTSV_CUDA_TRY(cudaStreamWaitEvent(st, h->join_event, 0));
+  } else {
+    lane_main(0);
+  }
+  for (Lane& ln : h->lanes) {  // merge the per-lane statistics
+    for (int i = 0; i < MTSVGPU_N_STAGES; ++i) {
+      h->stats.ms[i] += ln.stats.ms[i];
+      h->stats.launches[i] += ln.stats.launches[i];
+    }
+    h->stats.n_queries += ln.stats.n_queries;
+    h->stats.n_seed_slots += ln.stats.n_seed_slots;
+    h->stats.n_seed_hits += ln.stats.n_seed_hits;
+    h->stats.n_candidates += ln.stats.n_candidates;
+    h->stats.n_hits += ln.stats.n_hits;
+    h->stats.window_bytes += ln.stats.window_bytes;
+    h->stats.rank_queries += ln.stats.rank_queries;
+    h->stats.n_sub_batches += ln.stats.n_sub_batches;
+  }
+  if (h->abort_rc != 0) {
+    cudaStreamSynchronize(st);
+    if (h->lane1_stream) cudaStreamSynchronize(h->lane1_stream);
+    return set_error(h->abort_rc, "%s", h->abort_msg.c_str());
   }
   MTSV_CUDA_TRY(cudaStreamSynchronize(st));
   if (d_hits) *d_hits = reinterpret_cast<const mtsvgpu_hit*>(ws.out_hits.p);

@@ -90,8 +90,25 @@ static int ensure_pinned(void** p, size_t* cap, size_t bytes) {
   return 0;
 }
 
-static int wait_for_sub_batch_input(mtsvgpu_index* ix, uint64_t i) {
-  if (i < ix->in_events.size()) MTSV_CUDA_TRY(cudaStreamWaitEvent(ix->stream, ix->in_events[i], 0));
+// MTSV_B200_TRACE=1: per-slice timeline of the host API (when each slice landed, when its compute started)
+static std::vector<cudaEvent_t> g_trace_landed, g_trace_started;
+static cudaEvent_t g_trace_t0 = nullptr;
+static bool trace_on() {
+  static const bool t = getenv("MTSV_B200_TRACE") != nullptr;
+  return t;
+}
+static cudaEvent_t trace_event(std::vector<cudaEvent_t>& pool, size_t i) {
+  while (pool.size() <= i) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    pool.push_back(e);
+  }
+  return pool[i];
+}
+
+static int wait_for_sub_batch_input(mtsvgpu_index* ix, uint64_t i, cudaStream_t st) {
+  if (i < ix->in_events.size()) MTSV_CUDA_TRY(cudaStreamWaitEvent(st, ix->in_events[i], 0));
+  if (trace_on()) cudaEventRecord(g_trace_started[i], st);  // (pre-created by the caller: two lanes call this)
   return 0;
 }
 
@@ -99,7 +116,7 @@ static int wait_for_sub_batch_input(mtsvgpu_index* ix, uint64_t i) {
 // sub-batch computes.  Only used when the pinned buffers are known to be large enough (they keep the size
 // of earlier batches); otherwise everything is copied at the end.
 static int copy_results_slice(mtsvgpu_index* ix, uint64_t first_hit, uint64_t n_hits, uint64_t first_read,
-                              uint64_t n_reads) {
+                              uint64_t n_reads, cudaStream_t st) {
   if (!ix->out_overlap_ok) return 0;
   if ((first_hit + n_hits) * sizeof(mtsvgpu_hit) > ix->pin_hits_cap ||
       (first_read + n_reads + 1) * sizeof(uint64_t) > ix->pin_off_cap || first_hit != ix->out_copied_hits ||
@@ -107,7 +124,7 @@ static int copy_results_slice(mtsvgpu_index* ix, uint64_t first_hit, uint64_t n_
     ix->out_overlap_ok = false;  // does not fit / unexpected order: the caller copies everything at the end
     return 0;
   }
-  MTSV_CUDA_TRY(cudaEventRecord(ix->out_event, ix->stream));
+  MTSV_CUDA_TRY(cudaEventRecord(ix->out_event, st));
   MTSV_CUDA_TRY(cudaStreamWaitEvent(ix->copy_out_stream, ix->out_event, 0));
   const mtsvgpu_hit* d_hits = ix->ws.out_hits.as<mtsvgpu_hit>();
   const uint64_t* d_off = ix->ws.out_hit_off.as<uint64_t>();
@@ -151,13 +168,18 @@ static int bin_batch_host(mtsvgpu_index* ix, const uint8_t* seqs, const uint64_t
     offs = rebased.data();
   }
   // ---- H2D, pipelined per device sub-batch ----
-  const uint64_t step = ix->opts.batch_reads ? ix->opts.batch_reads : (1u << 20);
+  const uint64_t step = ix->opts.batch_reads ? ix->opts.batch_reads : kDefaultStepHost;
   const std::vector<uint64_t> rb = sub_batch_bounds(n_reads, step, true);
   const uint64_t n_sub = n_reads ? rb.size() - 1 : 0;
   while (ix->in_events.size() < n_sub) {
     cudaEvent_t e;
     MTSV_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     ix->in_events.push_back(e);
+  }
+  if (trace) {
+    if (!g_trace_t0) cudaEventCreate(&g_trace_t0);
+    cudaEventRecord(g_trace_t0, cin);
+    if (n_sub) trace_event(g_trace_started, n_sub - 1);
   }
   for (uint64_t i = 0; i < n_sub; ++i) {
     uint64_t r0 = rb[i], r1 = rb[i + 1];
@@ -171,6 +193,7 @@ static int bin_batch_host(mtsvgpu_index* ix, const uint8_t* seqs, const uint64_t
     if (nb)
       MTSV_CUDA_TRY(cudaMemcpyAsync(ws.d_seqs.as<uint8_t>() + b0, seqs + base + b0, nb, cudaMemcpyHostToDevice, cin));
     MTSV_CUDA_TRY(cudaEventRecord(ix->in_events[i], cin));
+    if (trace) cudaEventRecord(trace_event(g_trace_landed, i), cin);
   }
   if (n_sub == 0) MTSV_CUDA_TRY(cudaMemcpyAsync(ws.d_seq_off.p, offs, 8, cudaMemcpyHostToDevice, cin));
   const double t_enq = trace ? now() : 0;
@@ -235,6 +258,17 @@ static int bin_batch_host(mtsvgpu_index* ix, const uint8_t* seqs, const uint64_t
   *hits = h_hits;
   *hit_off = h_off;
   if (n_hits_out) *n_hits_out = n_hits;
+  if (trace) {
+    cudaDeviceSynchronize();
+    fprintf(stderr, "[mtsv_b200 trace] slice: reads, landed at ms, compute started at ms\n");
+    for (uint64_t i = 0; i < n_sub && i < g_trace_started.size(); ++i) {
+      float a = 0, b = 0;
+      cudaEventElapsedTime(&a, g_trace_t0, g_trace_landed[i]);
+      cudaEventElapsedTime(&b, g_trace_t0, g_trace_started[i]);
+      fprintf(stderr, "[mtsv_b200 trace]   %2llu: %8llu  %7.2f  %7.2f\n", (unsigned long long)i,
+              (unsigned long long)(rb[i + 1] - rb[i]), a, b);
+    }
+  }
   if (trace)
     fprintf(stderr, "[mtsv_b200 trace] bin_batch_host: enqueue H2D %.2f ms, compute %.2f ms, tail (D2H rest) %.2f ms, "
                     "overlapped D2H %s\n", t_enq - t_begin, t_comp - t_enq, now() - t_comp,

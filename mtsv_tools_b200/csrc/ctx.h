@@ -7,6 +7,8 @@
 
 #include <algorithm>
 #include <atomic>
+#include <condition_variable>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -141,6 +143,25 @@ struct BatchWorkspace {
   void release_all();
 };
 
+// One in-flight device sub-batch.  A batch call alternates its slices between two lanes (own stream, own
+// scratch, own host thread): while one lane's host thread waits for the scalars of a stage, the other lane's
+// kernels keep the device busy, and the tails of memory-bound and ALU-bound kernels of different slices overlap.
+struct Lane {
+  cudaStream_t stream = nullptr;     // lane 0: the handle's stream; lane 1: a private non-blocking stream
+  BatchWorkspace* ws = nullptr;      // scratch of the lane (results and staged inputs live in the handle's ws)
+  BatchCounters* h_ctr = nullptr;    // page-locked, mapped: sub-batch scalars published by the device
+  BatchCounters* h_ctr_dev = nullptr;
+  cudaEvent_t emit_event = nullptr;  // recorded after each append to the batch output
+  bool has_turn = false;             // holds the output turnstile for its current slice
+  uint64_t slice = 0;                // index of the slice being processed
+  uint64_t chunk_reads = 0;          // reads per launch group; halves when a group overflows the seed-hit cap
+  mtsvgpu_batch_stats stats{};
+  // event pool for profiling
+  std::vector<cudaEvent_t> ev_pool;
+  std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> ev_used;
+  size_t ev_next = 0;
+};
+
 }  // namespace mtsv
 
 struct mtsvgpu_index {
@@ -149,16 +170,25 @@ struct mtsvgpu_index {
   cudaStream_t own_stream = nullptr;
   cudaStream_t stream = nullptr;
   bool profiling = false;
-  mtsv::BatchWorkspace ws;
-  mtsv::BatchCounters* h_ctr = nullptr;      // page-locked, mapped: sub-batch scalars published by the device
-  mtsv::BatchCounters* h_ctr_dev = nullptr;  // its device alias
+  mtsv::BatchWorkspace ws;   // lane 0 scratch + the batch results + the staged inputs of the host API
+  mtsv::BatchWorkspace ws1;  // lane 1 scratch
+  mtsv::Lane lanes[2];
+  cudaStream_t lane1_stream = nullptr;
+  cudaEvent_t fork_event = nullptr, join_event = nullptr;
+  // slices append to the batch output in order: a turnstile over the slice index
+  std::mutex emit_mu;
+  std::condition_variable emit_cv;
+  uint64_t emit_turn = 0;
+  int abort_rc = 0;
+  std::string abort_msg;
   mtsvgpu_batch_stats stats{};
   // host API: copy streams, per-sub-batch "input landed" events, pinned result buffers
   cudaStream_t copy_in_stream = nullptr;
   std::vector<cudaEvent_t> in_events;
-  int (*sub_batch_hook)(mtsvgpu_index*, uint64_t) = nullptr;  // called before each sub-batch
-  // called after each sub-batch's results are enqueued: (first hit, #hits, first read, #reads)
-  int (*results_hook)(mtsvgpu_index*, uint64_t, uint64_t, uint64_t, uint64_t) = nullptr;
+  // called before each slice on the stream that will compute it
+  int (*sub_batch_hook)(mtsvgpu_index*, uint64_t, cudaStream_t) = nullptr;
+  // called after each sub-batch's results are enqueued on `stream`: (first hit, #hits, first read, #reads, stream)
+  int (*results_hook)(mtsvgpu_index*, uint64_t, uint64_t, uint64_t, uint64_t, cudaStream_t) = nullptr;
   cudaStream_t copy_out_stream = nullptr;
   cudaEvent_t out_event = nullptr;
   uint64_t out_copied_hits = 0, out_copied_reads = 0;  // prefix already on its way to the pinned buffers
@@ -167,28 +197,39 @@ struct mtsvgpu_index {
   size_t pin_hits_cap = 0;
   void* pin_off = nullptr;
   size_t pin_off_cap = 0;
-  // event pool for profiling
-  std::vector<cudaEvent_t> ev_pool;
-  std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> ev_used;
-  size_t ev_next = 0;
 };
 
 namespace mtsv {
-// Read boundaries of the device sub-batches of one batch call.  The host API uploads slice by slice while
-// earlier slices compute, so the first slices are short (step/8, step/4, step/2) to fill the pipeline quickly;
-// the rest have `step` reads.  Shared by capi.cu (uploads) and binner.cu (compute) so that they agree.
+// Read boundaries of the device sub-batches of one batch call.  Device-resident input: equal slices of `step`
+// reads.  Host input (ramp): the slices are uploaded one by one while earlier ones compute, so the call lasts
+// about (upload of everything) + (upload of the first slice) + (compute of the last slice): the first slices
+// grow geometrically from step/16 and the last ones shrink to step/8.  Shared by capi.cu (uploads) and
+// binner.cu (compute) so that they agree.
+constexpr uint64_t kDefaultStepDevice = 1ull << 22, kDefaultStepHost = 1ull << 20;
 inline std::vector<uint64_t> sub_batch_bounds(uint64_t n_reads, uint64_t step, bool ramp) {
   std::vector<uint64_t> b{0};
-  uint64_t r = 0;
-  if (ramp && n_reads > 2 * step && step >= 64) {
-    for (uint64_t d = 8; d >= 2; d /= 2) {
-      r += step / d;
-      b.push_back(r);
-    }
+  if (step == 0) step = 1;
+  std::vector<uint64_t> up, down;
+  if (ramp && step >= 1024) {
+    up = {step / 16, step / 8, step / 4, step / 2};
+    down = {step / 2, step / 4, step / 8};
   }
-  while (r < n_reads) {
-    r = std::min(n_reads, r + step);
-    b.push_back(r);
+  uint64_t edge = 0;
+  for (uint64_t x : up) edge += x;
+  for (uint64_t x : down) edge += x;
+  uint64_t r = 0;
+  if (!up.empty() && n_reads > edge + step / 2) {
+    for (uint64_t x : up) b.push_back(r += x);
+    const uint64_t middle = n_reads - edge, n_full = (middle + step - 1) / step;
+    for (uint64_t i = 1; i <= n_full; ++i) b.push_back(r + middle * i / n_full);
+    r += middle;
+    for (uint64_t x : down) b.push_back(r += x);
+  } else {
+    for (uint64_t x : up) {  // short batch: geometric slices until it is used up
+      if (r + x >= n_reads) break;
+      b.push_back(r += x);
+    }
+    while (r < n_reads) b.push_back(r = std::min(n_reads, r + step));
   }
   return b;
 }

@@ -261,14 +261,21 @@ void index_destroy(mtsvgpu_index* h) {
   cudaFree(d.bin_tax);
   cudaFree(d.bin_gi);
   h->ws.release_all();
-  if (h->h_ctr) cudaFreeHost(h->h_ctr);
+  h->ws1.release_all();
+  for (Lane& ln : h->lanes) {
+    if (ln.h_ctr) cudaFreeHost(ln.h_ctr);
+    if (ln.emit_event) cudaEventDestroy(ln.emit_event);
+    for (cudaEvent_t e : ln.ev_pool) cudaEventDestroy(e);
+  }
+  if (h->lane1_stream) cudaStreamDestroy(h->lane1_stream);
+  if (h->fork_event) cudaEventDestroy(h->fork_event);
+  if (h->join_event) cudaEventDestroy(h->join_event);
   if (h->pin_hits) cudaFreeHost(h->pin_hits);
   if (h->pin_off) cudaFreeHost(h->pin_off);
   for (cudaEvent_t e : h->in_events) cudaEventDestroy(e);
   if (h->copy_in_stream) cudaStreamDestroy(h->copy_in_stream);
   if (h->copy_out_stream) cudaStreamDestroy(h->copy_out_stream);
   if (h->out_event) cudaEventDestroy(h->out_event);
-  for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;
 }
