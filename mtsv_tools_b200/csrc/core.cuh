@@ -8,6 +8,9 @@
 #pragma once
 #include <stdint.h>
 
+#include <algorithm>
+#include <vector>
+
 #if defined(__CUDACC__)
 #define MTSV_HD __host__ __device__ __forceinline__
 #else
@@ -1087,6 +1090,43 @@ MTSV_HD uint32_t select_item(const BinsView& bv, const Params& p, const CandRec*
     if (p.max_assignments >= 0 && (uint64_t)n_out >= (uint64_t)p.max_assignments) break;  // :421-425
   }
   return n_out;
+}
+
+// ---------------------------------------------------------------------------------------------
+// host-side schedule (no device code; here so that tests/emul can check it)
+// ---------------------------------------------------------------------------------------------
+// Read boundaries of the device sub-batches of one batch call.  Device-resident input: equal slices of `step`
+// reads.  Host input (ramp): the slices are uploaded one by one while earlier ones compute, so the call lasts
+// about (upload of everything) + (upload of the first slice) + (compute of the last slice): the first slices
+// grow geometrically from step/16 and the last ones shrink to step/8.  Shared by capi.cu (uploads) and
+// binner.cu (compute) so that they agree.
+constexpr uint64_t kDefaultStepDevice = 1ull << 22, kDefaultStepHost = 1ull << 20;
+inline std::vector<uint64_t> sub_batch_bounds(uint64_t n_reads, uint64_t step, bool ramp) {
+  std::vector<uint64_t> b{0};
+  if (step == 0) step = 1;
+  std::vector<uint64_t> up, down;
+  if (ramp && step >= 1024) {
+    up = {step / 16, step / 8, step / 4, step / 2};
+    down = {step / 2, step / 4, step / 8};
+  }
+  uint64_t edge = 0;
+  for (uint64_t x : up) edge += x;
+  for (uint64_t x : down) edge += x;
+  uint64_t r = 0;
+  if (!up.empty() && n_reads > edge + step / 2) {
+    for (uint64_t x : up) b.push_back(r += x);
+    const uint64_t middle = n_reads - edge, n_full = (middle + step - 1) / step;
+    for (uint64_t i = 1; i <= n_full; ++i) b.push_back(r + middle * i / n_full);
+    r += middle;
+    for (uint64_t x : down) b.push_back(r += x);
+  } else {
+    for (uint64_t x : up) {  // short batch: geometric slices until it is used up
+      if (r + x >= n_reads) break;
+      b.push_back(r += x);
+    }
+    while (r < n_reads) b.push_back(r = std::min(n_reads, r + step));
+  }
+  return b;
 }
 
 }  // namespace mtsv

@@ -435,6 +435,13 @@ int emul_bin_reads(void* p, const uint8_t* seqs, const uint64_t* seq_off, uint64
   return 0;
 }
 
+// slice schedule of one batch call (core.cuh::sub_batch_bounds); returns the number of boundaries
+uint32_t emul_sub_batch_bounds(uint64_t n_reads, uint64_t step, int ramp, uint64_t* out, uint32_t cap) {
+  std::vector<uint64_t> b = sub_batch_bounds(n_reads, step, ramp != 0);
+  for (size_t i = 0; i < b.size() && i < cap; ++i) out[i] = b[i];
+  return (uint32_t)b.size();
+}
+
 void emul_free(void* p) { free(p); }
 
 void emul_myers_counters(unsigned long long* blocks, unsigned long long* cols, int reset) {

@@ -65,6 +65,8 @@ def lib():
     L.emul_edit_distance_end.restype = C.c_uint32
     L.emul_edit_distance_end.argtypes = [C.c_char_p, C.c_uint32, C.c_char_p, C.c_uint32, C.c_uint32,
                                          C.POINTER(C.c_uint32)]
+    L.emul_sub_batch_bounds.restype = C.c_uint32
+    L.emul_sub_batch_bounds.argtypes = [C.c_uint64, C.c_uint64, C.c_int, C.POINTER(C.c_uint64), C.c_uint32]
     L.emul_ssw_accepts.restype = C.c_uint32
     L.emul_ssw_accepts.argtypes = [C.c_char_p, C.c_uint32, C.c_char_p, C.c_uint32, C.c_uint32, C.c_uint32,
                                    C.c_uint32, C.c_int]
@@ -162,3 +164,10 @@ def edit_distance_end(pat, txt, k):
     ec = C.c_uint32()
     e = lib().emul_edit_distance_end(bytes(pat), len(pat), bytes(txt), len(txt), k, C.byref(ec))
     return int(e), ec.value
+
+
+def sub_batch_bounds(n_reads, step, ramp):
+    """Read boundaries of the device slices of one batch call (core.cuh::sub_batch_bounds)."""
+    buf = (C.c_uint64 * 4096)()
+    n = lib().emul_sub_batch_bounds(n_reads, step, int(ramp), buf, 4096)
+    return [int(buf[i]) for i in range(min(n, 4096))]

@@ -281,6 +281,27 @@ def test_pipeline_reads_of_254_bases_and_more(oracle, emul, small_ref, small_ind
     assert n_changed > 0, "no read exercised the 16-bit kernel's deviation; make the cases harder"
 
 
+def test_slice_schedule(emul):
+    """The slices of one batch call: cover the reads exactly once, in order, never longer than the step;
+    with host input short first and last slices (the call lasts upload + first upload + last compute)."""
+    rng = random.Random(3)
+    for _ in range(2000):
+        n = rng.choice([0, 1, 2, rng.randint(0, 5000), rng.randint(0, 3 << 20), rng.randint(0, 40 << 20)])
+        step = rng.choice([1, 7, 97, 1 << 10, 1 << 16, 1 << 20, 1 << 22, rng.randint(1, 1 << 22)])
+        if n // step > 3000:
+            continue
+        for ramp in (False, True):
+            b = emul.sub_batch_bounds(n, step, ramp)
+            assert b[0] == 0 and b[-1] == n
+            sizes = [y - x for x, y in zip(b, b[1:])]
+            assert all(0 < s <= step for s in sizes), (n, step, ramp, sizes[:8])
+            if not ramp:
+                assert all(s == step for s in sizes[:-1])
+    b = emul.sub_batch_bounds(10_000_000, 1 << 20, True)
+    sizes = [y - x for x, y in zip(b, b[1:])]
+    assert sizes[0] == 1 << 16 and sizes[-1] == 1 << 17 and max(sizes) <= 1 << 20
+
+
 CASES = [
     ("defaults dense+ktab", {}, 1, 8),
     ("sa_rate 4, no table", {}, 4, 0),
