@@ -164,15 +164,28 @@ __global__ void __launch_bounds__(256) seed_search_kernel(FmView fm, KtabView kt
                                                           uint32_t n_slots,
                                                           uint32_t* __restrict__ slot_lo,
                                                           uint32_t* __restrict__ slot_cnt,
-                                                          BatchCounters* __restrict__ ctr, int count_ranks) {
+                                                          BatchCounters* __restrict__ ctr, int count_ranks,
+                                                          uint32_t uni_len, uint32_t uni_spq) {
+  // uni_spq != 0: every read of the sub-batch has uni_len bases, so a slot's query, seed offset and plane words
+  // follow from its index alone (no slot_q / slot_off / seq_off loads in front of the index accesses)
   uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
   uint32_t steps = 0;
   if (s < n_slots) {
-    uint32_t q = slot_q[s];
-    uint32_t j = s - slot_off[q];
-    uint32_t L = query_len(rv, p.ns, q);
+    uint32_t q, j, L, woff;
+    if (uni_spq) {
+      q = s / uni_spq;
+      j = s - q * uni_spq;
+      L = uni_len;
+      const uint32_t r = q / p.ns;
+      woff = (uint32_t)(((uint64_t)r * L) >> 6) + r + (q % p.ns) * ev.total_words;
+    } else {
+      q = slot_q[s];
+      j = s - slot_off[q];
+      L = query_len(rv, p.ns, q);
+      woff = query_word_off(rv, ev, p.ns, q);
+    }
     uint32_t lo, cnt;
-    seed_search_item(fm, kt, ev.words + query_word_off(rv, ev, p.ns, q), L, p.S, j * p.G, &lo, &cnt, &steps);
+    seed_search_item(fm, kt, ev.words + woff, L, p.S, j * p.G, &lo, &cnt, &steps);
     slot_lo[s] = lo;
     slot_cnt[s] = cnt;
   }
@@ -200,44 +213,57 @@ __global__ void seed_select_kernel(ReadsView rv, EncView ev, Params p, const uin
   if (ovf) atomicExch(&ctr->overflow, 1u);
 }
 
-// locate: one lane per slot; intervals with more than a few rows are spread over the warp so that
-// consecutive SA entries are read coalesced and long LF walks are shared.
+// locate: one lane per query, walking its seed slots (most slots carry no hit, and with the k-mer table's
+// direct entries most hits already are text positions: a lane per slot would spend its time finding that
+// out).  Intervals with more than a few rows are spread over the warp so that consecutive SA entries are read
+// coalesced and long LF walks are shared.
 __global__ void __launch_bounds__(256) locate_kernel(FmView fm, SaView sv, Params p,
-                                                     const uint32_t* __restrict__ slot_off,
-                                                     const uint32_t* __restrict__ slot_q, uint32_t n_slots,
+                                                     const uint32_t* __restrict__ slot_off, uint32_t nq,
                                                      const uint32_t* __restrict__ slot_lo,
                                                      const uint32_t* __restrict__ slot_cnt,
                                                      const uint32_t* __restrict__ slot_hoff,
                                                      const uint32_t* __restrict__ hit_off,
+                                                     const uint32_t* __restrict__ q_nhits,
                                                      uint64_t* __restrict__ hit_keys) {
-  uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
   const unsigned lane = threadIdx.x & 31;
-  uint32_t cnt = 0, lo = 0, dst = 0, qoff = 0;
-  if (s < n_slots) {
-    uint32_t ho = slot_hoff[s];
-    if (ho != kUnused) {
-      uint32_t q = slot_q[s];
-      cnt = slot_cnt[s];
-      lo = slot_lo[s];
-      dst = hit_off[q] + ho;
-      qoff = (s - slot_off[q]) * p.G;
-    }
+  uint32_t b = 0, n_slots = 0, base = 0;
+  if (q < nq && q_nhits[q] != 0) {
+    b = slot_off[q];
+    n_slots = slot_off[q + 1] - b;
+    base = hit_off[q];
   }
+  const uint32_t n_max = __reduce_max_sync(0xffffffffu, n_slots);
   constexpr uint32_t kSolo = 4;
-  if (cnt <= kSolo) {
-    for (uint32_t j = 0; j < cnt; ++j)
-      hit_keys[dst + j] = make_hit_key(fm_locate(fm, sv, lo + j, nullptr), qoff);
-  }
-  unsigned big = __ballot_sync(0xffffffffu, cnt > kSolo);
-  while (big) {
-    int src = __ffs(big) - 1;
-    big &= big - 1;
-    uint32_t c = __shfl_sync(0xffffffffu, cnt, src);
-    uint32_t l = __shfl_sync(0xffffffffu, lo, src);
-    uint32_t d = __shfl_sync(0xffffffffu, dst, src);
-    uint32_t o = __shfl_sync(0xffffffffu, qoff, src);
-    for (uint32_t j = lane; j < c; j += 32)
-      hit_keys[d + j] = make_hit_key(fm_locate(fm, sv, l + j, nullptr), o);
+  for (uint32_t j = 0; j < n_max; ++j) {
+    uint32_t cnt = 0, lo = 0, dst = 0;
+    const uint32_t qoff = j * p.G;
+    if (j < n_slots) {
+      const uint32_t ho = slot_hoff[b + j];
+      if (ho != kUnused) {
+        cnt = slot_cnt[b + j];
+        lo = slot_lo[b + j];
+        dst = base + ho;
+      }
+    }
+    if (cnt & kDirectHit) {  // the k-mer table already gave the text position (core.cuh, direct entries)
+      hit_keys[dst] = make_hit_key(lo, qoff);
+      cnt = 0;
+    }
+    if (cnt <= kSolo) {
+      for (uint32_t r = 0; r < cnt; ++r)
+        hit_keys[dst + r] = make_hit_key(fm_locate(fm, sv, lo + r, nullptr), qoff);
+    }
+    unsigned big = __ballot_sync(0xffffffffu, cnt > kSolo);
+    while (big) {
+      int src = __ffs(big) - 1;
+      big &= big - 1;
+      uint32_t c = __shfl_sync(0xffffffffu, cnt, src);
+      uint32_t l = __shfl_sync(0xffffffffu, lo, src);
+      uint32_t d = __shfl_sync(0xffffffffu, dst, src);
+      for (uint32_t r = lane; r < c; r += 32)
+        hit_keys[d + r] = make_hit_key(fm_locate(fm, sv, l + r, nullptr), qoff);
+    }
   }
 }
 
@@ -1436,7 +1462,9 @@ static int run_sub_batch(mtsvgpu_index* h, Lane& ln, const Params& p, const uint
   ln.stats.n_seed_slots += n_slots;
   // (only now that the slot count is known to fit the buffers)
   clk.begin(ST_PREP);
-  MTSV_LAUNCH(expand_slots_kernel, qgrid, 256, 0, st, slot_off, nq, ws.slot_q.as<uint32_t>());
+  // all reads of one length: slots are addressed arithmetically, no slot -> query map needed
+  const uint32_t uni_spq = (min_len == hc.max_len && nq && n_slots % nq == 0) ? n_slots / nq : 0;
+  if (!uni_spq) MTSV_LAUNCH(expand_slots_kernel, qgrid, 256, 0, st, slot_off, nq, ws.slot_q.as<uint32_t>());
   MTSV_LAUNCH(encode_reads_kernel, (n_reads + 127) / 128, 128, 0, st, rv, ws.enc.as<ReadWord>());
   if (p.ns == 2) {
     const uint32_t w_max = hc.max_len ? (hc.max_len + 63) / 64 : 1;
@@ -1451,7 +1479,7 @@ static int run_sub_batch(mtsvgpu_index* h, Lane& ln, const Params& p, const uint
   if (n_slots)
     MTSV_LAUNCH(seed_search_kernel, (n_slots + 255) / 256, 256, 0, st, ix.fm_view(), ix.ktab_view(), rv, ev, p,
                 slot_off, ws.slot_q.as<uint32_t>(), n_slots, ws.slot_lo.as<uint32_t>(),
-                ws.slot_cnt.as<uint32_t>(), d_ctr, h->profiling ? 1 : 0);
+                ws.slot_cnt.as<uint32_t>(), d_ctr, h->profiling ? 1 : 0, hc.max_len, uni_spq);
   clk.end();
 
   // ---- replay the seed rule, hit offsets ----
@@ -1482,9 +1510,9 @@ static int run_sub_batch(mtsvgpu_index* h, Lane& ln, const Params& p, const uint
     MTSV_TRY(ws.cand_sparse.reserve((size_t)n_hits * sizeof(CandRec)));
     // ---- locate ----
     clk.begin(ST_LOCATE);
-    MTSV_LAUNCH(locate_kernel, (n_slots + 255) / 256, 256, 0, st, ix.fm_view(), ix.sa_view(), p, slot_off,
-                ws.slot_q.as<uint32_t>(), n_slots, ws.slot_lo.as<uint32_t>(), ws.slot_cnt.as<uint32_t>(),
-                ws.slot_hoff.as<uint32_t>(), ws.hit_off.as<uint32_t>(), ws.hit_keys.as<uint64_t>());
+    MTSV_LAUNCH(locate_kernel, qgrid, 256, 0, st, ix.fm_view(), ix.sa_view(), p, slot_off, nq,
+                ws.slot_lo.as<uint32_t>(), ws.slot_cnt.as<uint32_t>(), ws.slot_hoff.as<uint32_t>(),
+                ws.hit_off.as<uint32_t>(), ws.q_nhits.as<uint32_t>(), ws.hit_keys.as<uint64_t>());
     clk.end();
     // ---- sort hits per query ----
     clk.begin(ST_SORT);
@@ -1778,7 +1806,12 @@ __global__ void bs_patterns_kernel(FmView fm, KtabView kt, ReadsView pv, EncView
   if (i >= n) return;
   // a pattern is a forward-strand "read" whose single seed covers it entirely
   uint32_t lo, cnt;
-  seed_search_item(fm, kt, ev.words + query_word_off(pv, ev, 1, (uint32_t)i), len, len, 0, &lo, &cnt, nullptr);
+  const ReadWord* qw = ev.words + query_word_off(pv, ev, 1, (uint32_t)i);
+  seed_search_item(fm, kt, qw, len, len, 0, &lo, &cnt, nullptr);
+  if (cnt & kDirectHit) {  // this entry point reports SA rows: search again without the table
+    KtabView none{nullptr, 0, 0, nullptr};
+    seed_search_item(fm, none, qw, len, len, 0, &lo, &cnt, nullptr);
+  }
   lower[i] = cnt ? lo : 0;
   upper[i] = cnt ? (uint64_t)lo + cnt : 0;
 }

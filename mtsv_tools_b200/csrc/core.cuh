@@ -221,10 +221,40 @@ MTSV_HD uint32_t fm_locate(const FmView& fm, const SaView& sv, uint32_t row, uin
 
 // k-mer interval table: entry for a k-mer w (key = lo plane | hi plane << k, base j at bit j)
 // = SA interval [l,u) of w, or l == u when absent.  Legal shortcut 5 of SURVEY app. A.
+//
+// "Direct" entries: a k-mer that occurs exactly ONCE in the text does not need its SA interval — whatever longer
+// seed ends with it can only occur at that one place.  Such an entry holds the text position of the k-mer and
+// the 8 symbols that precede it (3 bits each): the remaining S - k symbols of a seed are compared right there
+// (further back than 8: against the text itself), and the seed's hit is (position - (S - k)) without any
+// rank query and without touching the suffix array.  On a 1 Gbp index that is every true seed outside repeats:
+// one 128-byte line per seed instead of one table line + two FM lines + one SA line.
 struct KtabView {
   const uint2* tab;
-  uint32_t k;  // 0 = no table
+  uint32_t k;           // 0 = no table
+  uint32_t direct;      // 1 = unique k-mers are stored as direct entries
+  const uint8_t* text;  // the reference text (only read for seeds longer than k + 8)
 };
+constexpr uint32_t kKtabDirectTag = 0xFFu;       // e.y >> 24 of a direct entry (needs n < 0xFF000000)
+constexpr uint32_t kKtabDirectCtx = 8;           // preceding symbols kept in the entry
+constexpr uint32_t kDirectHit = 0x80000000u;     // flag in a slot's count: `lo` is a text position, count 1
+constexpr uint32_t kSlotCountMask = 0x7fffffffu;
+
+// symbol class used to compare text with seed symbols: A,C,G,T = 0..3, N = 4, anything else 5
+MTSV_HD uint32_t ktab_ctx_code(uint8_t b) {
+  uint32_t c = upper_acgtn_code(b);
+  return c <= 4 ? c : 5u;
+}
+MTSV_HD uint2 ktab_direct_entry(uint32_t pos, const uint8_t* text) {
+  uint32_t ctx = 0;
+  for (uint32_t t = 1; t <= kKtabDirectCtx; ++t) {
+    uint32_t c = pos >= t ? ktab_ctx_code(ldg(text + pos - t)) : 5u;
+    ctx |= c << (3 * (t - 1));
+  }
+  uint2 e;
+  e.x = pos;
+  e.y = (kKtabDirectTag << 24) | ctx;
+  return e;
+}
 
 // ---------------------------------------------------------------------------------------------
 // batch description
@@ -410,10 +440,26 @@ MTSV_HD void seed_search_item(const FmView& fm, const KtabView& kt, const ReadWo
       if (((win.nn >> sh) & km) == 0) {
         uint64_t key = ((win.lo >> sh) & km) | (((win.hi >> sh) & km) << kt.k);
         uint2 e = ldg(&kt.tab[key]);
+        steps = 1;  // one table sector
+        if (kt.direct && (e.y >> 24) == kKtabDirectTag) {
+          // the k-mer occurs once, at text position e.x: compare the other S - k symbols with what precedes it
+          const uint32_t m = sh, pos = e.x;
+          bool ok = pos >= m;
+          for (uint32_t t = 1; t <= m && ok; ++t) {
+            const uint32_t j = m - t;  // seed symbol index
+            const uint32_t a = ((win.nn >> j) & 1) ? (uint32_t)SYM_N
+                                                   : ((uint32_t)((win.lo >> j) & 1) | ((uint32_t)((win.hi >> j) & 1) << 1));
+            const uint32_t c = t <= kKtabDirectCtx ? (e.y >> (3 * (t - 1))) & 7u : ktab_ctx_code(ldg(kt.text + pos - t));
+            ok = c == a;
+          }
+          if (rank_steps) *rank_steps = steps + (m > kKtabDirectCtx ? 1u : 0u);
+          *out_lo = ok ? pos - m : 0;
+          *out_cnt = ok ? (1u | kDirectHit) : 0;
+          return;
+        }
         l = e.x;
         u = e.y;
         i -= (int)kt.k;
-        steps = 1;  // one table sector
       }
     }
     for (; i >= 0 && l < u; --i) {
@@ -472,7 +518,7 @@ MTSV_HD void seed_select_item(const Params& p, uint32_t nslots, const uint32_t* 
   uint64_t total = 0;
   for (uint32_t j = 0; j < nslots; ++j) {
     uint64_t offset = (uint64_t)j * p.G;
-    uint32_t cnt = slot_cnt[j];
+    uint32_t cnt = slot_cnt[j] & kSlotCountMask;  // (a direct hit counts 1)
     uint32_t ho = kUnused;
     if (offset >= next_offset && cnt != 0 && (uint64_t)cnt <= p.max_hits) {  // :300-302,:330,:335
       if ((uint64_t)cnt > p.tune_max_hits) {                                 // :338-344

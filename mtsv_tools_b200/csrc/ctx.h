@@ -82,6 +82,7 @@ struct DeviceIndex {
   // k-mer interval table
   uint2* ktab = nullptr;
   uint32_t ktab_k = 0;
+  uint32_t ktab_direct = 0;  // unique k-mers hold (text position, preceding symbols) instead of their SA interval
   // reference text (bytes, as in the file) and bins (SoA)
   uint8_t* text = nullptr;
   uint64_t* text4 = nullptr;  // the same text as 4-bit match classes (0..3 = A,C,G,T, 4 = anything else), 16 per word
@@ -102,7 +103,7 @@ struct DeviceIndex {
     return v;
   }
   SaView sa_view() const { return SaView{sa, sa_rate}; }
-  KtabView ktab_view() const { return KtabView{ktab, ktab_k}; }
+  KtabView ktab_view() const { return KtabView{ktab, ktab_k, ktab_direct, text}; }
   BinsView bins_view() const { return BinsView{bin_start, bin_end, bin_tax, bin_gi, (uint32_t)n_bins}; }
 };
 

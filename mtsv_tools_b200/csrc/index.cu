@@ -206,6 +206,16 @@ __global__ void ktab_level_kernel(FmView fm, const uint2* __restrict__ cur, uint
 
 __global__ void ktab_init_kernel(uint2* cur, uint32_t n) { cur[0] = make_uint2(0, n); }
 
+// k-mers that occur exactly once become direct entries (core.cuh): text position + the 8 preceding symbols
+__global__ void ktab_direct_kernel(FmView fm, SaView sv, const uint8_t* __restrict__ text, uint2* __restrict__ tab,
+                                   uint64_t size) {
+  uint64_t key = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (key >= size) return;
+  uint2 e = tab[key];
+  if (e.y - e.x != 1) return;
+  tab[key] = ktab_direct_entry(fm_locate(fm, sv, e.x, nullptr), text);
+}
+
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
@@ -504,6 +514,13 @@ int index_from_host_parts(const uint8_t* text, uint64_t n, const mtsvgpu_bin* bi
                     bufs[cur], bufs[cur ^ 1], lev);
         cur ^= 1;
         cur_size *= 4;
+      }
+      // row indexes of ordinary entries must stay below the direct tag; MTSV_B200_KTAB_DIRECT=0 is an A/B knob
+      const char* de = getenv("MTSV_B200_KTAB_DIRECT");
+      if (n < ((uint64_t)kKtabDirectTag << 24) && !(de && de[0] == '0')) {
+        MTSV_LAUNCH(ktab_direct_kernel, (unsigned)((size + 255) / 256), 256, 0, st, d.fm_view(), d.sa_view(), d.text,
+                    d.ktab, size);
+        d.ktab_direct = 1;
       }
       MTSV_CUDA_TRY(cudaGetLastError());
       MTSV_CUDA_TRY(cudaStreamSynchronize(st));

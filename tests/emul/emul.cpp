@@ -143,10 +143,16 @@ void* emul_index_build(const uint8_t* text, uint64_t n, const emul_bin* bins, ui
       }
       cur.swap(next);
     }
+    // unique k-mers become direct entries, as ktab_direct_kernel does
+    for (uint64_t key = 0; key < cur.size(); ++key)
+      if (cur[key].y - cur[key].x == 1)
+        cur[key] = ktab_direct_entry(fm_locate(e->fm, e->sv, cur[key].x, nullptr), e->text.data());
     e->ktab = cur;
   }
   e->kt.tab = e->ktab.data();
   e->kt.k = ktab_k;
+  e->kt.direct = ktab_k ? 1 : 0;
+  e->kt.text = e->text.data();
   e->bv = BinsView{e->bin_start.data(), e->bin_end.data(), e->bin_tax.data(), e->bin_gi.data(),
                    (uint32_t)n_bins};
   return e;
@@ -380,8 +386,9 @@ int emul_bin_reads(void* p, const uint8_t* seqs, const uint64_t* seq_off, uint64
     std::vector<uint64_t> keys(nhits);
     for (uint32_t j = 0; j < nslots; ++j)
       if (hoff[j] != kUnused)
-        for (uint32_t r = 0; r < cnt[j]; ++r)
-          keys[hoff[j] + r] = make_hit_key(fm_locate(e->fm, e->sv, lo[j] + r, nullptr), j * prm.G);
+        for (uint32_t r = 0; r < (cnt[j] & kSlotCountMask); ++r)
+          keys[hoff[j] + r] = (cnt[j] & kDirectHit) ? make_hit_key(lo[j], j * prm.G)
+                                                    : make_hit_key(fm_locate(e->fm, e->sv, lo[j] + r, nullptr), j * prm.G);
     std::sort(keys.begin(), keys.end());
     uint32_t k = edit_budget(L, prm.edit_rate);
     std::vector<CandRec> cand(nhits ? nhits : 1);

@@ -44,14 +44,15 @@ def test_rank_symbol_locate(oracle, emul, small_index):
             assert e.locate(row) == ix.locate(row)[0]
 
 
-@pytest.mark.parametrize("ktab_k", [0, 1, 4, 7])
+@pytest.mark.parametrize("ktab_k", [0, 1, 4, 7, 10])
 def test_backward_search(oracle, emul, small_index, ktab_k):
     ix = small_index
     e = emul.EmulIndex(ix, sa_rate=1, ktab_k=ktab_k)
     text = bytes(ix.text)
     rng = random.Random(ktab_k)
+    n_direct = 0
     for _ in range(1500):
-        m = rng.randint(max(1, ktab_k), 24)
+        m = rng.randint(max(1, ktab_k), 40 if ktab_k == 10 else 24)  # > k + 8: the comparison continues in the text
         if rng.random() < 0.6:
             st = rng.randrange(0, len(text) - m - 1)
             pat = bytearray(text[st:st + m])
@@ -62,10 +63,16 @@ def test_backward_search(oracle, emul, small_index, ktab_k):
             pat = bytes(rng.choice(b"ACGTN") for _ in range(m))
         r, lo, up, _ = ix.backward_search(pat)
         elo, ecnt = e.backward_search(pat)
-        if r == 2:
+        if r == 2 and ecnt & 0x80000000:
+            # direct entry of the k-mer table (core.cuh): a seed that ends in a unique k-mer comes back as its
+            # text position, without rank queries
+            n_direct += 1
+            assert up - lo == 1 and ecnt == 0x80000001 and ix.locate(lo)[0] == elo, pat
+        elif r == 2:
             assert (elo, ecnt) == (lo, up - lo), pat
         else:
             assert ecnt == 0
+    assert n_direct > 100 or ktab_k < 10  # (a 160 kbp text: its 10-mers are mostly unique, shorter ones are not)
 
 
 def test_edit_distance_fuzz(oracle, emul):
@@ -304,6 +311,8 @@ def test_slice_schedule(emul):
 
 CASES = [
     ("defaults dense+ktab", {}, 1, 8),
+    ("direct k-mer entries", {}, 1, 10),
+    ("direct entries, seeds longer than k + 8", dict(seed_size=24, seed_gap=9), 1, 10),
     ("sa_rate 4, no table", {}, 4, 0),
     ("file-rate SA, ktab 5", {}, 32, 5),
     ("max_candidates 1", dict(max_candidates=1), 1, 6),

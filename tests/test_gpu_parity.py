@@ -142,6 +142,8 @@ CASES = [
     ("2k > L", dict(edit_rate=0.6), {}),
     ("edit 0", dict(edit_rate=0.0), {}),
     ("min_seed 0.5", dict(min_seed=0.5), {}),
+    ("seeds longer than k + 8 (direct k-mer entries continue in the text)", dict(seed_size=24, seed_gap=9), {}),
+    ("file-rate SA, auto table (direct entries located by LF walks)", {}, dict(sa_rate=32)),
     ("tiny sub-batches", {}, dict(batch_reads=97)),
     ("hit cap forces splitting", {}, dict(max_batch_hits=5000)),
 ]
