@@ -115,6 +115,8 @@ typedef struct {
   uint64_t window_bytes;   /* reference bytes read by the verifier */
   uint64_t rank_queries;   /* 32-byte index sectors touched by seed search: FM blocks + k-mer table (0 unless profiling) */
   uint64_t n_sub_batches;  /* device sub-batches the call was processed in (= launches of every stage kernel) */
+  uint64_t h2d_bytes;      /* host API: bytes actually uploaded (offsets of equal-length slices are generated
+                              on the device instead) */
 } mtsvgpu_batch_stats;
 
 /* ---- index lifetime: replaces from_file::<MGIndex> (src/io.rs:115-122, src/binner.rs:63-67) ---- */

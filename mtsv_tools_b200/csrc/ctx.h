@@ -185,6 +185,9 @@ struct mtsvgpu_index {
   mtsvgpu_batch_stats stats{};
   // host API: copy streams, per-sub-batch "input landed" events, pinned result buffers
   cudaStream_t copy_in_stream = nullptr;
+  std::atomic<uint64_t> slices_enqueued{0};  // host API: slices whose upload has been enqueued (uploader thread)
+  std::atomic<int> upload_rc{0};
+  std::string upload_msg;
   std::vector<cudaEvent_t> in_events;
   // called before each slice on the stream that will compute it
   int (*sub_batch_hook)(mtsvgpu_index*, uint64_t, cudaStream_t) = nullptr;
