@@ -468,11 +468,11 @@ def run_gpu_arm(args, cfg, rank, world, local_rank):
     dom = max(alg_bytes, key=lambda k: per_step.get(k, 0.0))
     notes = {
         "verify": {"bound_actual": "SM integer issue (ALU pipe), not memory: the Myers/Hyyro bit-vector recurrence "
-                                   "keeps the ALU pipe ~93 % busy (ncu); HBM fraction is reported as the contract asks"},
+                                   "keeps the ALU pipe ~92 % busy (ncu); HBM fraction is reported as the contract asks"},
         "seed_search": {"bound_actual": "HBM random access: every miss fills a whole 128-B line on this part "
                                         "(tools/randbench2.cu: 8/16/32-B random loads all read ~4 sectors from DRAM), so "
-                                        "DRAM traffic is ~4x the algorithmic sectors and the kernel sits at ~68 % of "
-                                        "peak DRAM throughput (ncu)",
+                                        "DRAM traffic is a multiple of the algorithmic sectors and the kernel sits at ~70 % of "
+                                        "peak DRAM throughput = 5.5 TB/s, the random-line ceiling (ncu)",
                         "random_line_ceiling_per_s": 4.6e10},
         "locate": {"bound_actual": "HBM random access (128-B line fills), see seed_search"},
     }
