@@ -321,6 +321,34 @@ def test_randomized_adversarial_cases(oracle):
         _same(h1, o1, h2, o2)
 
 
+def test_randomized_long_and_ragged_cases(oracle):
+    """tests/fuzz_cases.py::long_case through both host entry points: read lengths 0..420 (every verifier width,
+    uniform and ragged batches, the SW re-check of reads >= 254 bases), tiny sub-batches (many slices on both
+    lanes, adaptive launch groups).  tools/fuzz_gpu.py runs the same generator for minutes."""
+    from tests.fuzz_cases import long_case
+    rng = random.Random(4242)
+    for t in range(120):
+        ix, reads, p = long_case(rng)
+        h1, o1 = ix.bin_reads(reads, p)
+        pg = Params(edit_rate=p.edit_rate, seed_size=p.seed_size, seed_gap=p.seed_gap, min_seed=p.min_seed,
+                    max_hits=p.max_hits, tune_max_hits=p.tune_max_hits,
+                    max_candidates=None if p.max_candidates < 0 else p.max_candidates,
+                    max_assignments=None if p.max_assignments < 0 else p.max_assignments)
+        opts = dict(sa_rate=rng.choice([1, 2, 32]), ktab_k=rng.choice([0, 0xFFFFFFFF, 2, 5]),
+                    batch_reads=rng.choice([0, 0, 1, 3, 7, 16]), max_batch_hits=rng.choice([0, 0, 50]))
+        if opts["sa_rate"] > ix.sa_sample_rate:
+            opts["sa_rate"] = 1
+        with _gpu_index(ix, **opts) as g:
+            try:
+                h2, o2 = g.bin_reads(reads, pg)
+                h3, o3 = g.bin_reads_pinned(oracle.pack_seqs(reads), pg)
+            except Exception as e:  # a refused case (seed-hit cap of 50 on one read) must say so
+                assert "cap" in str(e) or "limit" in str(e).lower(), e
+                continue
+        _same(h1, o1, h2, o2)
+        _same(h1, o1, h3, o3)
+
+
 def test_appendix_e_vectors_on_gpu(oracle):
     from tests.test_oracle import APPENDIX_E
     for name, refs, read, flags, want, want_long in APPENDIX_E:

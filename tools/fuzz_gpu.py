@@ -15,64 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from mtsv_tools_b200 import MGIndex, Params  # noqa: E402
 from oracle import pyoracle as po  # noqa: E402
-from tests.fuzz_cases import rand_case  # noqa: E402
-
-
-def mutate(rng, s, n):
-    s = bytearray(s)
-    for _ in range(n):
-        if not s:
-            break
-        i = rng.randrange(len(s))
-        r = rng.random()
-        if r < 0.45:
-            s[i] = rng.choice(b"ACGTNacgtnx")
-        elif r < 0.75:
-            for _ in range(rng.randint(1, 3)):
-                s.insert(i, rng.choice(b"ACGT"))
-        else:
-            del s[i:i + rng.randint(1, 3)]
-    return bytes(s)
-
-
-def long_case(rng):
-    """Bigger references and reads of up to 420 bases, uniform or ragged."""
-    nseq = rng.randint(1, 5)
-    seqs = []
-    for _ in range(nseq):
-        L = rng.randint(400, 3000)
-        s = bytes(rng.choice(b"ACGT") for _ in range(L))
-        if seqs and rng.random() < 0.4:
-            s = mutate(rng, rng.choice(seqs), rng.randint(0, 30))
-        if rng.random() < 0.3:
-            p = rng.randrange(len(s) - 60)
-            s = s[:p] + b"N" * rng.randint(5, 50) + s[p + 50:]
-        seqs.append(s)
-    ix = po.Index.build(seqs, list(range(10, 10 + nseq)), [rng.randint(1, 3) for _ in range(nseq)],
-                        rng.choice([7, 64]), rng.choice([3, 32]))
-    text = bytes(ix.text)
-    uniform = rng.random() < 0.5
-    L0 = rng.choice([30, 64, 65, 100, 128, 129, 150, 192, 193, 250, 253, 254, 256, 257, 300, 420])
-    rate = rng.choice([0.02, 0.05, 0.13, 0.2, 0.3])
-    reads = []
-    for _ in range(rng.randint(1, 60)):
-        L = L0 if uniform else rng.randint(0, 420)
-        if rng.random() < 0.8:
-            st = rng.randrange(0, max(1, len(text) - 2))
-            s = text[st:st + L + 12].replace(b"$", b"A")
-            s = mutate(rng, s, int(rng.random() * 1.3 * rate * L))[:L]
-            if uniform and len(s) < L:
-                s = s + bytes(rng.choice(b"ACGT") for _ in range(L - len(s)))
-            if rng.random() < 0.5:
-                s = bytes({65: 84, 67: 71, 71: 67, 84: 65}.get(c, c) for c in reversed(s))
-        else:
-            s = bytes(rng.choice(b"ACGTN") for _ in range(L))
-        reads.append(s)
-    p = po.default_params(edit_rate=rate, seed_size=rng.choice([12, 18, 18, 24]), seed_gap=rng.choice([3, 7, 15]),
-                          min_seed=rng.choice([0.015, 0.3]), max_hits=rng.choice([20, 2000]),
-                          tune_max_hits=rng.choice([2, 200]), max_candidates=rng.choice([-1, -1, 2]),
-                          max_assignments=rng.choice([-1, -1, 1]))
-    return ix, reads, p
+from tests.fuzz_cases import long_case, rand_case  # noqa: E402
 
 
 def main():
