@@ -184,6 +184,12 @@ typedef struct {
 MTSVGPU_API int mtsvgpu_collapse_device(int device, void* stream, uint32_t n_parts,
                             const mtsvgpu_hit* const* d_hits, const uint32_t* const* d_counts,
                             uint64_t n_reads, mtsvgpu_taxhit** d_out, uint64_t** d_out_off, uint64_t* n_out);
+/* Same merge in mtsv-collapse's mode TaxIdGi (src/collapse.rs:603-625): per read and per (TaxID, GI) the hit with
+ * the smallest edit, ties to the smallest offset; listed by (TaxID, GI) as write_collapsed_taxid_gi does (:311-318).
+ * Output records are whole hits (tax_id, gi, offset, edit). */
+MTSVGPU_API int mtsvgpu_collapse_device_taxid_gi(int device, void* stream, uint32_t n_parts,
+                            const mtsvgpu_hit* const* d_hits, const uint32_t* const* d_counts,
+                            uint64_t n_reads, mtsvgpu_hit** d_out, uint64_t** d_out_off, uint64_t* n_out);
 MTSVGPU_API void mtsvgpu_device_free(void* d_ptr);
 
 MTSVGPU_API void mtsvgpu_free(void* p);

@@ -60,7 +60,7 @@ EXPORTS = [
     "mtsvgpu_index_open", "mtsvgpu_index_from_parts", "mtsvgpu_index_close", "mtsvgpu_index_get_info",
     "mtsvgpu_bin_batch", "mtsvgpu_bin_batch_pinned", "mtsvgpu_bin_batch_device", "mtsvgpu_last_batch_stats", "mtsvgpu_set_stream",
     "mtsvgpu_set_profiling", "mtsvgpu_backward_search", "mtsvgpu_locate", "mtsvgpu_edit_distance",
-    "mtsvgpu_collapse_device", "mtsvgpu_device_free", "mtsvgpu_free", "mtsvgpu_last_error", "mtsvgpu_launch_count", "mtsvgpu_version",
+    "mtsvgpu_collapse_device", "mtsvgpu_collapse_device_taxid_gi", "mtsvgpu_device_free", "mtsvgpu_free", "mtsvgpu_last_error", "mtsvgpu_launch_count", "mtsvgpu_version",
 ]
 
 
@@ -106,6 +106,7 @@ def load_library():
     L.mtsvgpu_locate.argtypes = [vp, vp, C.c_uint64, vp]
     L.mtsvgpu_collapse_device.argtypes = [C.c_int, vp, C.c_uint32, C.POINTER(vp), C.POINTER(vp), C.c_uint64,
                                           C.POINTER(vp), C.POINTER(vp), u64p]
+    L.mtsvgpu_collapse_device_taxid_gi.argtypes = L.mtsvgpu_collapse_device.argtypes
     L.mtsvgpu_device_free.argtypes = [vp]
     L.mtsvgpu_edit_distance.argtypes = [C.c_int, vp, vp, vp, vp, C.c_uint64, vp]
     _LIB = L

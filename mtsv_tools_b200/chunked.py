@@ -50,6 +50,26 @@ def collapse_parts_device(device, stream, parts_hits, parts_counts, n_reads):
     return pairs, offs.view(torch.int64)
 
 
+def collapse_parts_device_taxid_gi(device, stream, parts_hits, parts_counts, n_reads):
+    """mtsv-collapse's mode TaxIdGi on the device (src/collapse.rs:603-625): per read and (TaxID, GI) the hit with
+    the smallest edit, ties to the smallest offset, listed by (TaxID, GI).  Same inputs as collapse_parts_device;
+    returns (hits uint8 tensor of 24-byte mtsvgpu_hit records, offsets int64 tensor [n_reads+1])."""
+    import torch
+    L = _lib.load_library()
+    n = len(parts_hits)
+    hp = (C.c_void_p * n)(*[C.c_void_p(t.data_ptr()) for t in parts_hits])
+    cp = (C.c_void_p * n)(*[C.c_void_p(t.data_ptr()) for t in parts_counts])
+    d_out, d_off, n_out = C.c_void_p(), C.c_void_p(), C.c_uint64()
+    check(L.mtsvgpu_collapse_device_taxid_gi(device, C.c_void_p(stream or 0), n, hp, cp, n_reads, C.byref(d_out),
+                                             C.byref(d_off), C.byref(n_out)))
+    dev = torch.device("cuda", device)
+    hits = torch.as_tensor(_DevArray(d_out.value, max(1, n_out.value) * 24), device=dev).clone()[: n_out.value * 24]
+    offs = torch.as_tensor(_DevArray(d_off.value, (n_reads + 1) * 8), device=dev).clone()
+    L.mtsvgpu_device_free(d_out)
+    L.mtsvgpu_device_free(d_off)
+    return hits, offs.view(torch.int64)
+
+
 def exchange_hits(hits_bytes, counts, bounds, group=None):
     """The communication step.  hits_bytes: uint8 tensor (24 B per hit, CSR by read over ALL reads of the
     batch); counts: int32 tensor [n_reads] (hits per read).  bounds: read_ranges().  Returns, for this

@@ -356,6 +356,13 @@ int mtsvgpu_collapse_device(int device, void* stream, uint32_t n_parts, const mt
   return collapse_device(device, (cudaStream_t)stream, n_parts, d_hits, d_counts, n_reads, d_out, d_out_off, n_out);
 }
 
+int mtsvgpu_collapse_device_taxid_gi(int device, void* stream, uint32_t n_parts, const mtsvgpu_hit* const* d_hits,
+                                     const uint32_t* const* d_counts, uint64_t n_reads, mtsvgpu_hit** d_out,
+                                     uint64_t** d_out_off, uint64_t* n_out) {
+  return collapse_device_long(device, (cudaStream_t)stream, n_parts, d_hits, d_counts, n_reads, d_out, d_out_off,
+                              n_out);
+}
+
 void mtsvgpu_device_free(void* d_ptr) {
   if (d_ptr) cudaFree(d_ptr);
 }

@@ -228,6 +228,9 @@ int run_segmented_sort(cudaStream_t st, DevBuf& worklist, uint64_t* keys, const 
 int collapse_device(int device, cudaStream_t st, uint32_t n_parts, const mtsvgpu_hit* const* d_hits,
                     const uint32_t* const* d_counts, uint64_t n_reads, mtsvgpu_taxhit** d_out,
                     uint64_t** d_out_off, uint64_t* n_out);
+int collapse_device_long(int device, cudaStream_t st, uint32_t n_parts, const mtsvgpu_hit* const* d_hits,
+                         const uint32_t* const* d_counts, uint64_t n_reads, mtsvgpu_hit** d_out,
+                         uint64_t** d_out_off, uint64_t* n_out);
 // scan.cuh users
 int exclusive_scan_u32(const uint32_t* d_in, uint32_t* d_out, uint64_t n, DevBuf& tmp,
                        uint64_t* d_total, cudaStream_t stream);

@@ -329,3 +329,27 @@ def collapse_taxid(parts):
             pairs.append((t, best[t]))
         offs[r + 1] = len(pairs)
     return np.array(pairs, dtype=np.uint32).reshape(-1, 2), offs
+
+
+def collapse_taxid_gi(parts):
+    """mtsv-collapse, mode TaxIdGi (src/collapse.rs:603-625): per read and per (TaxID, GI) keep the smallest edit,
+    ties to the smallest offset; listed by (TaxID, GI, edit, offset) (write_collapsed_taxid_gi, :311-318).
+    parts as in collapse_taxid.  Returns (hits structured array HIT_DTYPE-like, offsets uint64 [n_reads+1])."""
+    n_reads = len(parts[0][1]) - 1
+    rows, offs = [], np.zeros(n_reads + 1, dtype=np.uint64)
+    for r in range(n_reads):
+        best = {}
+        for hits, o in parts:
+            for h in hits[int(o[r]):int(o[r + 1])]:
+                key = (int(h["tax_id"]), int(h["gi"]))
+                val = (int(h["edit"]), int(h["offset"]))
+                if key not in best or val < best[key]:  # :622: edit <, or edit == and offset <
+                    best[key] = val
+        for key in sorted(best):
+            rows.append((key[0], key[1], best[key][1], best[key][0]))
+        offs[r + 1] = len(rows)
+    out = np.zeros(len(rows), dtype=[("tax_id", "<u4"), ("gi", "<u4"), ("offset", "<u8"), ("edit", "<u4"),
+                                     ("reserved", "<u4")])
+    for i, (t, g, off, e) in enumerate(rows):
+        out[i] = (t, g, off, e, 0)
+    return out, offs

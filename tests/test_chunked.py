@@ -104,6 +104,67 @@ def test_collapse_rule_kats():
     assert pairs.tolist() == [[1, 2], [2, 9], [3, 1]] and offs.tolist() == [0, 2, 3]
 
 
+def test_collapse_rule_kat_taxid_gi():
+    """src/collapse.rs:804-817 collapse_edit_distances_taxid_gi_min_edit:
+    r1:1-5-3=7,1-5-2=4 | r2:2-9-1=3  +  r1:1-5-4=5,2-8-1=6 | r2:2-9-1=2  ->  r1:1-5-2=4,2-8-1=6 | r2:2-9-1=2."""
+    from oracle import pyoracle
+
+    def mk(lists):
+        hits = np.zeros(sum(len(x) for x in lists), dtype=HIT_DTYPE)
+        offs = np.zeros(len(lists) + 1, dtype=np.uint64)
+        k = 0
+        for i, l in enumerate(lists):
+            for t, g, off, e in l:
+                hits[k]["tax_id"], hits[k]["gi"], hits[k]["offset"], hits[k]["edit"] = t, g, off, e
+                k += 1
+            offs[i + 1] = k
+        return hits, offs
+    a = mk([[(1, 5, 3, 7), (1, 5, 2, 4)], [(2, 9, 1, 3)]])
+    b = mk([[(1, 5, 4, 5), (2, 8, 1, 6)], [(2, 9, 1, 2)]])
+    out, offs = pyoracle.collapse_taxid_gi([a, b])
+    got = [(int(h["tax_id"]), int(h["gi"]), int(h["offset"]), int(h["edit"])) for h in out]
+    assert got == [(1, 5, 2, 4), (2, 8, 1, 6), (2, 9, 1, 2)] and offs.tolist() == [0, 2, 3]
+    # ties on the edit go to the smaller offset (:622)
+    c = mk([[(1, 5, 9, 4)], []])
+    out, offs = pyoracle.collapse_taxid_gi([c, a])
+    assert (int(out[0]["offset"]), int(out[0]["edit"])) == (2, 4)
+
+
+@pytest.mark.gpu
+def test_collapse_device_taxid_gi_vs_oracle(oracle):
+    """Device merge in mode TaxIdGi == oracle restatement, on two chunks that share sequence (same TaxID/GI reached
+    from both) plus the reference's KAT."""
+    from mtsv_tools_b200 import MGIndex, Params, synth
+    refs = [synth.make_reference(6, 20000, seed=s, n_frac=0.001, shared_frac=0.1, taxids=[5, 6, 7, 8, 9, 10])
+            for s in (31, 32)]
+    refs[1][0][:30000] = refs[0][0][:30000]  # same GIs (1..6) in both chunks: groups meet across parts
+    idx = [oracle.Index.build((r[0], r[1]), r[2], r[3], 64, 32) for r in refs]
+    reads = synth.make_reads(np.concatenate([refs[0][0], refs[1][0]]),
+                             np.concatenate([refs[0][1], refs[1][1][1:] + refs[0][1][-1]]), 4000, 150, seed=33)
+    parts_o = [ix.bin_reads(reads, oracle.default_params(), threads=4) for ix in idx]
+    want, want_off = oracle.collapse_taxid_gi(parts_o)
+    parts_h = [torch.from_numpy(np.frombuffer(h.tobytes(), dtype=np.uint8).copy()).cuda() for h, _ in parts_o]
+    parts_c = [torch.from_numpy((o[1:] - o[:-1]).astype(np.int32)).cuda() for _, o in parts_o]
+    hits, offs = chunked.collapse_parts_device_taxid_gi(0, None, parts_h, parts_c, 4000)
+    got = np.frombuffer(hits.cpu().numpy().tobytes(), dtype=HIT_DTYPE)
+    assert np.array_equal(offs.cpu().numpy().astype(np.uint64), want_off)
+    for f in ("tax_id", "gi", "offset", "edit"):
+        assert np.array_equal(got[f], want[f]), f
+    assert len(want) > 3000
+    # the reference's own KAT through the device kernel
+    a = np.zeros(3, dtype=HIT_DTYPE)
+    a["tax_id"], a["gi"], a["offset"], a["edit"] = [1, 1, 2], [5, 5, 9], [3, 2, 1], [7, 4, 3]
+    b = np.zeros(3, dtype=HIT_DTYPE)
+    b["tax_id"], b["gi"], b["offset"], b["edit"] = [1, 2, 2], [5, 8, 9], [4, 1, 1], [5, 6, 2]
+    ph = [torch.from_numpy(np.frombuffer(x.tobytes(), dtype=np.uint8).copy()).cuda() for x in (a, b)]
+    pc = [torch.tensor([2, 1], dtype=torch.int32).cuda(), torch.tensor([2, 1], dtype=torch.int32).cuda()]
+    hits, offs = chunked.collapse_parts_device_taxid_gi(0, None, ph, pc, 2)
+    got = np.frombuffer(hits.cpu().numpy().tobytes(), dtype=HIT_DTYPE)
+    assert [(int(h["tax_id"]), int(h["gi"]), int(h["offset"]), int(h["edit"])) for h in got] == \
+        [(1, 5, 2, 4), (2, 8, 1, 6), (2, 9, 1, 2)]
+    assert offs.cpu().tolist() == [0, 2, 3]
+
+
 @pytest.mark.gpu
 def test_collapse_device_vs_oracle(oracle):
     """Two different chunks, the same reads: device merge == oracle merge of the two oracle runs."""
