@@ -601,9 +601,18 @@ __global__ void __launch_bounds__(128) coalesce_kernel(BinsView bv, ReadsView rv
   // hits, so lanes carry similar loads); a strand with many hits is handed to the whole warp
   const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
   const unsigned lane = threadIdx.x & 31;
-  for (uint32_t s = 0; s < p.ns; ++s) {
+  // first pass: every lane takes the strand of its read that has more hits (nearly always the only one with
+  // any), so that the lanes of a warp are busy together; second pass: the other strand
+  uint32_t first = 0;
+  if (p.ns == 2 && r * 2 + 1 < nq && q_nhits[r * 2 + 1] > q_nhits[r * 2]) first = 1;
+  for (uint32_t pass = 0; pass < p.ns; ++pass) {
+    const uint32_t s = p.ns == 2 ? (pass ^ first) : 0;
     const uint32_t q = r * p.ns + s;
     uint32_t nh = q < nq ? q_nhits[q] : 0;
+    if (pass == 1 && !__any_sync(0xffffffffu, nh != 0)) {  // nothing left for this warp
+      if (q < nq) q_ncand[q] = 0;
+      continue;
+    }
     uint32_t nc = 0, L = 0, k = 0, ms = 0, base = 0;
     if (nh) {
       L = query_len(rv, p.ns, q);
