@@ -376,6 +376,21 @@ def test_pipeline_n_rich_reference(oracle, emul):
         assert len(h1) > 500
 
 
+def test_pipeline_checklist_cases(oracle, emul):
+    """SURVEY appendix C, constructed (tests/checklist_cases.py): bin junctions, bins shorter than reads, equal seed
+    counts, the same TaxID on both strands, tandem repeats, min_seeds >= 2, degenerate read lengths."""
+    from tests.checklist_cases import build
+    ix, reads, flag_sets = build()
+    packed = oracle.pack_seqs(reads)
+    for sa_rate, ktab_k in ((1, 8), (32, 0)):
+        e = emul.EmulIndex(ix, sa_rate=sa_rate, ktab_k=ktab_k)
+        for flags in flag_sets:
+            p = oracle.default_params(**flags)
+            h1, o1 = ix.bin_reads(reads, p, threads=4)
+            h2, o2 = e.bin_reads(packed[0], packed[1], p)
+            _same(h1, o1, h2, o2)
+
+
 def test_pipeline_long_reads_high_edit(oracle, emul, small_ref, small_index):
     """BASELINE config 5 in miniature: 250 bp, edit-rate 0.2, dense seeding."""
     reads = synth.make_reads(small_ref[0], small_ref[1], 500, 250, seed=8, sub=0.10)

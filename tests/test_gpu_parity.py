@@ -321,6 +321,22 @@ def test_randomized_adversarial_cases(oracle):
         _same(h1, o1, h2, o2)
 
 
+def test_pipeline_checklist_cases(oracle):
+    """SURVEY appendix C, constructed (tests/checklist_cases.py), through both host entry points."""
+    from tests.checklist_cases import build
+    ix, reads, flag_sets = build()
+    packed = oracle.pack_seqs(reads)
+    for opts in ({}, dict(sa_rate=32, ktab_k=0xFFFFFFFF), dict(batch_reads=64)):
+        with _gpu_index(ix, **opts) as g:
+            for flags in flag_sets:
+                po, pg = _params(oracle, **flags)
+                h1, o1 = ix.bin_reads(reads, po, threads=8)
+                h2, o2 = g.bin_reads(reads, pg)
+                _same(h1, o1, h2, o2)
+                h3, o3 = g.bin_reads_pinned(packed, pg)
+                _same(h1, o1, h3, o3)
+
+
 def test_randomized_long_and_ragged_cases(oracle):
     """tests/fuzz_cases.py::long_case through both host entry points: read lengths 0..420 (every verifier width,
     uniform and ragged batches, the SW re-check of reads >= 254 bases), tiny sub-batches (many slices on both
