@@ -831,6 +831,9 @@ MTSV_HD void myers_cols4(uint32_t codes, uint32_t ncols, uint64_t (&Pv)[W], uint
 #pragma unroll
     for (int w = F; w <= Z; ++w) {
       uint64_t Ph, Mh;
+#ifdef MTSV_COUNT_BLOCKS
+      ++g_myers_blocks;
+#endif
       myers_block(peq(c, w), Pv[w], Mv[w], phin, mhin, Ph, Mh);  // leaves the carries in phin / mhin
       if (UNIFORM && w < W - 1) {
         bs[w] += phin;
