@@ -232,17 +232,19 @@ def test_pipeline_n_rich_reference(oracle):
 
 
 def test_verifier_fast_and_legacy_paths_agree(oracle, small_ref, small_index):
-    """Reads <= 256 bases go through verify_warp_kernel (warp-uniform block range, 4-bit text); the
-    per-lane verify_kernel stays for longer reads.  Both must give the oracle's hits on uniform and on
-    ragged batches (mutated reads of 1..256 bases so that the edit budget is actually used)."""
+    """Batches whose reads all have at most 253 bases go through verify_warp_kernel (warp-uniform block range, 4-bit
+    text); the per-lane verify_kernel (+ SW re-check) takes the others.  Both must give the oracle's hits on
+    uniform batches (1, 3 and 4 words; 256 bases = the per-lane path either way) and on a ragged one (mutated
+    reads of 1..253 bases so that the edit budget is actually used)."""
     rng = np.random.default_rng(21)
     ref = small_ref[0]
     batches = {"uniform_150": synth.make_reads(small_ref[0], small_ref[1], 4000, 150, seed=31, sub=0.05),
                "uniform_64": synth.make_reads(small_ref[0], small_ref[1], 3000, 64, seed=32, sub=0.04),
+               "uniform_253": synth.make_reads(small_ref[0], small_ref[1], 2000, 253, seed=34, sub=0.06),
                "uniform_256": synth.make_reads(small_ref[0], small_ref[1], 2000, 256, seed=33, sub=0.06)}
     rl = []
     for _ in range(4000):
-        L = int(rng.integers(1, 257))
+        L = int(rng.integers(1, 254))  # <= 253: the whole batch stays on verify_warp_kernel (W = 4, ragged)
         st = int(rng.integers(0, len(ref) - 300))
         s = bytearray(ref[st:st + L])
         for _ in range(int(rng.integers(0, max(1, L // 12)))):
