@@ -103,41 +103,49 @@ def make_reference_torch(cfg, seed, device):
     return cat, off, gi, tax
 
 
-def get_index_parts(name, cfg, device, rank, world, barrier):
-    """Build (GPU suffix sort) or load the cached MGIndex fields for the workload."""
+def index_file_path(name, cfg):
+    return os.path.join(CACHE_DIR, "%s_seed%d.index" % (name, cfg.get("seed", 3)))
+
+
+def ensure_index_file(name, cfg, local_rank, rank, barrier):
+    """The workload's `.index` file, as mtsv-build would leave it: reference generated on the GPU, index built by
+    the library's device builder (mtsvgpu_index_build: hand-written suffix sort + BWT kernels) and written as the
+    bincode MGIndex a reference mtsv-binner reads (mtsvgpu_index_write).  Cached per box under CACHE_DIR."""
     import torch
-    from mtsv_tools_b200.build_index import build_index_parts
-    seed = cfg.get("seed", 3)
-    d = os.path.join(CACHE_DIR, "%s_seed%d" % (name, seed))
-    done = os.path.join(d, "DONE")
+    from mtsv_tools_b200 import MGIndex
+    path = index_file_path(name, cfg)
+    done = path + ".done.json"
     if rank == 0 and not os.path.exists(done):
+        os.makedirs(CACHE_DIR, exist_ok=True)
         t0 = time.time()
-        os.makedirs(d, exist_ok=True)
-        dev = device if torch.cuda.is_available() else "cpu"
-        cat, off, gi, tax = make_reference_torch(cfg, seed, dev)
-        cat_np = cat.cpu().numpy()
-        del cat
-        if torch.cuda.is_available():
-            torch.cuda.empty_cache()
-        log("reference generated: %.1f Mbp in %.1fs" % (len(cat_np) / 1e6, time.time() - t0))
+        cat, off, gi, tax = make_reference_torch(cfg, cfg.get("seed", 3), "cuda:%d" % local_rank)
+        torch.cuda.synchronize()
         t1 = time.time()
-        parts = build_index_parts(cat_np, off, gi, tax, 32, device=dev, verbose=True)
-        log("index built (suffix array, BWT, samples) in %.1fs" % (time.time() - t1))
-        np.save(os.path.join(d, "text.npy"), parts["text"])
-        np.save(os.path.join(d, "bwt.npy"), parts["bwt"])
-        np.save(os.path.join(d, "sa_sample.npy"), parts["sa_sample"])
-        np.savez(os.path.join(d, "bins.npz"), gi=parts["bins"][0], tax=parts["bins"][1], start=parts["bins"][2],
-                 end=parts["bins"][3], off=off)
-        open(done, "w").write("ok")
-        del parts
+        with MGIndex.build(cat.data_ptr(), off, gi, tax, device=local_rank, ktab_k=0xFFFFFFFF) as g:
+            del cat
+            torch.cuda.empty_cache()
+            t2 = time.time()
+            info = g.info()
+            g.write(path, 64, 32)
+        t3 = time.time()
+        meta = {"reference_gen_seconds": t1 - t0, "build_seconds": info["build_seconds"],
+                "build_call_seconds": t2 - t1, "write_seconds": t3 - t2, "text_len": info["text_len"],
+                "file_bytes": os.path.getsize(path)}
+        log("index built on the GPU: %s" % meta)
+        json.dump(meta, open(done, "w"))
     barrier()
-    t0 = time.time()
-    b = np.load(os.path.join(d, "bins.npz"))
-    parts = dict(text=np.load(os.path.join(d, "text.npy")), bwt=np.load(os.path.join(d, "bwt.npy")),
-                 sa_sample=np.load(os.path.join(d, "sa_sample.npy")),
-                 bins=(b["gi"], b["tax"], b["start"], b["end"]), sa_rate=32, ref_off=b["off"])
-    log("rank %d: index parts loaded from %s in %.1fs" % (rank, d, time.time() - t0))
-    return parts
+    return path, json.load(open(done))
+
+
+def index_file_text_and_bins(path):
+    """Header of the bincode MGIndex (src/index.rs:60-68): sequences (memory-mapped) and the bins."""
+    n = int(np.fromfile(path, dtype="<u8", count=1)[0])
+    text = np.memmap(path, dtype=np.uint8, mode="r", offset=8, shape=(n,))
+    nb = int(np.fromfile(path, dtype="<u8", count=1, offset=8 + n)[0])
+    rec = np.fromfile(path, dtype=np.dtype([("gi", "<u4"), ("tax", "<u4"), ("start", "<u8"), ("end", "<u8")]),
+                      count=nb, offset=16 + n)
+    ref_off = np.concatenate([rec["start"], rec["end"][-1:]]).astype(np.uint64)
+    return text, rec, ref_off
 
 
 class ClockSampler:
@@ -212,14 +220,16 @@ def run_reference_arm(args, cfg, rank, world):
     from oracle import pyoracle
     from mtsv_tools_b200 import synth
     cores = os.cpu_count() or 1
-    parts = get_index_parts(args.config, cfg, "cuda:0", 0, 1, lambda: None)
+    path, _meta = ensure_index_file(args.config, cfg, 0, 0, lambda: None)
     t0 = time.time()
-    oix = pyoracle.Index.from_parts(parts["text"], parts["bins"], parts["bwt"], parts["sa_sample"], 32)
-    log("oracle index assembled in %.1fs" % (time.time() - t0))
+    oix = pyoracle.Index.read(path)
+    log("oracle index read from %s in %.1fs" % (path, time.time() - t0))
+    text, _bins, ref_off = index_file_text_and_bins(path)
+    parts = {"text": text, "ref_off": ref_off}
     L = cfg["read_len"]
     dev = "cuda:0" if torch.cuda.is_available() else "cpu"
     # bounded sample per step: calibrate on 20k reads, aim at ~10 s per step
-    ref_t = torch.from_numpy(parts["text"][:-1]).to(dev)
+    ref_t = torch.from_numpy(np.ascontiguousarray(parts["text"][:-1])).to(dev)
     calib = synth.make_reads_torch(ref_t, parts["ref_off"], 20000, L, 4, dev, sub=cfg.get("read_sub", 0.02)).cpu().numpy()
     off = np.arange(20001, dtype=np.uint64) * np.uint64(L)
     params = pyoracle.default_params(**cfg["flags"])
@@ -295,18 +305,20 @@ def run_gpu_arm(args, cfg, rank, world, local_rank):
             dist.barrier()
 
     lib = load_library()
-    parts = get_index_parts(args.config, cfg, dev, rank, world, barrier)
+    path, build_meta = ensure_index_file(args.config, cfg, local_rank, rank, barrier)
     t0 = time.time()
-    gix = MGIndex.from_parts(parts["text"], parts["bins"], parts["bwt"], parts["sa_sample"], 32,
-                             device=local_rank, sa_rate=args.sa_rate, ktab_k=args.ktab_k,
-                             batch_reads=args.batch_reads)
+    # the drop-in's own way in: mtsvgpu_index_open on the `.index` file (parse, upload, re-layout; nothing rebuilt)
+    gix = MGIndex.from_file(path, device=local_rank, sa_rate=args.sa_rate, ktab_k=args.ktab_k,
+                            batch_reads=args.batch_reads)
     info = gix.info()
-    log("rank %d: index on device in %.1fs (relayout %.2fs), %.2f GB HBM, sa_rate %d, ktab k=%d" %
-        (rank, time.time() - t0, info["relayout_seconds"], info["device_bytes"] / 1e9,
+    log("rank %d: %s opened in %.1fs (relayout %.2fs), %.2f GB HBM, sa_rate %d, ktab k=%d" %
+        (rank, path, time.time() - t0, info["relayout_seconds"], info["device_bytes"] / 1e9,
          info["device_sa_rate"], info["ktab_k"]))
+    text, _bins, ref_off = index_file_text_and_bins(path)
+    parts = {"text": text, "ref_off": ref_off}
     L = cfg["read_len"]
     n_reads = args.reads or cfg["reads"]
-    ref_t = torch.from_numpy(parts["text"][:-1]).to(dev)
+    ref_t = torch.from_numpy(np.ascontiguousarray(parts["text"][:-1])).to(dev)
     t0 = time.time()
     d_reads = synth.make_reads_torch(ref_t, parts["ref_off"], n_reads, L, 4 + 17 * rank, dev,
                                      sub=cfg.get("read_sub", 0.02))
@@ -330,7 +342,7 @@ def run_gpu_arm(args, cfg, rank, world, local_rank):
         from oracle import pyoracle
         ns = min(args.parity_reads, n_reads)
         t0 = time.time()
-        oix = pyoracle.Index.from_parts(parts["text"], parts["bins"], parts["bwt"], parts["sa_sample"], 32)
+        oix = pyoracle.Index.read(path)
         sub = (h_reads.numpy()[:ns * L], h_off.numpy()[:ns + 1].astype(np.uint64))
         octr = pyoracle.Counters()
         want_h, want_o = oix.bin_reads(sub, pyoracle.default_params(**cfg["flags"]), threads=os.cpu_count(),
@@ -485,7 +497,7 @@ def run_gpu_arm(args, cfg, rank, world, local_rank):
     if world == 1 and not args.no_cpu_baseline:
         from oracle import pyoracle
         if oix is None:
-            oix = pyoracle.Index.from_parts(parts["text"], parts["bins"], parts["bwt"], parts["sa_sample"], 32)
+            oix = pyoracle.Index.read(path)
         cores = os.cpu_count() or 1
         op = pyoracle.default_params(**cfg["flags"])
         t0 = time.time()
@@ -520,6 +532,8 @@ def run_gpu_arm(args, cfg, rank, world, local_rank):
         "work_per_step": {k: stats[k] for k in ("n_queries", "n_seed_slots", "n_seed_hits", "n_candidates",
                                                  "n_hits", "window_bytes", "rank_queries")},
         "parity": parity, "index_load_seconds": info["load_seconds"],
+        "index_build": dict(build_meta, note="mtsvgpu_index_build + mtsvgpu_index_write on this box (device suffix sort); "
+                                             "index_load_seconds = mtsvgpu_index_open of that file"),
     }
     if cpu:
         # the layout-independent work of the reference algorithm (32-byte index sectors per read,

@@ -99,6 +99,7 @@ typedef struct {
   uint64_t dollar_row;
   double load_seconds;     /* parse + upload + re-layout */
   double relayout_seconds; /* device re-layout only */
+  double build_seconds;    /* mtsvgpu_index_build only: text assembly + suffix array + BWT */
 } mtsvgpu_index_info;
 
 /* Per-stage device time of the last mtsvgpu_bin_batch*(), CUDA events on the launch stream (ms). */
@@ -128,6 +129,24 @@ MTSVGPU_API int mtsvgpu_index_from_parts(const uint8_t* text, uint64_t n, const 
                              uint64_t n_bins, const uint8_t* bwt, const uint64_t* sa_sample,
                              uint64_t sa_sample_len, uint64_t sa_rate, int device,
                              const mtsvgpu_index_opts* opts, mtsvgpu_index** out);
+/* ---- mtsv-build on the device: MGIndex::new (src/index.rs:491-582; called from src/bin/mtsv-build.rs) ----
+ * n_seqs reference sequences, raw bytes concatenated in `seqs` (host OR device memory) with n_seqs+1 offsets (host),
+ * their GI and TaxID (host; what parse_read_header extracts from `>seqid-taxid`, src/util.rs:26-55).  Bins are laid
+ * out in TaxID order, file order within a TaxID (parse_fasta_db's BTreeMap, src/io.rs:135-150); the text is folded
+ * to ACGTN and terminated by '$' (src/index.rs:543-556); suffix array and BWT are built on the device and go
+ * straight into the device layout: the returned handle is ready for mtsvgpu_bin_batch*.  Peak device memory of
+ * the construction is about 29 bytes per reference base. */
+MTSVGPU_API int mtsvgpu_index_build(const uint8_t* seqs, const uint64_t* seq_off, const uint32_t* gi,
+                        const uint32_t* tax_id, uint64_t n_seqs, int device, const mtsvgpu_index_opts* opts,
+                        mtsvgpu_index** out);
+/* write_to_file(&index, path) (src/io.rs:125-132): the bincode MGIndex a reference mtsv-binner / mtsv-collapse
+ * reads, with Occ checkpoints every `sample_interval` BWT rows (mtsv-build --sample-interval, default 64) and the
+ * suffix array sampled every `sa_sample` rows (--sa-sample, default 32).  Works for any loaded handle. */
+MTSVGPU_API int mtsvgpu_index_write(mtsvgpu_index* ix, const char* path, uint32_t sample_interval, uint32_t sa_sample);
+/* The same fields into caller-allocated host buffers instead of a file (each may be NULL): sequences [text_len],
+ * the byte BWT [text_len], the suffix array rows 0, s, 2s, ... [ceil(text_len / sa_sample)]. */
+MTSVGPU_API int mtsvgpu_index_export(mtsvgpu_index* ix, uint8_t* text_out, uint8_t* bwt_out, uint64_t* sa_sample_out,
+                         uint32_t sa_sample);
 MTSVGPU_API void mtsvgpu_index_close(mtsvgpu_index* ix);
 MTSVGPU_API int mtsvgpu_index_get_info(const mtsvgpu_index* ix, mtsvgpu_index_info* info);
 
@@ -163,6 +182,9 @@ MTSVGPU_API int mtsvgpu_set_profiling(mtsvgpu_index* ix, int on);
  * length over {A,C,G,T,N}: lower/upper = half-open SA interval when the result is Complete, else 0,0. */
 MTSVGPU_API int mtsvgpu_backward_search(mtsvgpu_index* ix, const uint8_t* pats, uint32_t pat_len,
                             uint64_t n_pats, uint64_t* lower, uint64_t* upper);
+/* suffix_array(&seq) and bwt(&seq, &sa) of MGIndex::new (src/index.rs:560-567) for a '$'-terminated text in host
+ * memory: sa_out[n] (and bwt_out[n] unless NULL). */
+MTSVGPU_API int mtsvgpu_suffix_array(int device, const uint8_t* text, uint64_t n, uint32_t* sa_out, uint8_t* bwt_out);
 /* SampledSuffixArray::get (bio 3.0.0; call site src/index.rs:347): text position of each SA row. */
 MTSVGPU_API int mtsvgpu_locate(mtsvgpu_index* ix, const uint64_t* rows, uint64_t n_rows, uint64_t* pos);
 /* Aligner::min_edit_distance (src/align.rs:28-85) for n pairs; pattern i = pats[pat_off[i]..pat_off[i+1]),

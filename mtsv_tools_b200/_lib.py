@@ -45,7 +45,7 @@ class InfoStruct(C.Structure):
     _fields_ = [("text_len", C.c_uint64), ("n_bins", C.c_uint64), ("file_sa_rate", C.c_uint64),
                 ("device_sa_rate", C.c_uint32), ("ktab_k", C.c_uint32), ("device_bytes", C.c_uint64),
                 ("dollar_row", C.c_uint64), ("load_seconds", C.c_double),
-                ("relayout_seconds", C.c_double)]
+                ("relayout_seconds", C.c_double), ("build_seconds", C.c_double)]
 
 
 class StatsStruct(C.Structure):
@@ -57,7 +57,7 @@ class StatsStruct(C.Structure):
 
 # every symbol include/mtsv_b200.h declares
 EXPORTS = [
-    "mtsvgpu_index_open", "mtsvgpu_index_from_parts", "mtsvgpu_index_close", "mtsvgpu_index_get_info",
+    "mtsvgpu_index_open", "mtsvgpu_index_from_parts", "mtsvgpu_index_build", "mtsvgpu_index_write", "mtsvgpu_index_export", "mtsvgpu_suffix_array", "mtsvgpu_index_close", "mtsvgpu_index_get_info",
     "mtsvgpu_bin_batch", "mtsvgpu_bin_batch_pinned", "mtsvgpu_bin_batch_device", "mtsvgpu_last_batch_stats", "mtsvgpu_set_stream",
     "mtsvgpu_set_profiling", "mtsvgpu_backward_search", "mtsvgpu_locate", "mtsvgpu_edit_distance",
     "mtsvgpu_collapse_device", "mtsvgpu_collapse_device_taxid_gi", "mtsvgpu_device_free", "mtsvgpu_free", "mtsvgpu_last_error", "mtsvgpu_launch_count", "mtsvgpu_version",
@@ -91,6 +91,10 @@ def load_library():
     L.mtsvgpu_index_open.argtypes = [C.c_char_p, C.c_int, C.POINTER(OptsStruct), C.POINTER(vp)]
     L.mtsvgpu_index_from_parts.argtypes = [vp, C.c_uint64, vp, C.c_uint64, vp, vp, C.c_uint64,
                                            C.c_uint64, C.c_int, C.POINTER(OptsStruct), C.POINTER(vp)]
+    L.mtsvgpu_index_build.argtypes = [vp, vp, vp, vp, C.c_uint64, C.c_int, C.POINTER(OptsStruct), C.POINTER(vp)]
+    L.mtsvgpu_index_write.argtypes = [vp, C.c_char_p, C.c_uint32, C.c_uint32]
+    L.mtsvgpu_index_export.argtypes = [vp, vp, vp, vp, C.c_uint32]
+    L.mtsvgpu_suffix_array.argtypes = [C.c_int, vp, C.c_uint64, vp, vp]
     L.mtsvgpu_index_close.argtypes = [vp]
     L.mtsvgpu_index_get_info.argtypes = [vp, C.POINTER(InfoStruct)]
     L.mtsvgpu_bin_batch.argtypes = [vp, vp, vp, C.c_uint64, C.POINTER(ParamsStruct),

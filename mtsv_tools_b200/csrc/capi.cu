@@ -35,6 +35,24 @@ int mtsvgpu_index_from_parts(const uint8_t* text, uint64_t n, const mtsvgpu_bin*
                                out);
 }
 
+int mtsvgpu_index_build(const uint8_t* seqs, const uint64_t* seq_off, const uint32_t* gi, const uint32_t* tax_id,
+                        uint64_t n_seqs, int device, const mtsvgpu_index_opts* opts, mtsvgpu_index** out) {
+  return index_build(seqs, seq_off, gi, tax_id, n_seqs, device, opts, out);
+}
+
+int mtsvgpu_index_write(mtsvgpu_index* ix, const char* path, uint32_t sample_interval, uint32_t sa_sample) {
+  return index_write(ix, path, sample_interval, sa_sample);
+}
+
+int mtsvgpu_index_export(mtsvgpu_index* ix, uint8_t* text_out, uint8_t* bwt_out, uint64_t* sa_sample_out,
+                         uint32_t sa_sample) {
+  return index_export(ix, text_out, bwt_out, sa_sample_out, sa_sample);
+}
+
+int mtsvgpu_suffix_array(int device, const uint8_t* text, uint64_t n, uint32_t* sa_out, uint8_t* bwt_out) {
+  return suffix_array_host(device, text, n, sa_out, bwt_out);
+}
+
 void mtsvgpu_index_close(mtsvgpu_index* ix) { index_destroy(ix); }
 
 int mtsvgpu_index_get_info(const mtsvgpu_index* ix, mtsvgpu_index_info* info) {
@@ -48,6 +66,7 @@ int mtsvgpu_index_get_info(const mtsvgpu_index* ix, mtsvgpu_index_info* info) {
   info->dollar_row = ix->ix.dollar_row;
   info->load_seconds = ix->ix.load_seconds;
   info->relayout_seconds = ix->ix.relayout_seconds;
+  info->build_seconds = ix->ix.build_seconds;
   return 0;
 }
 

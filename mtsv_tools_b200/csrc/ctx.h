@@ -90,7 +90,7 @@ struct DeviceIndex {
   uint32_t *bin_start = nullptr, *bin_end = nullptr, *bin_tax = nullptr, *bin_gi = nullptr;
   uint64_t n_bins = 0;
   uint64_t device_bytes = 0;
-  double load_seconds = 0, relayout_seconds = 0;
+  double load_seconds = 0, relayout_seconds = 0, build_seconds = 0;
 
   FmView fm_view() const {
     FmView v;
@@ -204,7 +204,22 @@ struct mtsvgpu_index {
 };
 
 namespace mtsv {
+// the fields of an MGIndex (src/index.rs:60-68) as index.cu takes them
+struct IndexParts {
+  const uint8_t* text = nullptr;  // n bytes incl. the final '$'; host memory unless text_on_device
+  bool text_on_device = false;
+  uint64_t n = 0;
+  const mtsvgpu_bin* bins = nullptr;  // host
+  uint64_t n_bins = 0;
+  const uint8_t* bwt = nullptr;  // n bytes; when bwt_on_device the allocation must extend 64 bytes past n
+  bool bwt_on_device = false;
+  const uint64_t* sa_sample = nullptr;  // host: suffix array rows 0, s, 2s, ... (the file's sample)
+  uint64_t sa_sample_len = 0;
+  uint64_t sa_rate = 0;  // s
+  uint32_t* d_sa_full = nullptr;  // instead of sa_sample: the complete suffix array on the device (adopted)
+};
 // index.cu
+int index_assemble(const IndexParts& parts, int device, const mtsvgpu_index_opts* opts, mtsvgpu_index** out);
 int index_from_host_parts(const uint8_t* text, uint64_t n, const mtsvgpu_bin* bins, uint64_t n_bins,
                           const uint8_t* bwt, const uint64_t* sa_sample, uint64_t sa_sample_len,
                           uint64_t sa_rate, int device, const mtsvgpu_index_opts* opts,
@@ -212,6 +227,12 @@ int index_from_host_parts(const uint8_t* text, uint64_t n, const mtsvgpu_bin* bi
 int index_open_file(const char* path, int device, const mtsvgpu_index_opts* opts,
                     mtsvgpu_index** out);
 void index_destroy(mtsvgpu_index* h);
+// build.cu
+int index_build(const uint8_t* seqs, const uint64_t* seq_off, const uint32_t* gi, const uint32_t* tax_id, uint64_t n_seqs,
+                int device, const mtsvgpu_index_opts* opts, mtsvgpu_index** out);
+int index_write(mtsvgpu_index* h, const char* path, uint32_t sample_interval, uint32_t sa_sample);
+int index_export(mtsvgpu_index* h, uint8_t* text_out, uint8_t* bwt_out, uint64_t* sample_out, uint32_t sa_sample);
+int suffix_array_host(int device, const uint8_t* text, uint64_t n, uint32_t* sa_out, uint8_t* bwt_out);
 // binner.cu
 int bin_batch_device(mtsvgpu_index* h, const uint8_t* d_seqs, const uint64_t* d_seq_off,
                      uint64_t n_reads, const uint64_t* h_seq_off_or_null,

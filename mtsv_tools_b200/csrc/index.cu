@@ -216,6 +216,11 @@ __global__ void ktab_direct_kernel(FmView fm, SaView sv, const uint8_t* __restri
   tab[key] = ktab_direct_entry(fm_locate(fm, sv, e.x, nullptr), text);
 }
 
+__global__ void sa_thin_kernel(const uint32_t* __restrict__ full, uint64_t len, uint32_t rate, uint32_t* __restrict__ out) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < len) out[i] = full[i * rate];
+}
+
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
@@ -302,12 +307,23 @@ static uint32_t auto_ktab_k(uint64_t n) {
   return k;
 }
 
-int index_from_host_parts(const uint8_t* text, uint64_t n, const mtsvgpu_bin* bins, uint64_t n_bins,
-                          const uint8_t* bwt, const uint64_t* sa_sample, uint64_t sa_sample_len,
-                          uint64_t sa_rate, int device, const mtsvgpu_index_opts* opts,
-                          mtsvgpu_index** out) {
+int index_assemble(const IndexParts& parts, int device, const mtsvgpu_index_opts* opts, mtsvgpu_index** out) {
   double t0 = now_s();
-  if (!text || !bins || !bwt || !sa_sample || !out)
+  const uint8_t* text = parts.text;
+  const uint64_t n = parts.n;
+  const mtsvgpu_bin* bins = parts.bins;
+  const uint64_t n_bins = parts.n_bins;
+  const uint8_t* bwt = parts.bwt;
+  const uint64_t* sa_sample = parts.sa_sample;
+  const uint64_t sa_sample_len = parts.sa_sample_len;
+  const uint64_t sa_rate = parts.sa_rate;
+  struct SaGuard {  // a device suffix array handed in is consumed whatever happens
+    uint32_t* p;
+    ~SaGuard() {
+      if (p) cudaFree(p);
+    }
+  } sag{parts.d_sa_full};
+  if (!text || !bins || !bwt || (!sa_sample && !parts.d_sa_full) || !out)
     return set_error(MTSVGPU_EINVAL, "null argument");
   *out = nullptr;
   // ---- validation of the MGIndex fields (SURVEY §8b "loader must assert") ----
@@ -316,10 +332,10 @@ int index_from_host_parts(const uint8_t* text, uint64_t n, const mtsvgpu_bin* bi
     return set_error(MTSVGPU_ELIMIT,
                      "index has %llu symbols; this build keeps 32-bit rows (limit 2^32-64)",
                      (unsigned long long)n);
-  if (text[n - 1] != '$') return set_error(MTSVGPU_EFORMAT, "sequences do not end with '$'");
+  if (!parts.text_on_device && text[n - 1] != '$') return set_error(MTSVGPU_EFORMAT, "sequences do not end with '$'");
   if (sa_rate == 0 || sa_rate > 0xffffffffull)
     return set_error(MTSVGPU_EFORMAT, "bad suffix-array sample rate");
-  if (sa_sample_len != (n + sa_rate - 1) / sa_rate)
+  if (!parts.d_sa_full && sa_sample_len != (n + sa_rate - 1) / sa_rate)
     return set_error(MTSVGPU_EFORMAT, "suffix-array sample has %llu entries, expected %llu",
                      (unsigned long long)sa_sample_len,
                      (unsigned long long)((n + sa_rate - 1) / sa_rate));
@@ -373,8 +389,14 @@ int index_from_host_parts(const uint8_t* text, uint64_t n, const mtsvgpu_bin* bi
 
   // ---- text and bins ----
   MTSV_TRY(dev_alloc(&d.text, n + 16, &d.device_bytes));
-  MTSV_CUDA_TRY(cudaMemcpyAsync(d.text, text, n, cudaMemcpyHostToDevice, st));
+  MTSV_CUDA_TRY(cudaMemcpyAsync(d.text, text, n, cudaMemcpyDefault, st));
   MTSV_CUDA_TRY(cudaMemsetAsync(d.text + n, 0, 16, st));
+  if (parts.text_on_device) {
+    uint8_t last = 0;
+    MTSV_CUDA_TRY(cudaMemcpyAsync(&last, d.text + n - 1, 1, cudaMemcpyDeviceToHost, st));
+    MTSV_CUDA_TRY(cudaStreamSynchronize(st));
+    if (last != '$') return set_error(MTSVGPU_EFORMAT, "sequences do not end with '$'");
+  }
   // 4-bit match classes for the verifier's fast path (+ 2 words of slack: it reads one word ahead)
   d.text4_words = (n + 15) / 16 + 2;
   MTSV_TRY(dev_alloc(&d.text4, d.text4_words, &d.device_bytes));
@@ -419,17 +441,22 @@ int index_from_host_parts(const uint8_t* text, uint64_t n, const mtsvgpu_bin* bi
     }
   } tg{{(void**)&d_bwt, (void**)&d_super_tot, (void**)&d_super_n, (void**)&d_totals,
         (void**)&d_diag, (void**)&d_sample, (void**)&d_ktmp}};
-  MTSV_TRY(dev_alloc(&d_bwt, n + 64, nullptr));
+  // (a BWT that is already on the device is used where it lies: the caller pads it by 64 bytes)
+  const uint8_t* bwt_dev = bwt;
+  if (!parts.bwt_on_device) {
+    MTSV_TRY(dev_alloc(&d_bwt, n + 64, nullptr));
+    bwt_dev = d_bwt;
+  }
   MTSV_TRY(dev_alloc(&d_super_tot, d.n_super * 5, nullptr));
   MTSV_TRY(dev_alloc(&d_super_n, d.n_super, nullptr));
   MTSV_TRY(dev_alloc(&d_totals, 5, nullptr));
   MTSV_TRY(dev_alloc(&d_diag, 1, nullptr));
   MTSV_CUDA_TRY(cudaMemsetAsync(d_diag, 0, sizeof(PackDiag), st));
-  MTSV_CUDA_TRY(cudaMemcpyAsync(d_bwt, bwt, n, cudaMemcpyHostToDevice, st));
+  if (!parts.bwt_on_device) MTSV_CUDA_TRY(cudaMemcpyAsync(d_bwt, bwt, n, cudaMemcpyHostToDevice, st));
   MTSV_CUDA_TRY(cudaStreamSynchronize(st));
   double t_relayout0 = now_s();
 
-  MTSV_LAUNCH(fm_pack_kernel, (unsigned)d.n_super, kBlocksPerSuper, 0, st, d_bwt, n, d.n_blocks,
+  MTSV_LAUNCH(fm_pack_kernel, (unsigned)d.n_super, kBlocksPerSuper, 0, st, bwt_dev, n, d.n_blocks,
               d.blocks, d.n_before, d_super_tot, d_diag);
   MTSV_LAUNCH(fm_super_scan_kernel, 1, 32, 0, st, d_super_tot, d.n_super, d.super, d_super_n,
               d_totals);
@@ -456,13 +483,31 @@ int index_from_host_parts(const uint8_t* text, uint64_t n, const mtsvgpu_bin* bi
   d.C[SYM_T] = (uint32_t)(1 + totals[0] + totals[1] + totals[2] + totals[4]);
   MTSV_TRY(dev_alloc(&d.d_C, 8, &d.device_bytes));
   MTSV_CUDA_TRY(cudaMemcpy(d.d_C, d.C, 5 * sizeof(uint32_t), cudaMemcpyHostToDevice));
-  cudaFree(d_bwt);
+  if (d_bwt) cudaFree(d_bwt);
   d_bwt = nullptr;
 
   // ---- suffix array at the device rate ----
   size_t free_b = 0, total_b = 0;
   MTSV_CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
   uint32_t rate = h->opts.sa_rate;
+  if (parts.d_sa_full) {
+    // built on this device (sufsort.cu): the complete array is adopted as it is, or thinned to the requested rate
+    if (rate <= 1) {
+      d.sa = parts.d_sa_full;
+      sag.p = nullptr;
+      d.sa_rate = 1;
+      d.sa_len = n;
+      d.device_bytes += n * 4;
+    } else {
+      d.sa_rate = rate;
+      d.sa_len = (n + rate - 1) / rate;
+      MTSV_TRY(dev_alloc(&d.sa, d.sa_len, &d.device_bytes));
+      MTSV_LAUNCH(sa_thin_kernel, (unsigned)((d.sa_len + 255) / 256), 256, 0, st, parts.d_sa_full, d.sa_len, rate, d.sa);
+      MTSV_CUDA_TRY(cudaStreamSynchronize(st));
+      cudaFree(sag.p);
+      sag.p = nullptr;
+    }
+  } else {
   if (rate == 0) {
     rate = 1;
     // keep the dense array under a quarter of what is still free (the rest is for batches)
@@ -488,6 +533,7 @@ int index_from_host_parts(const uint8_t* text, uint64_t n, const mtsvgpu_bin* bi
                      diag.sa_mismatch, diag.rows_seen, (unsigned long long)n);
   cudaFree(d_sample);
   d_sample = nullptr;
+  }
 
   // ---- k-mer interval table ----
   uint32_t kk = h->opts.ktab_k;
@@ -536,6 +582,23 @@ int index_from_host_parts(const uint8_t* text, uint64_t n, const mtsvgpu_bin* bi
   guard.h = nullptr;
   *out = h;
   return 0;
+}
+
+int index_from_host_parts(const uint8_t* text, uint64_t n, const mtsvgpu_bin* bins, uint64_t n_bins,
+                          const uint8_t* bwt, const uint64_t* sa_sample, uint64_t sa_sample_len,
+                          uint64_t sa_rate, int device, const mtsvgpu_index_opts* opts,
+                          mtsvgpu_index** out) {
+  if (!sa_sample) return set_error(MTSVGPU_EINVAL, "null argument");
+  IndexParts parts;
+  parts.text = text;
+  parts.n = n;
+  parts.bins = bins;
+  parts.n_bins = n_bins;
+  parts.bwt = bwt;
+  parts.sa_sample = sa_sample;
+  parts.sa_sample_len = sa_sample_len;
+  parts.sa_rate = sa_rate;
+  return index_assemble(parts, device, opts, out);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -88,6 +88,42 @@ class MGIndex:
                                          len(sa_sample), file_sa_rate, device, C.byref(o), C.byref(h)))
         return cls(h.value)
 
+    @classmethod
+    def build(cls, cat, off, gi, taxid, device=0, **opts):
+        """``MGIndex::new`` (src/index.rs:491-582) on the GPU: reference sequences (uint8 concat + uint64
+        offsets[n+1], GI and TaxID per sequence) -> device-resident index, ready to bin.  `cat` may be a numpy
+        array (host) or an int device pointer to the concatenated bytes (e.g. a torch tensor's data_ptr())."""
+        L = _lib.load_library()
+        off = np.ascontiguousarray(off, dtype=np.uint64)
+        gi = np.ascontiguousarray(gi, dtype=np.uint32)
+        taxid = np.ascontiguousarray(taxid, dtype=np.uint32)
+        if isinstance(cat, int):
+            cat_ptr = C.c_void_p(cat)
+        else:
+            cat = np.ascontiguousarray(cat, dtype=np.uint8)
+            cat_ptr = _ptr(cat)
+        h = C.c_void_p()
+        o = cls._opts(**opts)
+        check(L.mtsvgpu_index_build(cat_ptr, _ptr(off), _ptr(gi), _ptr(taxid), len(gi), device, C.byref(o),
+                                    C.byref(h)))
+        return cls(h.value)
+
+    def write(self, path, sample_interval=64, sa_sample=32):
+        """``write_to_file(&index, path)`` (src/io.rs:125-132): the bincode `.index` of this index, with the
+        defaults of mtsv-build's --sample-interval / --sa-sample."""
+        check(_lib.load_library().mtsvgpu_index_write(self._h, os.fsencode(path), sample_interval, sa_sample))
+
+    def export_parts(self, sa_sample=32):
+        """The MGIndex fields back on the host: dict(text, bins, bwt, sa_sample, sa_rate) — what
+        ``from_parts`` (here and in the oracle) takes."""
+        info = self.info()
+        n = info["text_len"]
+        text = np.empty(n, np.uint8)
+        bwt = np.empty(n, np.uint8)
+        sample = np.empty((n + sa_sample - 1) // sa_sample, np.uint64)
+        check(_lib.load_library().mtsvgpu_index_export(self._h, _ptr(text), _ptr(bwt), _ptr(sample), sa_sample))
+        return dict(text=text, bwt=bwt, sa_sample=sample, sa_rate=sa_sample)
+
     def close(self):
         if getattr(self, "_h", None) and self._h.value:
             _lib.load_library().mtsvgpu_index_close(self._h)

@@ -265,6 +265,15 @@ class Index:
         return hits, offs
 
 
+def suffix_array(text):
+    """SA-IS suffix array (uint64) of a uint8 text ending in its unique smallest symbol."""
+    t = np.ascontiguousarray(text, dtype=np.uint8)
+    sa = np.zeros(len(t), dtype=np.uint64)
+    if lib().orc_suffix_array(_ptr(t), len(t), _ptr(sa)) != 0:
+        raise RuntimeError("orc_suffix_array failed")
+    return sa
+
+
 def min_edit_distance(p, t):
     return int(lib().orc_min_edit_distance(bytes(p), len(p), bytes(t), len(t)))
 
