@@ -209,57 +209,105 @@ def measured_peaks():
 
 
 # ------------------------------------------------------------------------------------------------
-# arms
+# shared by both arms
 # ------------------------------------------------------------------------------------------------
-def run_reference_arm(args, cfg, rank, world):
+METRIC = "reads/sec binned (150 bp)"
+
+
+def config_dict(name, cfg, n_reads):
+    """Identical in the GPU arm and the reference arm: what the workload IS (not how an arm ran it)."""
+    return {"workload": cfg["label"], "config": name, "reads_per_gpu_per_step": int(n_reads),
+            "read_len": cfg["read_len"], "index_mbp": cfg["n_seqs"] * cfg["seq_len"] / 1e6,
+            "flags": cfg["flags"] or "defaults", "index_replicated": True,
+            "l2_note": "index and per-step read batch exceed the 126 MB L2 (different reads every sub-batch)"}
+
+
+def make_reads(cfg, ref_t, ref_off, n_reads, seed, dev, ragged=False):
+    """Reads of the workload on `dev`: (uint8 bytes tensor, int64 offsets tensor).  ragged: every read trimmed
+    at its 3' end to a length drawn uniformly from [2/3 L, L] (adapter / quality trimming)."""
+    import torch
+    from mtsv_tools_b200 import synth
+    L = cfg["read_len"]
+    flat = synth.make_reads_torch(ref_t, ref_off, n_reads, L, seed, dev, sub=cfg.get("read_sub", 0.02))
+    if not ragged:
+        return flat, torch.arange(n_reads + 1, dtype=torch.int64, device=dev) * L
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed + 991)
+    lens = torch.randint(2 * L // 3, L + 1, (n_reads,), generator=g, device=dev)
+    keep = torch.arange(L, device=dev)[None, :] < lens[:, None]
+    out = flat.view(n_reads, L)[keep]
+    off = torch.zeros(n_reads + 1, dtype=torch.int64, device=dev)
+    off[1:] = torch.cumsum(lens, 0)
+    return out.contiguous(), off
+
+
+def oracle_rate(oix, pyoracle, reads_np, off_np, params, seconds, cores, counters=None):
+    """Times the CPU restatement on a bounded prefix of (reads_np, off_np): about `seconds` of work."""
+    n_all = len(off_np) - 1
+    probe = min(n_all, 1000)
+    t0 = time.time()
+    oix.bin_reads((reads_np[:int(off_np[probe])], off_np[:probe + 1]), params, threads=cores)
+    rate = probe / max(time.time() - t0, 1e-6)
+    if rate * seconds > 8 * probe:  # a probe that short under-estimates a fast config: probe again, longer
+        probe = min(n_all, 20000)
+        t0 = time.time()
+        oix.bin_reads((reads_np[:int(off_np[probe])], off_np[:probe + 1]), params, threads=cores)
+        rate = probe / max(time.time() - t0, 1e-6)
+    ns = int(min(n_all, max(probe, rate * seconds)))
+    t0 = time.time()
+    h, _ = oix.bin_reads((reads_np[:int(off_np[ns])], off_np[:ns + 1]), params, threads=cores, counters=counters)
+    dt = time.time() - t0
+    return ns, dt, len(h)
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm
+# ------------------------------------------------------------------------------------------------
+def run_reference_arm(args, name, cfg, rank, world):
     """The reference's CPU implementation of the path = the oracle (the Rust binary cannot be built in
     this image: no cargo/rustc), with the reference's own ssw.c, on all host cores."""
     if rank != 0:
         return
     import torch
     from oracle import pyoracle
-    from mtsv_tools_b200 import synth
     cores = os.cpu_count() or 1
-    path, _meta = ensure_index_file(args.config, cfg, 0, 0, lambda: None)
+    path, _meta = ensure_index_file(name, cfg, 0, 0, lambda: None)
     t0 = time.time()
     oix = pyoracle.Index.read(path)
     log("oracle index read from %s in %.1fs" % (path, time.time() - t0))
     text, _bins, ref_off = index_file_text_and_bins(path)
-    parts = {"text": text, "ref_off": ref_off}
-    L = cfg["read_len"]
     dev = "cuda:0" if torch.cuda.is_available() else "cpu"
-    # bounded sample per step: calibrate on 20k reads, aim at ~10 s per step
-    ref_t = torch.from_numpy(np.ascontiguousarray(parts["text"][:-1])).to(dev)
-    calib = synth.make_reads_torch(ref_t, parts["ref_off"], 20000, L, 4, dev, sub=cfg.get("read_sub", 0.02)).cpu().numpy()
-    off = np.arange(20001, dtype=np.uint64) * np.uint64(L)
+    ref_t = torch.from_numpy(np.array(text[:-1])).to(dev)
+    n_reads = args.reads or cfg["reads"]
     params = pyoracle.default_params(**cfg["flags"])
-    t0 = time.time()
-    oix.bin_reads((calib, off), params, threads=cores)
-    rate = 20000 / (time.time() - t0)
-    n_sample = int(min(cfg["reads"], max(20000, rate * args.ref_seconds)))
-    reads = synth.make_reads_torch(ref_t, parts["ref_off"], n_sample, L, 4, dev, sub=cfg.get("read_sub", 0.02)).cpu().numpy()
-    del ref_t
-    off = np.arange(n_sample + 1, dtype=np.uint64) * np.uint64(L)
+    # same generator, same seed as rank 0 of the GPU arm: the sample is a prefix of the very same reads
+    n_gen = int(min(n_reads, 1 << 21))  # (whole generator chunks: the same reads as the GPU arm's first 2 Mi)
+    r_t, o_t = make_reads(cfg, ref_t, ref_off, n_gen, 4, dev)
+    reads, off = r_t.cpu().numpy(), o_t.cpu().numpy().astype(np.uint64)
+    del ref_t, r_t, o_t
+    ns, dt1, _ = oracle_rate(oix, pyoracle, reads, off, params, args.ref_seconds, cores)
+    sub = (reads[:int(off[ns])], off[:ns + 1])
     for _ in range(min(args.warmup, 1)):
-        oix.bin_reads((reads[:20000 * L], off[:20001]), params, threads=cores)
+        oix.bin_reads((reads[:int(off[min(ns, 20000)])], off[:min(ns, 20000) + 1]), params, threads=cores)
     t0 = time.time()
     n_hits = 0
     for _ in range(args.steps):
-        h, o = oix.bin_reads((reads, off), params, threads=cores)
+        h, o = oix.bin_reads(sub, params, threads=cores)
         n_hits = len(h)
     dt = time.time() - t0
-    value = n_sample * args.steps / dt
-    sample = "%d of the workload's %d reads per step (same generator, same index)" % (n_sample, cfg["reads"])
+    value = ns * args.steps / dt
+    sample = "first %d of the step's %d reads (same generator, seed and index file as the GPU arm)" % (ns, n_reads)
     line = {
-        "impl": "reference", "metric": "reads/sec binned (150 bp)", "value": value, "unit": "reads/s",
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "reads/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8/u32 integer", "data": "synthetic",
-        "config": {"workload": cfg["label"], "reads_per_step": n_sample, "threads": cores,
-                   "index_mbp": len(parts["text"]) / 1e6, "hits_per_step": n_hits},
+        "config": config_dict(name, cfg, n_reads),
+        "run": {"sampled_reads_per_step": ns, "threads": cores, "hits_per_step": n_hits,
+                "note": "the CPU arm does not depend on --gpus: one host, all its cores"},
         "cpu_baseline": {"value": value, "unit": "reads/s", "cores": cores, "kind": "port", "sample": sample,
                          "note": "C++ restatement of src/index.rs:258-432 + reference ssw.c (oracle/); "
-                                 "the Rust mtsv-binner cannot be built here"},
+                                 "the Rust mtsv-binner cannot be built here (no cargo/rustc)"},
         "e2e": {"value": value, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -287,179 +335,226 @@ def bind_to_gpu_numa_node(local_rank):
         return "unbound (%s)" % (e,)
 
 
-def run_gpu_arm(args, cfg, rank, world, local_rank):
-    import torch
-    import torch.distributed as dist
-    from mtsv_tools_b200 import MGIndex, Params, synth, load_library
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+class Ctx:
+    def __init__(self, rank, world, local_rank):
+        self.rank, self.world, self.local_rank = rank, world, local_rank
+        self.dev = "cuda:%d" % local_rank
 
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device — this implementation has no CPU path "
-                         "(use --impl reference for the CPU arm)")
-    torch.cuda.set_device(local_rank)
-    dev = "cuda:%d" % local_rank
-    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else "single rank: unbound"
-    log("rank %d: host affinity: %s" % (rank, numa))
-
-    def barrier():
-        if world > 1:
+    def barrier(self):
+        if self.world > 1:
+            import torch.distributed as dist
             dist.barrier()
 
-    lib = load_library()
-    path, build_meta = ensure_index_file(args.config, cfg, local_rank, rank, barrier)
-    t0 = time.time()
-    # the drop-in's own way in: mtsvgpu_index_open on the `.index` file (parse, upload, re-layout; nothing rebuilt)
-    gix = MGIndex.from_file(path, device=local_rank, sa_rate=args.sa_rate, ktab_k=args.ktab_k,
-                            batch_reads=args.batch_reads)
-    info = gix.info()
-    log("rank %d: %s opened in %.1fs (relayout %.2fs), %.2f GB HBM, sa_rate %d, ktab k=%d" %
-        (rank, path, time.time() - t0, info["relayout_seconds"], info["device_bytes"] / 1e9,
-         info["device_sa_rate"], info["ktab_k"]))
-    text, _bins, ref_off = index_file_text_and_bins(path)
-    parts = {"text": text, "ref_off": ref_off}
-    L = cfg["read_len"]
-    n_reads = args.reads or cfg["reads"]
-    ref_t = torch.from_numpy(np.ascontiguousarray(parts["text"][:-1])).to(dev)
-    t0 = time.time()
-    d_reads = synth.make_reads_torch(ref_t, parts["ref_off"], n_reads, L, 4 + 17 * rank, dev,
-                                     sub=cfg.get("read_sub", 0.02))
-    del ref_t
-    d_off = (torch.arange(n_reads + 1, dtype=torch.int64, device=dev) * L)
-    torch.cuda.synchronize()
-    log("rank %d: %d reads generated on device in %.1fs" % (rank, n_reads, time.time() - t0))
-    # pinned host copies for the end-to-end leg
-    h_reads = torch.empty(d_reads.numel(), dtype=torch.uint8, pin_memory=True)
-    h_reads.copy_(d_reads)
-    h_off = torch.empty(n_reads + 1, dtype=torch.int64, pin_memory=True)
-    h_off.copy_(d_off)
-    torch.cuda.synchronize()
-    params = Params(**cfg["flags"])
-    stream = torch.cuda.current_stream()
-    gix.set_stream(stream.cuda_stream)
+    def max_over_ranks(self, vals):
+        if self.world == 1:
+            return [float(v) for v in vals]
+        import torch
+        import torch.distributed as dist
+        t = torch.tensor(list(vals), dtype=torch.float64, device=self.dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(x) for x in t]
 
-    # ---- parity gate on a sample before any timing (rank 0): GPU vs oracle, bit-exact ----
-    parity = None
-    if rank == 0 and not args.no_parity:
-        from oracle import pyoracle
-        ns = min(args.parity_reads, n_reads)
+
+class Workload:
+    """One config on one rank: the index opened from its `.index` file, this rank's reads on the device and in
+    page-locked host memory."""
+
+    def __init__(self, args, name, cfg, ctx, ragged=False, n_reads=None):
+        import torch
+        from mtsv_tools_b200 import MGIndex, Params
+        self.name, self.cfg, self.ctx, self.ragged = name, cfg, ctx, ragged
+        self.path, self.build_meta = ensure_index_file(name, cfg, ctx.local_rank, ctx.rank, ctx.barrier)
         t0 = time.time()
-        oix = pyoracle.Index.read(path)
-        sub = (h_reads.numpy()[:ns * L], h_off.numpy()[:ns + 1].astype(np.uint64))
-        octr = pyoracle.Counters()
-        want_h, want_o = oix.bin_reads(sub, pyoracle.default_params(**cfg["flags"]), threads=os.cpu_count(),
-                                       counters=octr)
-        got_h, got_o = gix.bin_reads(sub, params)
-        gst = gix.last_batch_stats()
-        ok = np.array_equal(want_o, got_o) and all(np.array_equal(want_h[f], got_h[f])
-                                                   for f in ("tax_id", "gi", "offset", "edit"))
-        oc = octr.as_dict()
-        # work cross-check against the reference algorithm's own counters: rows located and candidates verified
-        # (the GPU path verifies all candidates of a strand concurrently where the reference stops early, and
-        # skips strands that cannot be accepted: more N than the edit budget, core.cuh::query_hopeless)
-        parity = {"reads": ns, "hits": int(len(want_h)), "bit_exact": bool(ok),
-                  "rows_located": {"oracle": int(oc["rows_located"]), "gpu": gst["n_seed_hits"]},
-                  "candidates": {"oracle_built": int(oc["candidates"]), "oracle_verified": int(oc["sw_calls"]),
-                                 "gpu_verified": gst["n_candidates"]}}
-        log("parity gate: %s (%.1fs)" % (parity, time.time() - t0))
-        if not ok:
-            raise SystemExit("bench.py: GPU results differ from the oracle — refusing to report a number")
-    else:
-        oix = None
-    barrier()
+        # the drop-in's own way in: mtsvgpu_index_open on the `.index` file (parse, upload, re-layout; nothing rebuilt)
+        self.gix = MGIndex.from_file(self.path, device=ctx.local_rank, sa_rate=args.sa_rate, ktab_k=args.ktab_k,
+                                     batch_reads=args.batch_reads)
+        self.info = self.gix.info()
+        log("rank %d: %s opened in %.1fs (relayout %.2fs), %.2f GB HBM, sa_rate %d, ktab k=%d" %
+            (ctx.rank, self.path, time.time() - t0, self.info["relayout_seconds"], self.info["device_bytes"] / 1e9,
+             self.info["device_sa_rate"], self.info["ktab_k"]))
+        text, _bins, ref_off = index_file_text_and_bins(self.path)
+        self.L = cfg["read_len"]
+        self.n_reads = n_reads or args.reads or cfg["reads"]
+        ref_t = torch.from_numpy(np.array(text[:-1])).to(ctx.dev)
+        t0 = time.time()
+        self.d_reads, self.d_off = make_reads(cfg, ref_t, ref_off, self.n_reads, 4 + 17 * ctx.rank, ctx.dev, ragged)
+        del ref_t
+        torch.cuda.synchronize()
+        log("rank %d: %d reads generated on device in %.1fs" % (ctx.rank, self.n_reads, time.time() - t0))
+        # pinned host copies for the end-to-end leg
+        self.h_reads = torch.empty(self.d_reads.numel(), dtype=torch.uint8, pin_memory=True)
+        self.h_reads.copy_(self.d_reads)
+        self.h_off = torch.empty(self.n_reads + 1, dtype=torch.int64, pin_memory=True)
+        self.h_off.copy_(self.d_off)
+        torch.cuda.synchronize()
+        self.params = Params(**cfg["flags"])
+        self.stream = torch.cuda.current_stream()
+        self.gix.set_stream(self.stream.cuda_stream)
+        self.oix = None
 
-    def step_device():
-        return gix.bin_reads_device(d_reads.data_ptr(), d_off.data_ptr(), n_reads, params)
+    def host_views(self, n=None):
+        n = self.n_reads if n is None else n
+        ho = self.h_off.numpy().view(np.uint64)[:n + 1]
+        return self.h_reads.numpy()[:int(ho[n])], ho
 
-    # ---- device-resident timing ----
-    for _ in range(max(3, args.warmup)):
-        step_device()
-    gix.set_profiling(not args.no_profile)
+    def oracle(self):
+        if self.oix is None:
+            from oracle import pyoracle
+            self.oix = pyoracle.Index.read(self.path)
+        return self.oix
+
+    def close(self):
+        import torch
+        self.gix.close()
+        self.oix = None
+        del self.d_reads, self.d_off, self.h_reads, self.h_off
+        torch.cuda.empty_cache()
+
+
+def parity_gate(args, w):
+    """GPU vs oracle on a prefix of rank 0's reads before any timing: bit-exact or no number."""
+    from oracle import pyoracle
+    ns = min(args.parity_reads, w.n_reads)
+    t0 = time.time()
+    oix = w.oracle()
+    sub = w.host_views(ns)
+    octr = pyoracle.Counters()
+    want_h, want_o = oix.bin_reads(sub, pyoracle.default_params(**w.cfg["flags"]), threads=os.cpu_count(), counters=octr)
+    got_h, got_o = w.gix.bin_reads(sub, w.params)
+    gst = w.gix.last_batch_stats()
+    ok = np.array_equal(want_o, got_o) and all(np.array_equal(want_h[f], got_h[f])
+                                               for f in ("tax_id", "gi", "offset", "edit"))
+    oc = octr.as_dict()
+    # work cross-check against the reference algorithm's own counters: rows located and candidates verified
+    # (the GPU path skips strands that cannot be accepted: more N than the edit budget, core.cuh::query_hopeless)
+    parity = {"reads": ns, "hits": int(len(want_h)), "bit_exact": bool(ok),
+              "rows_located": {"oracle": int(oc["rows_located"]), "gpu": gst["n_seed_hits"]},
+              "candidates": {"oracle_built": int(oc["candidates"]), "oracle_verified": int(oc["sw_calls"]),
+                             "gpu_verified": gst["n_candidates"]}}
+    log("parity gate %s: %s (%.1fs)" % (w.name, parity, time.time() - t0))
+    if not ok:
+        raise SystemExit("bench.py: GPU results differ from the oracle on %s — refusing to report a number" % w.name)
+    return parity
+
+
+def time_device(w, steps, warmup, n=None, profile=True):
+    """Device-resident leg: reads already in HBM, results left there.  Returns (ms, stats, stage_ms, launches)."""
+    import torch
+    from mtsv_tools_b200 import load_library
+    lib = load_library()
+    n = w.n_reads if n is None else n
+
+    def step():
+        return w.gix.bin_reads_device(w.d_reads.data_ptr(), w.d_off.data_ptr(), n, w.params)
+
+    for _ in range(warmup):
+        step()
+    w.gix.set_profiling(profile)
     launches0 = lib.mtsvgpu_launch_count()
-    clocks = ClockSampler(local_rank)
     torch.cuda.synchronize()
-    barrier()
+    w.ctx.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    stage_ms = {}
-    stats = None
-    e0.record(stream)
-    for _ in range(args.steps):
-        _, _, n_hits = step_device()
-        if not args.no_profile:
-            stats = gix.last_batch_stats()
+    stage_ms, stats = {}, None
+    e0.record(w.stream)
+    for _ in range(steps):
+        step()
+        if profile:
+            stats = w.gix.last_batch_stats()
             for k, v in stats["ms"].items():
                 stage_ms[k] = stage_ms.get(k, 0.0) + v
-    e1.record(stream)
+    e1.record(w.stream)
     torch.cuda.synchronize()
-    barrier()
+    w.ctx.barrier()
     ms = e0.elapsed_time(e1)
-    clk = clocks.stop()
     launches = lib.mtsvgpu_launch_count() - launches0
-    gix.set_profiling(False)
+    w.gix.set_profiling(False)
     if stats is None:
-        gix.set_profiling(True)
-        step_device()
-        stats = gix.last_batch_stats()
-        stage_ms = {k: v * args.steps for k, v in stats["ms"].items()}
-        gix.set_profiling(False)
+        stats = w.gix.last_batch_stats()
+    return ms, stats, {k: v / steps for k, v in stage_ms.items()}, int(launches)
 
-    # ---- end-to-end timing: host buffers in, host results out ----
-    # (mtsvgpu_bin_batch_pinned: host buffers in, host results out in the handle's page-locked buffers)
-    hr, ho = h_reads.numpy(), h_off.numpy().view(np.uint64)
+
+def time_e2e(w, steps, n=None):
+    """End-to-end leg: mtsvgpu_bin_batch_pinned — pinned host reads in, hits in pinned host memory out, wall clock."""
+    import torch
+    hr, ho = w.host_views(n)
     for _ in range(2):
-        gix.bin_reads_pinned((hr, ho), params)
+        w.gix.bin_reads_pinned((hr, ho), w.params)
     torch.cuda.synchronize()
-    barrier()
+    w.ctx.barrier()
     t0 = time.perf_counter()
     d2h = 0
-    for _ in range(args.steps):
-        hits, offs = gix.bin_reads_pinned((hr, ho), params)
+    for _ in range(steps):
+        hits, offs = w.gix.bin_reads_pinned((hr, ho), w.params)
         d2h = hits.nbytes + offs.nbytes
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     # bytes the library actually uploaded per call (seq_off of equal-length slices is generated on the device)
-    h2d = int(gix.last_batch_stats().get("h2d_bytes", 0)) or int(hr.nbytes + ho.nbytes)
-    barrier()
+    h2d = int(w.gix.last_batch_stats().get("h2d_bytes", 0)) or int(hr.nbytes + ho.nbytes)
+    w.ctx.barrier()
+    return e2e_s * 1e3, h2d, int(d2h)
 
-    # ---- reduce over ranks: max time ----
-    if world > 1:
-        t = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, e2e_ms = float(t[0]), float(t[1])
-    else:
-        e2e_ms = e2e_s * 1e3
-    if rank != 0:
-        return
-    total_reads = n_reads * world * args.steps
-    value = total_reads / (ms * 1e-3)
-    e2e_value = total_reads / (e2e_ms * 1e-3)
 
-    # ---- roofline ----
-    # achieved = algorithmic bytes per launch / mean launch duration (CUDA events inside the timed region);
-    # algorithmic bytes = per-unit figure of DESIGN.md §3 x units counted by the kernels themselves.
+def h2d_ceiling(w):
+    """What this box gives plain page-locked uploads: every rank copies its reads buffer host -> device with
+    nothing else going on (torch copy_ = one cudaMemcpyAsync), all ranks at once and rank 0 alone."""
+    import torch
+    nbytes = w.h_reads.numel()
+    dst = torch.empty(nbytes, dtype=torch.uint8, device=w.ctx.dev)
+
+    def run(active):
+        for _ in range(1):
+            if active:
+                dst.copy_(w.h_reads, non_blocking=True)
+        torch.cuda.synchronize()
+        w.ctx.barrier()
+        t0 = time.perf_counter()
+        if active:
+            for _ in range(3):
+                dst.copy_(w.h_reads, non_blocking=True)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        w.ctx.barrier()
+        return dt
+
+    dt_all = w.ctx.max_over_ranks([run(True)])[0]
+    dt_alone = w.ctx.max_over_ranks([run(w.ctx.rank == 0)])[0]
+    del dst
+    return {"bytes_per_copy": int(nbytes), "all_ranks_gbs_aggregate": 3 * nbytes * w.ctx.world / dt_all / 1e9,
+            "all_ranks_gbs_per_gpu": 3 * nbytes / dt_all / 1e9, "one_rank_alone_gbs": 3 * nbytes / dt_alone / 1e9,
+            "how": "3 back-to-back cudaMemcpyAsync of the rank's pinned reads buffer, wall clock, max over ranks"}
+
+
+def rooflines(w, stats, per_step, ms_per_step, clocks):
+    """DESIGN.md §4.  Memory kernels: algorithmic bytes per launch / mean launch duration against the measured HBM
+    copy bandwidth.  Verifier: executed ALU-pipe warp instructions / time against the SM integer issue roof."""
     peaks, peak_kind = measured_peaks()
-    S = params.seed_size
-    n_sub = max(1, int(stats.get("n_sub_batches", 0)) or -(-n_reads // (args.batch_reads or (1 << 22))))
-    per_step = {k: v / args.steps for k, v in stage_ms.items()}
+    L = w.L
+    n_sub = max(1, int(stats.get("n_sub_batches", 0)) or 1)
+    window_cols = float(stats["window_bytes"])  # reference columns (bases) the verifier walks, summed over candidates
     alg_bytes = {
         # index sectors needed (k-mer table + FmBlock sectors, counted in-kernel) + 2 plane words in + 8 B out
         "seed_search": 32.0 * stats["rank_queries"] + (48.0 + 8.0) * stats["n_seed_slots"],
         # one 32-B SA sector per located row + 8 B key out
         "locate": (32.0 + 8.0) * stats["n_seed_hits"],
-        # reference window bytes + the read's planes + 4 B result
-        "verify": stats["window_bytes"] + (24.0 * ((L + 63) // 64) + 4.0) * stats["n_candidates"],
+        # the fast verifier reads the 4-bit text (0.5 B per reference column) + the read's planes + 4 B result
+        "verify": 0.5 * window_cols + (24.0 * ((L + 63) // 64) + 4.0) * stats["n_candidates"],
     }
     traffic = {}
-    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    if os.path.exists(tpath):
-        try:
-            traffic = json.load(open(tpath))
-        except Exception:
-            traffic = {}
+    for tp in ("r02_traffic.json", "r01_traffic.json"):
+        tpath = os.path.join(ROOT, "profiles", tp)
+        if os.path.exists(tpath):
+            try:
+                traffic, tsrc = json.load(open(tpath)), tp
+                break
+            except Exception:
+                pass
+    fast = L <= 253 and os.environ.get("MTSV_B200_VERIFIER") != "legacy"
+    kernel_of = {"verify": "verify_warp_kernel" if fast else "verify_kernel"}
 
-    # the verifier has two kernels: verify_warp_kernel for reads <= 256 bases, verify_kernel beyond
-    kernel_of = {"verify": "verify_warp_kernel" if L <= 256 and os.environ.get("MTSV_B200_VERIFIER") != "legacy"
-                 else "verify_kernel"}
-
-    def roof(stage, extra):
+    def hbm_roof(stage, extra):
         ms_k = per_step.get(stage, 0.0)
         ach = alg_bytes[stage] / (ms_k * 1e-3) / 1e9 if ms_k > 0 else 0.0
         kname = kernel_of.get(stage, stage + "_kernel")
@@ -468,73 +563,140 @@ def run_gpu_arm(args, cfg, rank, world, local_rank):
              "frac": ach / peaks["hbm_gbs"], "traffic": t.get("dram_bytes_per_launch"),
              "peak_source": "%s MEASURED_PEAKS.json hbm_gbs (streaming copy)" % peak_kind,
              "algorithmic_bytes_per_launch": alg_bytes[stage] / n_sub, "launches_per_step": n_sub,
-             "kernel_ms_per_launch": ms_k / n_sub, "share_of_step": ms_k / (ms / args.steps)}
+             "kernel_ms_per_launch": ms_k / n_sub, "share_of_step": ms_k / ms_per_step if ms_per_step else None}
         if t:
-            r["ncu"] = {"dram_throughput_pct_of_peak": t.get("dram_throughput_pct_of_peak"),
-                        "alu_pipe_pct_of_peak": t.get("alu_pipe_pct_of_peak"),
-                        "fma_pipe_pct_of_peak": t.get("fma_pipe_pct_of_peak"),
-                        "issue_active_pct": t.get("issue_active_pct"), "source": "profiles/r01_%s.txt" % kname}
+            r["ncu"] = {k: t.get(k) for k in ("dram_throughput_pct_of_peak", "alu_pipe_pct_of_peak",
+                                              "fma_pipe_pct_of_peak", "issue_active_pct")}
+            r["ncu"]["source"] = "profiles/%s" % tsrc
+            if r["traffic"]:
+                r["frac_in_dram_bytes"] = r["traffic"] / (ms_k / n_sub * 1e-3) / 1e9 / peaks["hbm_gbs"] if ms_k else None
         r.update(extra)
         return r
 
-    dom = max(alg_bytes, key=lambda k: per_step.get(k, 0.0))
+    def alu_roof():
+        # SM integer roof: the ALU pipe issues one warp instruction per 2 cycles per scheduler (16 lanes each):
+        # 148 SMs x 4 schedulers x 0.5 x clock warp-instructions/s
+        ms_k = per_step.get("verify", 0.0)
+        kname = kernel_of["verify"]
+        t = traffic.get(kname, {})
+        mhz = (clocks or {}).get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0)
+        peak = 148 * 4 * 0.5 * mhz * 1e6 / 1e9  # G warp-inst/s
+        word_steps = ((L + 63) // 64) * window_cols  # bit-vector word-steps of the full matrices
+        r = {"bound": "alu", "kernel": kname, "unit": "G warp-inst/s (ALU pipe)", "peak": peak,
+             "peak_source": "148 SMs x 4 schedulers x 1 ALU-pipe warp instruction per 2 cycles x %.0f MHz "
+                            "(SM clock sampled under load)" % mhz,
+             "traffic": t.get("dram_bytes_per_launch"), "launches_per_step": n_sub,
+             "kernel_ms_per_launch": ms_k / n_sub, "share_of_step": ms_k / ms_per_step if ms_per_step else None,
+             "algorithmic_word_steps_per_launch": word_steps / n_sub,
+             "algorithmic_word_steps_per_s": word_steps / (ms_k * 1e-3) if ms_k else None,
+             "hbm_view": {"achieved_gbs": alg_bytes["verify"] / (ms_k * 1e-3) / 1e9 if ms_k else None,
+                          "frac_of_hbm_peak": alg_bytes["verify"] / (ms_k * 1e-3) / 1e9 / peaks["hbm_gbs"] if ms_k else None,
+                          "note": "memory is not what bounds this kernel"},
+             "bound_actual": "SM integer issue: the Myers/Hyyro bit-vector recurrence is LOP3/IADD3/SHF on the ALU pipe"}
+        ipc = t.get("alu_warp_inst_per_candidate")
+        if ipc and ms_k:
+            ach = ipc * stats["n_candidates"] / (ms_k * 1e-3) / 1e9
+            r.update({"achieved": ach, "frac": ach / peak,
+                      "achieved_how": "ALU-pipe warp instructions per candidate (ncu, profiles/%s) x candidates "
+                                      "verified in the timed region / kernel time (CUDA events)" % tsrc})
+        elif t.get("alu_pipe_pct_of_peak"):
+            f = t["alu_pipe_pct_of_peak"] / 100.0
+            r.update({"achieved": f * peak, "frac": f,
+                      "achieved_how": "ncu sm__inst_executed_pipe_alu pct_of_peak_sustained_active (profiles/%s)" % tsrc})
+        else:
+            r.update({"achieved": None, "frac": None})
+        return r
+
     notes = {
-        "verify": {"bound_actual": "SM integer issue (ALU pipe), not memory: the Myers/Hyyro bit-vector recurrence "
-                                   "keeps the ALU pipe ~92 % busy (ncu); HBM fraction is reported as the contract asks"},
         "seed_search": {"bound_actual": "HBM random access: every miss fills a whole 128-B line on this part "
-                                        "(tools/randbench2.cu: 8/16/32-B random loads all read ~4 sectors from DRAM), so "
-                                        "DRAM traffic is a multiple of the algorithmic sectors and the kernel sits at ~70 % of "
-                                        "peak DRAM throughput = 5.5 TB/s, the random-line ceiling (ncu)",
+                                        "(tools/randbench2.cu), so DRAM traffic is a multiple of the algorithmic "
+                                        "sectors; frac_in_dram_bytes is the share of the copy peak the kernel really moves",
                         "random_line_ceiling_per_s": 4.6e10},
         "locate": {"bound_actual": "HBM random access (128-B line fills), see seed_search"},
     }
-    roofline = roof(dom, notes.get(dom, {}))
+    dom = max(alg_bytes, key=lambda k: per_step.get(k, 0.0))
+    roofline = alu_roof() if dom == "verify" else hbm_roof(dom, notes.get(dom, {}))
     mem_dom = max(("seed_search", "locate"), key=lambda k: per_step.get(k, 0.0))
-    roofline_memory = roof(mem_dom, notes.get(mem_dom, {}))
+    return roofline, hbm_roof(mem_dom, notes.get(mem_dom, {}))
 
-    # ---- CPU baseline on a bounded sample (rank 0, N=1 only) ----
-    cpu = None
-    if world == 1 and not args.no_cpu_baseline:
-        from oracle import pyoracle
-        if oix is None:
-            oix = pyoracle.Index.read(path)
-        cores = os.cpu_count() or 1
-        op = pyoracle.default_params(**cfg["flags"])
-        t0 = time.time()
-        oix.bin_reads((hr[:20000 * L], ho[:20001]), op, threads=cores)
-        rate = 20000 / (time.time() - t0)
-        ns = int(min(n_reads, max(20000, rate * args.cpu_seconds)))
-        ctr = pyoracle.Counters()
-        t0 = time.time()
-        oix.bin_reads((hr[:ns * L], ho[:ns + 1]), op, threads=cores, counters=ctr)
-        dt = time.time() - t0
-        c = ctr.as_dict()
-        cpu = {"value": ns / dt, "unit": "reads/s", "cores": cores, "kind": "port",
-               "sample": "first %d of the step's %d reads, %.1f s" % (ns, n_reads, dt),
-               "reference_algorithm_sectors_per_read":
-                   (2 * c["bs_steps"] + c["lf_steps"] + c["rows_located"] + c["window_bytes"] / 128.0) / ns}
 
+def cpu_baseline(args, w, seconds):
+    from oracle import pyoracle
+    cores = os.cpu_count() or 1
+    hr, ho = w.host_views(min(w.n_reads, 1 << 21))
+    ctr = pyoracle.Counters()
+    ns, dt, _ = oracle_rate(w.oracle(), pyoracle, hr, ho, pyoracle.default_params(**w.cfg["flags"]), seconds, cores,
+                            counters=ctr)
+    c = ctr.as_dict()
+    return {"value": ns / dt, "unit": "reads/s", "cores": cores, "kind": "port",
+            "sample": "first %d of the step's %d reads, %.1f s" % (ns, w.n_reads, dt),
+            "reference_algorithm_sectors_per_read":
+                (2 * c["bs_steps"] + c["lf_steps"] + c["rows_located"] + c["window_bytes"] / 128.0) / ns}
+
+
+def measure(args, name, cfg, ctx, steps, warmup, ragged=False, n_reads=None, cpu_seconds=None, full=False):
+    """One workload on this rank set: parity gate, device-resident leg, end-to-end leg, CPU baseline.
+    Returns (summary dict on rank 0 / None elsewhere, Workload)."""
+    w = Workload(args, name, cfg, ctx, ragged=ragged, n_reads=n_reads)
+    parity = parity_gate(args, w) if (ctx.rank == 0 and not args.no_parity) else None
+    ctx.barrier()
+    clocks = ClockSampler(ctx.local_rank) if full else None
+    ms, stats, per_step, launches = time_device(w, steps, max(3, warmup), profile=not args.no_profile)
+    clk = clocks.stop() if clocks else None
+    if args.no_profile:
+        _, stats, per_step, _ = time_device(w, 1, 0, profile=True)
+    e2e_ms, h2d, d2h = time_e2e(w, steps)
+    ms, e2e_ms = ctx.max_over_ranks([ms, e2e_ms])
+    total = w.n_reads * ctx.world * steps
+    out = {"value": total / (ms * 1e-3), "ms_per_step": ms / steps,
+           "e2e": {"value": total / (e2e_ms * 1e-3), "unit": "reads/s", "h2d_bytes_per_step": h2d,
+                   "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / steps,
+                   "h2d_gbs_achieved_per_gpu": h2d / (e2e_ms / steps * 1e-3) / 1e9},
+           "gpu_launches": launches, "clocks": clk, "stages_ms_per_step": per_step,
+           "work_per_step": {k: stats[k] for k in ("n_queries", "n_seed_slots", "n_seed_hits", "n_candidates",
+                                                    "n_hits", "window_bytes", "rank_queries", "n_sub_batches")},
+           "parity": parity, "index_load_seconds": w.info["load_seconds"], "index_hbm_gb": w.info["device_bytes"] / 1e9,
+           "device_sa_rate": w.info["device_sa_rate"], "ktab_k": w.info["ktab_k"],
+           "index_build": w.build_meta, "_stats": stats}
+    if ctx.rank == 0 and ctx.world == 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline(args, w, cpu_seconds or args.cpu_seconds)
+    else:
+        out["cpu_baseline"] = None
+    return out, w
+
+
+def strip(d):
+    return {k: v for k, v in d.items() if not k.startswith("_")}
+
+
+def run_gpu_arm(args, name, cfg, ctx):
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — this implementation has no CPU path "
+                         "(use --impl reference for the CPU arm)")
+    torch.cuda.set_device(ctx.local_rank)
+    numa = bind_to_gpu_numa_node(ctx.local_rank) if ctx.world > 1 else "single rank: unbound"
+    log("rank %d: host affinity: %s" % (ctx.rank, numa))
+    world = ctx.world
+    m, w = measure(args, name, cfg, ctx, args.steps, args.warmup, full=True)
+    roofline, roofline_mem = rooflines(w, m["_stats"], m["stages_ms_per_step"], m["ms_per_step"], m["clocks"])
+    L = w.L
     line = {
-        "metric": "reads/sec binned (150 bp)", "value": value, "unit": "reads/s", "n_gpus": world,
-        "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps,
+        "metric": METRIC, "value": m["value"], "unit": "reads/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": m["ms_per_step"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/u32 integer",
-        "data": "synthetic",
-        "config": {"workload": cfg["label"], "reads_per_gpu_per_step": n_reads, "index_mbp": info["text_len"] / 1e6,
-                   "index_replicated": True, "device_sa_rate": info["device_sa_rate"], "ktab_k": info["ktab_k"],
-                   "index_hbm_gb": info["device_bytes"] / 1e9, "batch_reads": args.batch_reads or "default (1<<22 device-resident; host input: ramped slices up to 1<<20 on two lanes)",
-                   "l2_note": "index (>= 1 GB at cfg2) and per-step read batch exceed the 126 MB L2",
-                   "hits_per_step": int(stats["n_hits"]), "profiling_events": not args.no_profile},
-        "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms / args.steps},
-        "gpu_launches": int(launches), "clocks": clk, "roofline": roofline,
-        "roofline_memory_kernel": roofline_memory, "cpu_baseline": cpu,
-        "stages_ms_per_step": per_step,
-        "work_per_step": {k: stats[k] for k in ("n_queries", "n_seed_slots", "n_seed_hits", "n_candidates",
-                                                 "n_hits", "window_bytes", "rank_queries")},
-        "parity": parity, "index_load_seconds": info["load_seconds"],
-        "index_build": dict(build_meta, note="mtsvgpu_index_build + mtsvgpu_index_write on this box (device suffix sort); "
-                                             "index_load_seconds = mtsvgpu_index_open of that file"),
+        "data": "synthetic", "config": config_dict(name, cfg, w.n_reads),
+        "run": {"device_sa_rate": m["device_sa_rate"], "ktab_k": m["ktab_k"], "index_hbm_gb": m["index_hbm_gb"],
+                "batch_reads": args.batch_reads or "default (1<<22 device-resident; host input: ramped slices up to 1<<20 on two lanes)",
+                "hits_per_step": int(m["work_per_step"]["n_hits"]), "profiling_events": not args.no_profile},
+        "e2e": m["e2e"], "gpu_launches": m["gpu_launches"], "clocks": m["clocks"], "roofline": roofline,
+        "roofline_memory_kernel": roofline_mem, "cpu_baseline": m["cpu_baseline"],
+        "stages_ms_per_step": m["stages_ms_per_step"], "work_per_step": m["work_per_step"],
+        "parity": m["parity"], "index_load_seconds": m["index_load_seconds"],
+        "index_build": dict(m["index_build"], note="mtsvgpu_index_build + mtsvgpu_index_write on this box (device "
+                            "suffix sort); index_load_seconds = mtsvgpu_index_open of that file"),
     }
+    cpu = m["cpu_baseline"]
     if cpu:
         # SURVEY §8(d): the layout-independent work of the reference algorithm (32-byte index sectors per read,
         # counted by the instrumented oracle) over this implementation's time — it exceeds the HBM peak because the
@@ -542,87 +704,61 @@ def run_gpu_arm(args, cfg, rank, world, local_rank):
         spr = cpu["reference_algorithm_sectors_per_read"]
         line["reference_work_equivalent"] = {
             "sectors_per_read": spr, "bytes_per_read": 32.0 * spr + 2 * L,
-            "gbs_at_value": (32.0 * spr + 2 * L) * value / 1e9, "gbs_at_e2e": (32.0 * spr + 2 * L) * e2e_value / 1e9}
-    print(json.dumps(line), flush=True)
+            "gbs_at_value": (32.0 * spr + 2 * L) * m["value"] / 1e9,
+            "gbs_at_e2e": (32.0 * spr + 2 * L) * m["e2e"]["value"] / 1e9}
+
+    # ---- what bounds the end-to-end number: the box's own upload ceiling, measured here ----
+    if not args.only_main:
+        line["h2d"] = h2d_ceiling(w)
+        line["h2d"]["e2e_achieved_gbs_aggregate"] = m["e2e"]["h2d_gbs_achieved_per_gpu"] * world
+
+    # ---- strong scaling: the workload's reads (10 M at cfg2) split N ways, as BASELINE configs[1] states ----
+    if world > 1 and not args.only_main:
+        n_s = max(1, (args.reads or cfg["reads"]) // world)
+        ms_s, _, _, _ = time_device(w, args.steps, 3, n=n_s, profile=False)
+        e2e_s, h2d_s, _ = time_e2e(w, args.steps, n=n_s)
+        ms_s, e2e_s = ctx.max_over_ranks([ms_s, e2e_s])
+        tot = n_s * world * args.steps
+        line["strong_scaling"] = {
+            "reads_total_per_step": n_s * world, "reads_per_gpu_per_step": n_s,
+            "value": tot / (ms_s * 1e-3), "ms_per_step": ms_s / args.steps,
+            "e2e_value": tot / (e2e_s * 1e-3), "e2e_ms_per_step": e2e_s / args.steps,
+            "note": "same index, the step's reads divided among the ranks; compare with the N=1 line's value / e2e"}
+    w.close()
+
+    # ---- the other BASELINE configs and a ragged-read batch, shorter runs attached to the same line (N=1) ----
+    if world == 1 and name == "cfg2" and not args.only_main:
+        others = {}
+        rw_m, rw = measure(args, "cfg2", cfg, ctx, max(2, args.steps // 2), 3, ragged=True, n_reads=args.reads or cfg["reads"],
+                           cpu_seconds=0)
+        rw.close()
+        rw_m.pop("cpu_baseline", None)
+        others["cfg2_ragged"] = dict(strip(rw_m), note="cfg2 with every read trimmed to 100-150 bases: per-slot offsets, "
+                                     "non-uniform verifier, seq_off uploaded")
+        for oname in ("cfg1", "cfg4", "cfg5"):
+            try:
+                om, ow = measure(args, oname, CONFIGS[oname], ctx, max(2, args.steps // 2), 3, cpu_seconds=args.other_cpu_seconds)
+                ow.close()
+                others[oname] = dict(strip(om), config=config_dict(oname, CONFIGS[oname], ow.n_reads))
+            except SystemExit:
+                raise
+            except Exception as e:  # a side config must not cost the headline line
+                others[oname] = {"error": repr(e)}
+        line["other_configs"] = others
+
+    if world > 1 and not args.only_main and not args.no_chunk:
+        try:
+            line["chunk_sharded"] = run_chunk_arm(args, ctx, as_dict=True)
+        except SystemExit:
+            raise
+        except Exception as e:
+            line["chunk_sharded"] = {"error": repr(e)}
+    if ctx.rank == 0:
+        print(json.dumps(line), flush=True)
 
 
-def run_chunk_arm(args, cfg, rank, world, local_rank):
-    """BASELINE config 3, scaled: every rank holds a DIFFERENT ~1 Gbp chunk, every read visits every chunk,
-    per-read hit lists are exchanged over NCCL (all_to_all by read range) and merged on the device by the
-    mtsv-collapse rule (min edit per TaxID).  value = reads/s binned against ALL chunks."""
-    import torch
-    import torch.distributed as dist
-    from mtsv_tools_b200 import MGIndex, Params, synth, load_library, chunked
-
-    torch.cuda.set_device(local_rank)
-    dev = "cuda:%d" % local_rank
-    lib = load_library()
-    # each rank builds / loads its own chunk (seed 5 + rank), chunk 0 provides the reads for everybody
-    name = "%s_chunk%d" % (args.config, rank)
-    parts = get_index_parts(name, dict(cfg, seed=5 + rank), dev, 0, 1, lambda: None)
-    if world > 1:
-        dist.barrier()
-    parts0 = parts if rank == 0 else get_index_parts("%s_chunk0" % args.config, dict(cfg, seed=5), dev, 1, 1,
-                                                     lambda: None)
-    gix = MGIndex.from_parts(parts["text"], parts["bins"], parts["bwt"], parts["sa_sample"], 32, device=local_rank,
-                             sa_rate=args.sa_rate, ktab_k=args.ktab_k, batch_reads=args.batch_reads)
-    L = cfg["read_len"]
-    n_reads = args.reads or cfg["reads"]
-    ref_t = torch.from_numpy(parts0["text"][:-1]).to(dev)
-    d_reads = synth.make_reads_torch(ref_t, parts0["ref_off"], n_reads, L, 4, dev)
-    del ref_t
-    d_off = torch.arange(n_reads + 1, dtype=torch.int64, device=dev) * L
-    torch.cuda.synchronize()
-    params = Params(**cfg["flags"])
-    stream = torch.cuda.current_stream()
-    gix.set_stream(stream.cuda_stream)
-
-    def step():
-        return chunked.bin_reads_chunk_sharded(gix, d_reads, d_off, n_reads, params, local_rank)
-
-    for _ in range(max(3, args.warmup)):
-        pairs, offs = step()
-    launches0 = lib.mtsvgpu_launch_count()
-    clocks = ClockSampler(local_rank)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for _ in range(args.steps):
-        pairs, offs = step()
-    e1.record(stream)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    ms = e0.elapsed_time(e1)
-    clk = clocks.stop()
-    launches = lib.mtsvgpu_launch_count() - launches0
-    t = torch.tensor([ms, float(pairs.shape[0])], dtype=torch.float64, device=dev)
-    if world > 1:
-        tm = t.clone()
-        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-        ts = t.clone()
-        dist.all_reduce(ts, op=dist.ReduceOp.SUM)
-        ms, total_pairs = float(tm[0]), float(ts[1])
-    else:
-        total_pairs = float(t[1])
-    if rank != 0:
-        return
-    value = n_reads * args.steps / (ms * 1e-3)
-    line = {
-        "metric": "reads/sec binned (150 bp)", "value": value, "unit": "reads/s", "n_gpus": world,
-        "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/u32 integer",
-        "data": "synthetic",
-        "config": {"workload": "cfg3 (scaled): %d chunks x %.1f Gbp chunk-sharded, every read visits every chunk, "
-                               "NCCL all_to_all of hit lists + device collapse (min edit per TaxID)"
-                               % (world, len(parts["text"]) / 1e9),
-                   "reads_per_step": n_reads, "collapsed_taxid_hits_per_step": total_pairs,
-                   "scaling_note": "reference size grows with N (one chunk per GPU); reads per step fixed"},
-        "e2e": None, "gpu_launches": int(launches), "clocks": clk, "roofline": None, "cpu_baseline": None,
-    }
-    print(json.dumps(line), flush=True)
+def run_chunk_arm(args, ctx, as_dict=False):
+    raise NotImplementedError("rewritten with the fused exchange (see below)")
 
 
 def main():
@@ -639,19 +775,24 @@ def main():
     ap.add_argument("--ktab-k", type=int, default=0)
     ap.add_argument("--batch-reads", type=int, default=0)
     ap.add_argument("--parity-reads", type=int, default=50000)
-    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--other-cpu-seconds", type=float, default=5.0)
     ap.add_argument("--ref-seconds", type=float, default=10.0)
+    ap.add_argument("--chunk-mbp", type=int, default=0, help="chunk mode: Mbp per chunk (default 4000 at 8 GPUs)")
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-chunk", action="store_true", help="N>1: skip the chunk-sharded leg")
+    ap.add_argument("--only-main", action="store_true", help="only the headline workload (no side configs / legs)")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
-        run_reference_arm(args, cfg, rank, world)
+        run_reference_arm(args, args.config, cfg, rank, world)
         return
+    ctx = Ctx(rank, world, local_rank)
     if world > 1 or args.mode == "chunk":
         import torch
         import torch.distributed as dist
@@ -661,9 +802,9 @@ def main():
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local_rank))
     try:
         if args.mode == "chunk":
-            run_chunk_arm(args, cfg, rank, world, local_rank)
+            run_chunk_arm(args, ctx)
         else:
-            run_gpu_arm(args, cfg, rank, world, local_rank)
+            run_gpu_arm(args, args.config, cfg, ctx)
     finally:
         if world > 1 or args.mode == "chunk":
             import torch.distributed as dist

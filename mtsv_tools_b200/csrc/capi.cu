@@ -302,6 +302,8 @@ static int bin_batch_host(mtsvgpu_index* ix, const uint8_t* seqs, const uint64_t
   uint64_t* h_off = nullptr;
   const size_t hb = (n_hits ? n_hits : 1) * sizeof(mtsvgpu_hit), ob = (n_reads + 1) * sizeof(uint64_t);
   if (pinned_result) {
+    // slices may still be on their way into the buffers ensure_pinned is about to replace
+    MTSV_CUDA_TRY(cudaStreamSynchronize(ix->copy_out_stream));
     MTSV_TRY(ensure_pinned(&ix->pin_hits, &ix->pin_hits_cap, hb));
     MTSV_TRY(ensure_pinned(&ix->pin_off, &ix->pin_off_cap, ob));
     h_hits = (mtsvgpu_hit*)ix->pin_hits;
