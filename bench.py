@@ -758,7 +758,178 @@ def run_gpu_arm(args, name, cfg, ctx):
 
 
 def run_chunk_arm(args, ctx, as_dict=False):
-    raise NotImplementedError("rewritten with the fused exchange (see below)")
+    """BASELINE config 3: every rank holds a DIFFERENT MG-index chunk (4 Gbp by default: rows beyond 2^31), every
+    read visits every chunk, the per-read TaxID sets are brought together over NVLink by the library's own exchange
+    (mtsvgpu_bin_batch_chunked: peer-memory stores + flag barrier + device collapse, min edit per TaxID).
+    value = reads/s binned against ALL chunks.  With --hybrid-chunks C < N the N ranks form N/C groups of C chunks,
+    each group working on its own shard of the reads."""
+    import torch
+    import torch.distributed as dist
+    from mtsv_tools_b200 import MGIndex, Params, load_library, chunked
+    from mtsv_tools_b200._lib import LibraryError
+    rank, world, dev = ctx.rank, ctx.world, ctx.dev
+    torch.cuda.set_device(ctx.local_rank)
+    lib = load_library()
+    n_chunks = args.hybrid_chunks or world
+    groups = chunked.hybrid_groups(world, n_chunks)
+    shard, chunk_id = rank // n_chunks, rank % n_chunks
+    group = None
+    if len(groups) > 1:
+        for g in groups:  # (every rank creates every group, as torch.distributed requires)
+            pg = dist.new_group(g)
+            if rank in g:
+                group = pg
+    chunk_mbp = args.chunk_mbp or 4000
+    base = CONFIGS["cfg2"]
+    cfgc = dict(base, n_seqs=max(1, chunk_mbp // 5), seed=5 + chunk_id)
+    L = base["read_len"]
+    n_reads = args.reads or base["reads"]  # per group per step
+    # ---- this rank's chunk, built where it will be used (nothing goes through the host) ----
+    t0 = time.time()
+    cat, off, gi, tax = make_reference_torch(cfgc, cfgc["seed"], dev)
+    tax = tax + np.uint32(100000 * chunk_id)  # distinct TaxIDs per chunk, except ...
+    tax[: len(tax) // 10] = (1000 + np.arange(len(tax) // 10)).astype(np.uint32)  # ... a tenth shared with chunk 0's
+    torch.cuda.synchronize()
+    t_gen = time.time() - t0
+    # chunk 0 of each group provides the reads for its group
+    src_rank = shard * n_chunks
+    d_reads = torch.empty(n_reads * L, dtype=torch.uint8, device=dev)
+    if chunk_id == 0:
+        r_t, _ = make_reads(base, cat, off, n_reads, 4 + 17 * shard, dev)
+        d_reads.copy_(r_t)
+        del r_t
+    torch.cuda.empty_cache()
+    t0 = time.time()
+    gix = MGIndex.build(cat.data_ptr(), off, gi, tax, device=ctx.local_rank, sa_rate=args.sa_rate, ktab_k=args.ktab_k,
+                        batch_reads=args.batch_reads)
+    del cat
+    torch.cuda.empty_cache()
+    info = gix.info()
+    log("rank %d: chunk %d (%.2f Gbp) generated in %.1fs, built in %.1fs (suffix array + BWT %.1fs), %.1f GB HBM, k=%d" %
+        (rank, chunk_id, info["text_len"] / 1e9, t_gen, time.time() - t0, info["build_seconds"],
+         info["device_bytes"] / 1e9, info["ktab_k"]))
+    if world > 1:
+        dist.broadcast(d_reads, src=src_rank, group=group)
+    d_off = torch.arange(n_reads + 1, dtype=torch.int64, device=dev) * L
+    torch.cuda.synchronize()
+    params = Params(**base["flags"])
+    stream = torch.cuda.current_stream()
+    gix.set_stream(stream.cuda_stream)
+    n_local = -(-n_reads // n_chunks)
+    comm = chunked.ChunkComm(ctx.local_rank, max_local_reads=n_local, max_hits_per_source=4 * n_local + (1 << 20),
+                             group=group)
+
+    # ---- parity gate on a sample, before any timing ----
+    parity = None
+    if not args.no_parity:
+        from oracle import pyoracle
+        ns = min(20000, n_reads)
+        sub_r, sub_o = d_reads[: ns * L], d_off[: ns + 1]
+        first, pairs, offs = comm.bin_reads_tensors(gix, sub_r, sub_o, ns, params)
+        fused = (first, pairs.cpu().numpy().astype(np.uint32), offs.cpu().numpy().astype(np.uint64))
+        h_sub = (sub_r.cpu().numpy(), sub_o.cpu().numpy().astype(np.uint64))
+        local_h, local_o = gix.bin_reads(h_sub, params)  # this chunk alone, through the plain host entry point
+        gathered = [None] * n_chunks if chunk_id == 0 else None
+        dist.gather_object((fused, local_h, local_o), gathered, dst=src_rank, group=group) if world > 1 else None
+        if world == 1:
+            gathered = [(fused, local_h, local_o)]
+        ok_merge, ok_chunk, t_or = True, None, 0.0
+        if chunk_id == 0:
+            # (1) exchange + merge == mtsv-collapse's rule (oracle restatement) over the chunks' own hit lists
+            want_pairs, want_off = pyoracle.collapse_taxid([(g[1], g[2]) for g in gathered])
+            bounds = chunked.read_ranges(ns, n_chunks)
+            for r, g in enumerate(gathered):
+                f, pr, of = g[0]
+                a, e = int(want_off[bounds[r]]), int(want_off[bounds[r + 1]])
+                ok_merge &= f == bounds[r] and np.array_equal(pr, want_pairs[a:e]) and \
+                    np.array_equal(of, want_off[bounds[r]:bounds[r + 1] + 1] - want_off[bounds[r]])
+        if rank == 0 and not args.no_chunk_oracle:
+            # (2) this chunk's hits == the CPU oracle on the very same index fields (rows beyond 2^31 at 4 Gbp)
+            t1 = time.time()
+            parts = gix.export_parts(32)
+            b_gi, b_tax = gi, tax
+            order = np.argsort(b_tax, kind="stable")
+            st = np.zeros(len(order), np.uint64)
+            lens = (off[1:] - off[:-1])[order]
+            st[1:] = np.cumsum(lens[:-1], dtype=np.uint64)
+            oix = pyoracle.Index.from_parts(parts["text"], (b_gi[order], b_tax[order], st, st + lens), parts["bwt"],
+                                            parts["sa_sample"], 32)
+            del parts
+            want_h, want_o = oix.bin_reads(h_sub, pyoracle.default_params(**base["flags"]), threads=os.cpu_count())
+            ok_chunk = bool(np.array_equal(want_o, local_o) and all(np.array_equal(want_h[f], local_h[f])
+                                                                    for f in ("tax_id", "gi", "offset", "edit")))
+            del oix
+            t_or = time.time() - t1
+        flags = torch.tensor([1.0 if ok_merge else 0.0, 1.0 if ok_chunk in (None, True) else 0.0], device=dev)
+        if world > 1:
+            dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+        parity = {"reads": ns, "merged_pairs": int(len(fused[1])), "exchange_and_merge_bit_exact": bool(flags[0] > 0),
+                  "chunk0_vs_oracle_bit_exact": ok_chunk, "chunk0_hits": int(len(local_h)), "oracle_gate_seconds": t_or}
+        log("rank %d: chunk parity gate: %s" % (rank, parity))
+        if not (flags[0] > 0 and flags[1] > 0):
+            raise SystemExit("bench.py: chunk-sharded results differ from the oracle — refusing to report a number")
+
+    def step():
+        return comm.bin_reads(gix, d_reads.data_ptr(), d_off.data_ptr(), n_reads, params)
+
+    def step_local():
+        return gix.bin_reads_device(d_reads.data_ptr(), d_off.data_ptr(), n_reads, params)
+
+    def timed(fn, steps):
+        torch.cuda.synchronize()
+        ctx.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            r = fn()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ctx.barrier()
+        return e0.elapsed_time(e1), r
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    launches0 = lib.mtsvgpu_launch_count()
+    clocks = ClockSampler(ctx.local_rank)
+    ms, last = timed(step, args.steps)
+    clk = clocks.stop()
+    launches = lib.mtsvgpu_launch_count() - launches0
+    ms_local, _ = timed(step_local, args.steps)
+    n_pairs = float(last[4])
+    ms, ms_local = ctx.max_over_ranks([ms, ms_local])
+    if world > 1:
+        t = torch.tensor([n_pairs], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        n_pairs = float(t[0])
+    comm.close()
+    gix.close()
+    del d_reads, d_off
+    torch.cuda.empty_cache()
+    n_shards = world // n_chunks
+    out = {
+        "value": n_reads * n_shards * args.steps / (ms * 1e-3), "unit": "reads/s (each read binned against all %d chunks)" % n_chunks,
+        "ms_per_step": ms / args.steps, "exchange_and_merge_ms": (ms - ms_local) / args.steps,
+        "local_binning_ms": ms_local / args.steps,
+        "workload": "cfg3: %d chunks x %.1f Gbp%s, every read visits every chunk, hits stored into the owning rank's "
+                    "buffer over NVLink peer memory (own kernels, CUDA IPC), one flag barrier, device collapse "
+                    "(min edit per TaxID)" % (n_chunks, info["text_len"] / 1e9,
+                                              " x %d read shards (hybrid)" % n_shards if n_shards > 1 else ""),
+        "reads_per_step": n_reads * n_shards, "reference_gbp_total": n_chunks * info["text_len"] / 1e9,
+        "collapsed_taxid_hits_per_step": n_pairs, "chunk_build_seconds": info["build_seconds"],
+        "chunk_hbm_gb": info["device_bytes"] / 1e9, "gpu_launches": int(launches), "clocks": clk, "parity": parity,
+        "scaling_note": "reference size grows with the number of chunks (one chunk per GPU); reads per step fixed",
+    }
+    if as_dict:
+        return out
+    if rank == 0:
+        line = {"metric": METRIC, "value": out["value"], "unit": "reads/s", "n_gpus": world, "steps": args.steps,
+                "warmup": max(3, args.warmup), "ms_per_step": out["ms_per_step"], "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "u8/u32 integer", "data": "synthetic",
+                "config": {"workload": out["workload"], "reads_per_step": out["reads_per_step"]},
+                "chunk_sharded": out, "e2e": None, "gpu_launches": int(launches), "clocks": clk, "roofline": None,
+                "cpu_baseline": None}
+        print(json.dumps(line), flush=True)
+    return out
 
 
 def main():
@@ -778,11 +949,13 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--other-cpu-seconds", type=float, default=5.0)
     ap.add_argument("--ref-seconds", type=float, default=10.0)
-    ap.add_argument("--chunk-mbp", type=int, default=0, help="chunk mode: Mbp per chunk (default 4000 at 8 GPUs)")
+    ap.add_argument("--chunk-mbp", type=int, default=0, help="chunk mode: Mbp per chunk (default 4000)")
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-chunk", action="store_true", help="N>1: skip the chunk-sharded leg")
+    ap.add_argument("--no-chunk-oracle", action="store_true", help="chunk mode: skip the CPU-oracle check of chunk 0")
+    ap.add_argument("--hybrid-chunks", type=int, default=0, help="chunk mode: chunks per copy of the database (< N: hybrid)")
     ap.add_argument("--only-main", action="store_true", help="only the headline workload (no side configs / legs)")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]

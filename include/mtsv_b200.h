@@ -214,6 +214,33 @@ MTSVGPU_API int mtsvgpu_collapse_device_taxid_gi(int device, void* stream, uint3
                             uint64_t n_reads, mtsvgpu_hit** d_out, uint64_t** d_out_off, uint64_t* n_out);
 MTSVGPU_API void mtsvgpu_device_free(void* d_ptr);
 
+/* ---- chunk-sharded batches (BASELINE config 3): GPU g holds MG-index chunk g, every read visits every chunk, the
+ * per-read TaxID sets are gathered over NVLink into the collapse step.  One process per GPU on one NVSwitch box.
+ * The exchange is done by this library's own kernels through peer memory: each rank's communicator owns one device
+ * buffer that its peers map (CUDA IPC).  Setup is mediated by the host, which only has to move `world` opaque
+ * 128-byte handles between the ranks (any channel: MPI, a pipe, torch.distributed ...):
+ *     mtsvgpu_comm_create(...)  on every rank  -> its handle
+ *     (host: all-gather the handles, in rank order)
+ *     mtsvgpu_comm_connect(comm, all_handles)
+ * max_local_reads: upper bound on ceil(n_reads / world) of any batch; max_hits_per_source: upper bound on the hits
+ * one chunk produces for one rank's range of reads in one batch (a batch that exceeds it fails on every rank with
+ * MTSVGPU_ELIMIT; nothing is truncated).  Destroy only after every rank has finished its last batch. */
+#define MTSVGPU_COMM_HANDLE_BYTES 128
+typedef struct mtsvgpu_comm mtsvgpu_comm;
+MTSVGPU_API int mtsvgpu_comm_create(int device, uint32_t rank, uint32_t world, uint64_t max_local_reads,
+                        uint64_t max_hits_per_source, mtsvgpu_comm** out, uint8_t* handle_out);
+MTSVGPU_API int mtsvgpu_comm_connect(mtsvgpu_comm* comm, const uint8_t* all_handles);
+MTSVGPU_API void mtsvgpu_comm_destroy(mtsvgpu_comm* comm);
+/* One batch.  Every rank passes the SAME n_reads reads (device memory, as for mtsvgpu_bin_batch_device) and its own
+ * chunk's index.  On return this rank holds, for the reads [*first_read, *first_read + *n_local_reads) (the rank-th
+ * of `world` contiguous ranges), what mtsv-collapse leaves of the per-chunk results (src/collapse.rs:597-602,
+ * :278-279): each TaxID once with its minimum edit, by ascending TaxID, CSR by read.  The device pointers are owned
+ * by the communicator and stay valid until its next batch. */
+MTSVGPU_API int mtsvgpu_bin_batch_chunked(mtsvgpu_index* ix, mtsvgpu_comm* comm, const uint8_t* d_seqs,
+                              const uint64_t* d_seq_off, uint64_t n_reads, const mtsvgpu_params* params,
+                              uint64_t* first_read, uint64_t* n_local_reads, const mtsvgpu_taxhit** d_out,
+                              const uint64_t** d_out_off, uint64_t* n_out);
+
 MTSVGPU_API void mtsvgpu_free(void* p);
 MTSVGPU_API const char* mtsvgpu_last_error(void);
 /* Number of kernels this library has launched in this process (all handles). */

@@ -60,7 +60,7 @@ EXPORTS = [
     "mtsvgpu_index_open", "mtsvgpu_index_from_parts", "mtsvgpu_index_build", "mtsvgpu_index_write", "mtsvgpu_index_export", "mtsvgpu_suffix_array", "mtsvgpu_index_close", "mtsvgpu_index_get_info",
     "mtsvgpu_bin_batch", "mtsvgpu_bin_batch_pinned", "mtsvgpu_bin_batch_device", "mtsvgpu_last_batch_stats", "mtsvgpu_set_stream",
     "mtsvgpu_set_profiling", "mtsvgpu_backward_search", "mtsvgpu_locate", "mtsvgpu_edit_distance",
-    "mtsvgpu_collapse_device", "mtsvgpu_collapse_device_taxid_gi", "mtsvgpu_device_free", "mtsvgpu_free", "mtsvgpu_last_error", "mtsvgpu_launch_count", "mtsvgpu_version",
+    "mtsvgpu_collapse_device", "mtsvgpu_collapse_device_taxid_gi", "mtsvgpu_device_free", "mtsvgpu_comm_create", "mtsvgpu_comm_connect", "mtsvgpu_comm_destroy", "mtsvgpu_bin_batch_chunked", "mtsvgpu_free", "mtsvgpu_last_error", "mtsvgpu_launch_count", "mtsvgpu_version",
 ]
 
 
@@ -112,6 +112,11 @@ def load_library():
                                           C.POINTER(vp), C.POINTER(vp), u64p]
     L.mtsvgpu_collapse_device_taxid_gi.argtypes = L.mtsvgpu_collapse_device.argtypes
     L.mtsvgpu_device_free.argtypes = [vp]
+    L.mtsvgpu_comm_create.argtypes = [C.c_int, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint64, C.POINTER(vp), vp]
+    L.mtsvgpu_comm_connect.argtypes = [vp, vp]
+    L.mtsvgpu_comm_destroy.argtypes = [vp]
+    L.mtsvgpu_bin_batch_chunked.argtypes = [vp, vp, vp, vp, C.c_uint64, C.POINTER(ParamsStruct), u64p, u64p,
+                                            C.POINTER(vp), C.POINTER(vp), u64p]
     L.mtsvgpu_edit_distance.argtypes = [C.c_int, vp, vp, vp, vp, C.c_uint64, vp]
     _LIB = L
     return L

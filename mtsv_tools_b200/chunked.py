@@ -2,10 +2,12 @@
 visits every chunk, and the per-read hit lists are merged the way ``mtsv-collapse`` merges the per-chunk
 results files (src/collapse.rs:543-654, mode TaxId: minimum edit per TaxID, :597-602).
 
-The exchange is the path's one real communication step: every rank keeps a contiguous range of the reads
-and receives, from every other rank, that rank's hits for the range (`all_to_all_single` over NCCL /
-NVLink); the merge itself is the device kernel behind ``mtsvgpu_collapse_device``.  Payload is ~24 B per
-hit, so the step is latency- not bandwidth-bound: two collectives per batch (counts, hits).
+Product path: ``ChunkComm`` = mtsvgpu_comm_* / mtsvgpu_bin_batch_chunked — the exchange and the merge run
+inside the library (csrc/chunked.cu: hits stored straight into the owning rank's buffer over NVLink peer
+memory, one flag barrier, collapse as the epilogue); the host only moves `world` 128-byte handles once.
+``exchange_hits`` / ``bin_reads_chunk_sharded`` below are the earlier formulation on torch.distributed
+collectives (all_to_all_single x3): kept as the A/B baseline the fused path is checked and timed against,
+and because it runs on gloo without a GPU.
 """
 import ctypes as C
 
@@ -13,6 +15,80 @@ import numpy as np
 
 from . import _lib
 from ._lib import check
+
+HANDLE_BYTES = 128  # MTSVGPU_COMM_HANDLE_BYTES
+
+
+def gather_handles(my_handle, group=None):
+    """The host's part of the communicator setup: move every rank's opaque 128-byte handle to every rank, in
+    rank order.  Any channel would do; here it is one all_gather (NCCL on GPU boxes, gloo in the CPU tests)."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    backend = dist.get_backend(group)
+    dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+    mine = torch.frombuffer(bytearray(my_handle), dtype=torch.uint8).to(dev)
+    allh = torch.empty(world * HANDLE_BYTES, dtype=torch.uint8, device=dev)
+    dist.all_gather_into_tensor(allh, mine, group=group)
+    return bytes(allh.cpu().numpy().tobytes())
+
+
+class ChunkComm:
+    """mtsvgpu_comm: the peer-memory communicator of the chunk-sharded mode (include/mtsv_b200.h).  `group` is the
+    torch.distributed group whose ranks hold the chunks of ONE copy of the database: the whole world in plain
+    chunk-sharded operation, a sub-group in hybrid operation (chunk groups x read shards)."""
+
+    def __init__(self, device, max_local_reads, max_hits_per_source, group=None):
+        import torch.distributed as dist
+        L = _lib.load_library()
+        self.group = group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.device = device
+        self._c = C.c_void_p()
+        blob = (C.c_uint8 * HANDLE_BYTES)()
+        check(L.mtsvgpu_comm_create(device, self.rank, self.world, max_local_reads, max_hits_per_source,
+                                    C.byref(self._c), blob))
+        allh = gather_handles(bytes(blob), group)
+        buf = (C.c_uint8 * len(allh)).from_buffer_copy(allh)
+        check(L.mtsvgpu_comm_connect(self._c, buf))
+        dist.barrier(group)  # every rank has mapped every buffer before the first batch stores into one
+
+    def bin_reads(self, index, d_seqs_ptr, d_seq_off_ptr, n_reads, params):
+        """mtsvgpu_bin_batch_chunked.  Returns (first_read, n_local_reads, d_pairs_ptr, d_off_ptr, n_pairs): the
+        merged (tax_id, edit) lists of this rank's range, device pointers owned by the communicator."""
+        L = _lib.load_library()
+        ps = params.c_struct(2)
+        first, nloc, nout = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        dp, do = C.c_void_p(), C.c_void_p()
+        check(L.mtsvgpu_bin_batch_chunked(index._h, self._c, C.c_void_p(d_seqs_ptr), C.c_void_p(d_seq_off_ptr), n_reads,
+                                          C.byref(ps), C.byref(first), C.byref(nloc), C.byref(dp), C.byref(do),
+                                          C.byref(nout)))
+        return first.value, nloc.value, dp.value, do.value, nout.value
+
+    def bin_reads_tensors(self, index, d_reads, d_off, n_reads, params):
+        """Same with torch tensors in and out: (first_read, pairs int32 [n, 2] = (tax_id, edit), offsets int64)."""
+        import torch
+        first, nloc, dp, do, nout = self.bin_reads(index, d_reads.data_ptr(), d_off.data_ptr(), n_reads, params)
+        dev = torch.device("cuda", self.device)
+        pairs = torch.as_tensor(_DevArray(dp, max(1, nout) * 8), device=dev).view(torch.int32).reshape(-1, 2)[:nout]
+        offs = torch.as_tensor(_DevArray(do, (nloc + 1) * 8), device=dev).view(torch.int64)
+        return first, pairs, offs
+
+    def close(self):
+        import torch.distributed as dist
+        if self._c:
+            dist.barrier(self.group)  # nobody may still be storing into a buffer that is about to go away
+            _lib.load_library().mtsvgpu_comm_destroy(self._c)
+            self._c = C.c_void_p()
+
+
+def hybrid_groups(world, n_chunks):
+    """Hybrid operation: `n_chunks` chunks on `world` GPUs, world = n_chunks x n_shards.  Rank r
+    holds chunk r % n_chunks and works on read shard r // n_chunks; the ranks of one shard form one exchange group.
+    Returns the list of rank lists, one per shard."""
+    if n_chunks <= 0 or world % n_chunks:
+        raise ValueError("world size %d is not a multiple of %d chunks" % (world, n_chunks))
+    return [list(range(s * n_chunks, (s + 1) * n_chunks)) for s in range(world // n_chunks)]
 
 
 class _DevArray:

@@ -384,6 +384,20 @@ int mtsvgpu_collapse_device_taxid_gi(int device, void* stream, uint32_t n_parts,
                               n_out);
 }
 
+int mtsvgpu_comm_create(int device, uint32_t rank, uint32_t world, uint64_t max_local_reads,
+                        uint64_t max_hits_per_source, mtsvgpu_comm** out, uint8_t* handle_out) {
+  return comm_create(device, rank, world, max_local_reads, max_hits_per_source, out, handle_out);
+}
+int mtsvgpu_comm_connect(mtsvgpu_comm* comm, const uint8_t* all_handles) { return comm_connect(comm, all_handles); }
+void mtsvgpu_comm_destroy(mtsvgpu_comm* comm) { comm_destroy(comm); }
+int mtsvgpu_bin_batch_chunked(mtsvgpu_index* ix, mtsvgpu_comm* comm, const uint8_t* d_seqs, const uint64_t* d_seq_off,
+                              uint64_t n_reads, const mtsvgpu_params* params, uint64_t* first_read,
+                              uint64_t* n_local_reads, const mtsvgpu_taxhit** d_out, const uint64_t** d_out_off,
+                              uint64_t* n_out) {
+  return bin_batch_chunked(ix, comm, d_seqs, d_seq_off, n_reads, params, first_read, n_local_reads, d_out, d_out_off,
+                           n_out);
+}
+
 void mtsvgpu_device_free(void* d_ptr) {
   if (d_ptr) cudaFree(d_ptr);
 }

@@ -224,6 +224,57 @@ int collapse_device(int device, cudaStream_t st, uint32_t n_parts, const mtsvgpu
   return 0;
 }
 
+// The same TaxId-mode merge without a host round trip: scratch and outputs are pre-sized by the caller's bound on
+// the combined hits (`hit_cap`), the total lands in *d_n_out.  Used as the epilogue of the chunk-sharded exchange
+// (chunked.cu); once the scratch has grown to its working size nothing here synchronises.
+int collapse_taxid_async(CollapseScratch& w, cudaStream_t st, uint32_t n_parts, const mtsvgpu_hit* const* d_hits,
+                         const uint32_t* const* d_counts, uint32_t nr, uint64_t hit_cap, mtsvgpu_taxhit* out,
+                         uint64_t* out_off, uint64_t* d_n_out) {
+  if (n_parts == 0 || n_parts > 16) return set_error(MTSVGPU_EINVAL, "n_parts must be in [1,16]");
+  if (hit_cap > 0xfffffff0ull) return set_error(MTSVGPU_ELIMIT, "more than 2^32 hits in one collapse call");
+  PartsView pv{};
+  pv.n_parts = n_parts;
+  MTSV_TRY(w.counters.reserve(sizeof(BatchCounters) + 16));
+  MTSV_CUDA_TRY(cudaMemsetAsync(w.counters.p, 0, sizeof(BatchCounters) + 16, st));
+  uint64_t* d_tot = reinterpret_cast<uint64_t*>(w.counters.as<uint8_t>() + sizeof(BatchCounters));
+  MTSV_TRY(w.scan_tmp.reserve((((size_t)nr + 1 + 2047) / 2048 + 1) * 8));
+  MTSV_TRY(w.worklist.reserve((size_t)3 * (nr + 1) * 4));
+  for (uint32_t p = 0; p < n_parts; ++p) {
+    pv.hits[p] = d_hits[p];
+    pv.counts[p] = d_counts[p];
+    MTSV_TRY(w.offs[p].reserve(((size_t)nr + 1) * 4));
+    MTSV_TRY(exclusive_scan_u32(d_counts[p], w.offs[p].as<uint32_t>(), nr, w.scan_tmp, nullptr, st));
+    pv.offs[p] = w.offs[p].as<uint32_t>();
+  }
+  MTSV_TRY(w.total.reserve(((size_t)nr + 1) * 4));
+  MTSV_TRY(w.comb_off.reserve(((size_t)nr + 1) * 4));
+  MTSV_TRY(w.cnt_out.reserve(((size_t)nr + 1) * 4));
+  MTSV_TRY(w.off_out32.reserve(((size_t)nr + 1) * 4));
+  MTSV_TRY(w.keys.reserve((size_t)(hit_cap + 1) * 8));
+  const unsigned rgrid = (nr + 255) / 256 + 1;
+  if (nr) MTSV_LAUNCH(collapse_total_kernel, rgrid, 256, 0, st, pv, nr, w.total.as<uint32_t>());
+  MTSV_TRY(exclusive_scan_u32(w.total.as<uint32_t>(), w.comb_off.as<uint32_t>(), nr, w.scan_tmp, d_tot, st));
+  if (nr) {
+    const uint64_t threads = (uint64_t)nr * n_parts;
+    MTSV_LAUNCH(collapse_scatter_kernel, (unsigned)((threads + 255) / 256), 256, 0, st, pv, nr,
+                w.comb_off.as<uint32_t>(), w.keys.as<uint64_t>());
+    MTSV_TRY(run_segmented_sort(st, w.worklist, w.keys.as<uint64_t>(), w.comb_off.as<uint32_t>(), w.total.as<uint32_t>(),
+                                nr, 1, w.counters.as<BatchCounters>()));
+    MTSV_LAUNCH(collapse_count_kernel, rgrid, 256, 0, st, w.keys.as<uint64_t>(), w.comb_off.as<uint32_t>(), nr,
+                w.cnt_out.as<uint32_t>());
+  }
+  MTSV_TRY(exclusive_scan_u32(w.cnt_out.as<uint32_t>(), w.off_out32.as<uint32_t>(), nr, w.scan_tmp, d_n_out, st));
+  MTSV_LAUNCH(collapse_write_kernel, rgrid, 256, 0, st, w.keys.as<uint64_t>(), w.comb_off.as<uint32_t>(),
+              w.off_out32.as<uint32_t>(), nr, out, out_off);
+  MTSV_CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+void CollapseScratch::release_all() {
+  for (auto& o : offs) o.release();
+  for (DevBuf* b : {&total, &comb_off, &keys, &scan_tmp, &counters, &worklist, &cnt_out, &off_out32}) b->release();
+}
+
 int collapse_device_long(int device, cudaStream_t st, uint32_t n_parts, const mtsvgpu_hit* const* d_hits,
                          const uint32_t* const* d_counts, uint64_t n_reads, mtsvgpu_hit** d_out,
                          uint64_t** d_out_off, uint64_t* n_out) {

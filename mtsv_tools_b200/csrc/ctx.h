@@ -252,6 +252,21 @@ int collapse_device(int device, cudaStream_t st, uint32_t n_parts, const mtsvgpu
 int collapse_device_long(int device, cudaStream_t st, uint32_t n_parts, const mtsvgpu_hit* const* d_hits,
                          const uint32_t* const* d_counts, uint64_t n_reads, mtsvgpu_hit** d_out,
                          uint64_t** d_out_off, uint64_t* n_out);
+struct CollapseScratch {
+  DevBuf offs[16], total, comb_off, keys, scan_tmp, counters, worklist, cnt_out, off_out32;
+  void release_all();
+};
+int collapse_taxid_async(CollapseScratch& w, cudaStream_t st, uint32_t n_parts, const mtsvgpu_hit* const* d_hits,
+                         const uint32_t* const* d_counts, uint32_t nr, uint64_t hit_cap, mtsvgpu_taxhit* out,
+                         uint64_t* out_off, uint64_t* d_n_out);
+// chunked.cu
+int comm_create(int device, uint32_t rank, uint32_t world, uint64_t max_local_reads, uint64_t max_hits_per_source,
+                mtsvgpu_comm** out, uint8_t* handle_out);
+int comm_connect(mtsvgpu_comm* c, const uint8_t* all_handles);
+void comm_destroy(mtsvgpu_comm* c);
+int bin_batch_chunked(mtsvgpu_index* h, mtsvgpu_comm* c, const uint8_t* d_seqs, const uint64_t* d_seq_off,
+                      uint64_t n_reads, const mtsvgpu_params* params, uint64_t* first_read, uint64_t* n_local_reads,
+                      const mtsvgpu_taxhit** d_out, const uint64_t** d_out_off, uint64_t* n_out);
 // scan.cuh users
 int exclusive_scan_u32(const uint32_t* d_in, uint32_t* d_out, uint64_t n, DevBuf& tmp,
                        uint64_t* d_total, cudaStream_t stream);

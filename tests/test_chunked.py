@@ -188,3 +188,140 @@ def test_collapse_device_vs_oracle(oracle):
     assert np.array_equal(offs.cpu().numpy().astype(np.uint64), want_off)
     assert np.array_equal(pairs.cpu().numpy().astype(np.uint32), want_pairs)
     assert len(want_pairs) > 3000
+
+
+# ------------------------------------------------------------------------------------------------
+# the fused path: mtsvgpu_comm_* / mtsvgpu_bin_batch_chunked (csrc/chunked.cu)
+# ------------------------------------------------------------------------------------------------
+def test_hybrid_groups():
+    assert chunked.hybrid_groups(8, 8) == [[0, 1, 2, 3, 4, 5, 6, 7]]
+    assert chunked.hybrid_groups(8, 2) == [[0, 1], [2, 3], [4, 5], [6, 7]]
+    with pytest.raises(ValueError):
+        chunked.hybrid_groups(8, 3)
+    assert chunked.read_ranges(10, 4) == [0, 3, 6, 9, 10]
+
+
+def _handles_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        mine = bytes([rank + 1]) * chunked.HANDLE_BYTES
+        out.put((rank, chunked.gather_handles(mine)))
+    finally:
+        dist.destroy_process_group()
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def test_handle_exchange_gloo_world2():
+    """The host's part of the communicator setup: every rank ends up with all handles in rank order."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_handles_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    want = b"".join(bytes([r + 1]) * chunked.HANDLE_BYTES for r in range(world))
+    assert got[0] == want and got[1] == want
+
+
+def _chunk_refs(world):
+    from mtsv_tools_b200 import synth
+    refs = [synth.make_reference(6, 20000, seed=40 + s, n_frac=0.001, shared_frac=0.1, taxids=[5, 6, 7, 8, 9, 10])
+            for s in range(world)]
+    for s in range(1, world):  # shared sequence: the same TaxIDs are reached from several chunks
+        refs[s][0][:30000] = refs[0][0][:30000]
+    cat = np.concatenate([r[0] for r in refs])
+    off = np.concatenate([[0]] + [r[1][1:] + i * refs[0][1][-1] for i, r in enumerate(refs)]).astype(np.uint64)
+    return refs, cat, off
+
+
+def _fused_worker(rank, world, port, n_batches, n_reads, cap, out):
+    """One rank of the fused chunk-sharded path.  With fewer GPUs than ranks the ranks share device 0: CUDA IPC
+    works between processes on one device too, the peer stores are then local stores."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from mtsv_tools_b200 import MGIndex, Params, synth, LibraryError
+        dev = rank % torch.cuda.device_count()
+        torch.cuda.set_device(dev)
+        refs, cat, off = _chunk_refs(world)
+        r = refs[rank]
+        res = []
+        with MGIndex.build(r[0], r[1], r[2], r[3], device=dev) as gix:
+            comm = chunked.ChunkComm(dev, max_local_reads=-(-n_reads // world), max_hits_per_source=cap)
+            try:
+                for b in range(n_batches):
+                    nb = n_reads if b % 2 == 0 else n_reads - 37  # (ragged last range on odd batches)
+                    reads, roff = synth.make_reads(cat, off, nb, 150, seed=50 + b)
+                    d_reads = torch.from_numpy(reads).cuda()
+                    d_off = torch.from_numpy(roff.astype(np.int64)).cuda()
+                    try:
+                        first, pairs, offs = comm.bin_reads_tensors(gix, d_reads, d_off, nb, Params())
+                        res.append((first, pairs.cpu().numpy().astype(np.uint32), offs.cpu().numpy().astype(np.uint64)))
+                    except LibraryError as e:
+                        res.append(("error", e.code))
+            finally:
+                comm.close()
+        out.put((rank, res))
+    finally:
+        dist.destroy_process_group()
+
+
+def _run_fused(world, n_batches, n_reads, cap):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_fused_worker, args=(r, world, port, n_batches, n_reads, cap, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=600) for _ in range(world))
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    return got
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world", [2, 3])
+def test_fused_chunk_exchange_vs_oracle(oracle, world):
+    """mtsvgpu_bin_batch_chunked on `world` ranks == mtsv-collapse's merge (oracle restatement) of `world`
+    independent oracle runs, range by range, over several consecutive batches (both buffer parities)."""
+    from mtsv_tools_b200 import synth
+    n_batches, n_reads = 3, 3000
+    got = _run_fused(world, n_batches, n_reads, cap=200000)
+    refs, cat, off = _chunk_refs(world)
+    idx = [oracle.Index.build((r[0], r[1]), r[2], r[3], 64, 32) for r in refs]
+    for b in range(n_batches):
+        nb = n_reads if b % 2 == 0 else n_reads - 37
+        reads = synth.make_reads(cat, off, nb, 150, seed=50 + b)
+        want_pairs, want_off = oracle.collapse_taxid([ix.bin_reads(reads, oracle.default_params(), threads=4) for ix in idx])
+        bounds = chunked.read_ranges(nb, world)
+        assert len(want_pairs) > 1000
+        for r in range(world):
+            first, pairs, offs = got[r][b]
+            assert first == bounds[r]
+            a, e = int(want_off[bounds[r]]), int(want_off[bounds[r + 1]])
+            assert np.array_equal(offs, want_off[bounds[r]:bounds[r + 1] + 1] - want_off[bounds[r]]), (b, r)
+            assert np.array_equal(pairs, want_pairs[a:e]), (b, r)
+
+
+@pytest.mark.gpu
+def test_fused_chunk_exchange_overflow_fails_on_every_rank():
+    """A range that does not fit its slot fails the batch with ELIMIT on all ranks (nothing truncated), and the
+    communicator stays usable."""
+    got = _run_fused(2, 1, 3000, cap=50)
+    assert got[0] == [("error", -7)] and got[1] == [("error", -7)]
