@@ -788,16 +788,39 @@ def run_chunk_arm(args, ctx, as_dict=False):
     t0 = time.time()
     cat, off, gi, tax = make_reference_torch(cfgc, cfgc["seed"], dev)
     tax = tax + np.uint32(100000 * chunk_id)  # distinct TaxIDs per chunk, except ...
-    tax[: len(tax) // 10] = (1000 + np.arange(len(tax) // 10)).astype(np.uint32)  # ... a tenth shared with chunk 0's
+    src_rank = shard * n_chunks
+    # ... the first 2 % of chunk 0's genomes, which every other chunk of the group also carries at 0.5 % divergence
+    # under the same TaxIDs (strains of one species filed in different chunks): reads from there hit several chunks
+    # with different edit distances, which is what the min-edit merge is for
+    n_sh = max(1, len(tax) // 50)
+    sh_len = int(off[n_sh])
+    shared = cat[:sh_len].clone()
+    if world > 1:
+        dist.broadcast(shared, src=src_rank, group=group)
+    if chunk_id != 0:
+        g = torch.Generator(device=dev)
+        g.manual_seed(900 + chunk_id)
+        pos = torch.randint(0, sh_len, (int(sh_len * 0.005),), generator=g, device=dev)
+        shared[pos] = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device=dev)[
+            torch.randint(0, 4, (len(pos),), generator=g, device=dev)]
+        cat[:sh_len] = shared
+        tax[:n_sh] = (1000 + np.arange(n_sh)).astype(np.uint32)
+    del shared
     torch.cuda.synchronize()
     t_gen = time.time() - t0
-    # chunk 0 of each group provides the reads for its group
-    src_rank = shard * n_chunks
+    # the batch is a metagenome spread over the whole database: every chunk contributes an equal share of the reads
+    # (generated from its own genomes), all ranks of the group then hold the same n_reads reads
+    per = n_reads // n_chunks
+    n_reads = per * n_chunks
+    mine, _ = make_reads(base, cat, off, per, 4 + 17 * rank, dev)
     d_reads = torch.empty(n_reads * L, dtype=torch.uint8, device=dev)
-    if chunk_id == 0:
-        r_t, _ = make_reads(base, cat, off, n_reads, 4 + 17 * shard, dev)
-        d_reads.copy_(r_t)
-        del r_t
+    if world > 1:
+        dist.all_gather_into_tensor(d_reads, mine, group=group)
+    else:
+        d_reads.copy_(mine)
+    del mine
+    # interleave the chunks' shares so that every rank's range of the reads is the same mix
+    d_reads = d_reads.view(n_chunks, per, L).transpose(0, 1).contiguous().view(-1)
     torch.cuda.empty_cache()
     t0 = time.time()
     gix = MGIndex.build(cat.data_ptr(), off, gi, tax, device=ctx.local_rank, sa_rate=args.sa_rate, ktab_k=args.ktab_k,
@@ -808,8 +831,6 @@ def run_chunk_arm(args, ctx, as_dict=False):
     log("rank %d: chunk %d (%.2f Gbp) generated in %.1fs, built in %.1fs (suffix array + BWT %.1fs), %.1f GB HBM, k=%d" %
         (rank, chunk_id, info["text_len"] / 1e9, t_gen, time.time() - t0, info["build_seconds"],
          info["device_bytes"] / 1e9, info["ktab_k"]))
-    if world > 1:
-        dist.broadcast(d_reads, src=src_rank, group=group)
     d_off = torch.arange(n_reads + 1, dtype=torch.int64, device=dev) * L
     torch.cuda.synchronize()
     params = Params(**base["flags"])

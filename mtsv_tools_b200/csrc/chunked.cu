@@ -11,6 +11,8 @@
 // flag there, and the owner starts the merge (collapse.cu) as soon as all its flags are up.  Buffers are double
 // buffered by batch parity, so the one flag barrier per batch is the only inter-GPU synchronisation, and the
 // host synchronises once, at the end, to read the result size.
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "ctx.h"
@@ -95,7 +97,26 @@ __global__ void __launch_bounds__(256) chunk_push_kernel(PeerTable pt, CommLayou
   const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, nthr = (uint64_t)gridDim.x * blockDim.x;
   const uint64_t* src = reinterpret_cast<const uint64_t*>(hits + h0);
   uint64_t* dst = reinterpret_cast<uint64_t*>(peer + lay.hits_off(parity, rank));
-  for (uint64_t i = tid; i < cnt * 3; i += nthr) dst[i] = src[i];
+  const uint64_t words = cnt * 3;
+  // the slot is 16-byte aligned, the span starts on an 8-byte boundary: 16-byte stores when both agree, four in
+  // flight per thread (the NVLink round trip is what has to be covered)
+  if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+    const uint64_t pairs = words >> 1;
+    const ulonglong2* s2 = reinterpret_cast<const ulonglong2*>(src);
+    ulonglong2* d2 = reinterpret_cast<ulonglong2*>(dst);
+    uint64_t i = tid;
+    for (; i + 3 * nthr < pairs; i += 4 * nthr) {
+      const ulonglong2 a = s2[i], b = s2[i + nthr], c2 = s2[i + 2 * nthr], e = s2[i + 3 * nthr];
+      d2[i] = a;
+      d2[i + nthr] = b;
+      d2[i + 2 * nthr] = c2;
+      d2[i + 3 * nthr] = e;
+    }
+    for (; i < pairs; i += nthr) d2[i] = s2[i];
+    if (tid == 0 && (words & 1)) dst[words - 1] = src[words - 1];
+  } else {
+    for (uint64_t i = tid; i < words; i += nthr) dst[i] = src[i];
+  }
   uint32_t* cdst = reinterpret_cast<uint32_t*>(peer + lay.counts_off(parity, rank));
   for (uint64_t i = tid; i < hi - lo; i += nthr) cdst[i] = (uint32_t)(hit_off[lo + i + 1] - hit_off[lo + i]);
   if (tid == 0) reinterpret_cast<CommHeader*>(peer)->slot_hits[parity][rank] = cnt;
@@ -215,7 +236,8 @@ int comm_create(int device, uint32_t rank, uint32_t world, uint64_t max_local_re
                        cudaGetErrorString(e));
     }
   }
-  MTSV_CUDA_TRY(cudaMemset(c->base, 0, 512));
+  // header and per-read counts start at zero: a slot that was never (or not this batch) written reads as "no hits"
+  MTSV_CUDA_TRY(cudaMemset(c->base, 0, c->lay.hits_base()));
   MTSV_CUDA_TRY(cudaMalloc((void**)&c->d_status, 16));
   MTSV_CUDA_TRY(cudaMemset(c->d_status, 0, 16));
   MTSV_CUDA_TRY(cudaMalloc((void**)&c->d_n_out, 8));
@@ -282,6 +304,12 @@ int bin_batch_chunked(mtsvgpu_index* h, mtsvgpu_comm* c, const uint8_t* d_seqs, 
   uint64_t n_hits = 0;
   MTSV_TRY(bin_batch_device(h, d_seqs, d_seq_off, n_reads, nullptr, params, &d_hits, &d_hit_off, &n_hits));
   cudaStream_t st = h->stream;
+  static const bool trace = getenv("MTSV_B200_TRACE") != nullptr;  // phase times on stderr
+  cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  if (trace) {
+    for (auto& e : ev) cudaEventCreate(&e);
+    cudaEventRecord(ev[0], st);
+  }
   // ---- exchange: my hits of range d into rank d's buffer, flag, wait for everybody's flags here ----
   const uint32_t epoch = ++c->epoch, parity = epoch & 1u;
   uint32_t* d_overflow = c->d_status + 1;
@@ -294,11 +322,13 @@ int bin_batch_chunked(mtsvgpu_index* h, mtsvgpu_comm* c, const uint8_t* d_seqs, 
     MTSV_LAUNCH(chunk_push_kernel, dim3(gx, c->world), 256, 0, st, c->peers, c->lay, d_hits, d_hit_off, n_reads, step,
                 c->rank, parity, d_overflow);
   }
+  if (trace) cudaEventRecord(ev[1], st);
   MTSV_LAUNCH(chunk_signal_kernel, 1, 32, 0, st, c->peers, c->world, c->rank, epoch);
   int clock_khz = 1965000;
   cudaDeviceGetAttribute(&clock_khz, cudaDevAttrClockRate, c->device);
   const long long timeout_cycles = (long long)clock_khz * 1000ll * 30ll;  // 30 s: a peer that never arrives is an error
   MTSV_LAUNCH(chunk_wait_kernel, 1, 32, 0, st, c->base, c->world, epoch, timeout_cycles, c->d_status, c->h_status_dev);
+  if (trace) cudaEventRecord(ev[2], st);
   // ---- merge epilogue over the world slots of my range (src/collapse.rs:597-602) ----
   const mtsvgpu_hit* part_hits[kMaxRanks];
   const uint32_t* part_counts[kMaxRanks];
@@ -306,13 +336,23 @@ int bin_batch_chunked(mtsvgpu_index* h, mtsvgpu_comm* c, const uint8_t* d_seqs, 
     part_hits[s] = reinterpret_cast<const mtsvgpu_hit*>(c->base + c->lay.hits_off(parity, s));
     part_counts[s] = reinterpret_cast<const uint32_t*>(c->base + c->lay.counts_off(parity, s));
   }
-  // (a failed exchange leaves stale slots: they still hold whole, in-range lists of an earlier batch or zeros,
-  // and the result is discarded below)
+  // (a failed exchange leaves slots untouched: they hold the whole, in-range lists of an earlier batch or the
+  // zeros they were created with, so the merge below stays in bounds; its result is discarded)
   MTSV_TRY(collapse_taxid_async(c->scratch, st, c->world, part_hits, part_counts, (uint32_t)(hi - lo),
                                 (uint64_t)c->world * c->lay.cap_hits, c->out, c->out_off, c->d_n_out));
+  if (trace) cudaEventRecord(ev[3], st);
   uint64_t total = 0;
   MTSV_CUDA_TRY(cudaMemcpyAsync(&total, c->d_n_out, 8, cudaMemcpyDeviceToHost, st));
   MTSV_CUDA_TRY(cudaStreamSynchronize(st));  // the batch's one host synchronisation after the local binning
+  if (trace) {
+    float a = 0, b = 0, d = 0;
+    cudaEventElapsedTime(&a, ev[0], ev[1]);
+    cudaEventElapsedTime(&b, ev[1], ev[2]);
+    cudaEventElapsedTime(&d, ev[2], ev[3]);
+    fprintf(stderr, "[mtsv_b200 trace] rank %u chunked batch: %llu hits, push %.3f ms, signal+wait %.3f ms, merge %.3f ms\n",
+            c->rank, (unsigned long long)n_hits, a, b, d);
+    for (auto& e : ev) cudaEventDestroy(e);
+  }
   const uint32_t status = c->h_status[0];
   if (status == 1)
     return set_error(MTSVGPU_ELIMIT, "chunk exchange: a rank produced more hits for one read range than max_hits_per_source "
