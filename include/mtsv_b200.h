@@ -169,6 +169,20 @@ MTSVGPU_API int mtsvgpu_bin_batch_device(mtsvgpu_index* ix, const uint8_t* d_seq
                              uint64_t n_reads, const mtsvgpu_params* params,
                              const mtsvgpu_hit** d_hits, const uint64_t** d_hit_off,
                              uint64_t* n_hits);
+/* Same as mtsvgpu_bin_batch_pinned for reads the host parser has already PACKED: per read three bit planes of
+ * ceil(L/8) bytes each — lo, hi (the two bits of the base code: A 0, C 1, G 2, T 3) and nn (1 = not a base after
+ * the folding of src/binner.rs:88-100, lo = hi = 0 there), base j at bit j%8 of byte j/8 — records back to back
+ * in read order (57 bytes instead of 150 for a 150-base read, and the upload is what bounds the host API).
+ * seq_off still counts BASES (n_reads+1 entries): it gives every read's length.  A parser fills the planes while
+ * it scans the record; mtsvgpu_pack_reads does it for bytes already in memory. */
+MTSVGPU_API int mtsvgpu_bin_batch_packed(mtsvgpu_index* ix, const uint8_t* packed, uint64_t packed_bytes,
+                             const uint64_t* seq_off, uint64_t n_reads, const mtsvgpu_params* params,
+                             const mtsvgpu_hit** hits, const uint64_t** hit_off, uint64_t* n_hits);
+/* Host helpers of the packed format (no GPU involved).  mtsvgpu_packed_size: bytes of the records of n_reads reads.
+ * mtsvgpu_pack_reads: raw read bytes -> records, on `threads` host threads (0 = all); *packed_bytes gets the size. */
+MTSVGPU_API uint64_t mtsvgpu_packed_size(const uint64_t* seq_off, uint64_t n_reads);
+MTSVGPU_API int mtsvgpu_pack_reads(const uint8_t* seqs, const uint64_t* seq_off, uint64_t n_reads, uint8_t* packed,
+                       uint64_t packed_cap, uint64_t* packed_bytes, int threads);
 MTSVGPU_API int mtsvgpu_last_batch_stats(const mtsvgpu_index* ix, mtsvgpu_batch_stats* stats);
 /* Launch on a caller-provided cudaStream_t (e.g. torch's current stream); NULL = the handle's own
  * non-blocking stream.  To use the legacy default stream pass cudaStreamLegacy ((cudaStream_t)0x1).

@@ -156,6 +156,26 @@ __global__ void __launch_bounds__(128) encode_reads_kernel(ReadsView rv, ReadWor
   }
 }
 
+// packed input: the planes come from the host parser (core.cuh "packed reads"); one thread per read lays its
+// record out as ReadWords.  rel == nullptr: every read has the same length, records are `uni_rec` bytes apart.
+__global__ void __launch_bounds__(128) packed_sizes_kernel(ReadsView rv, uint32_t* __restrict__ rel) {
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rv.n_reads) return;
+  rel[r] = packed_record_bytes((uint32_t)(rv.seq_off[rv.read0 + r + 1] - rv.seq_off[rv.read0 + r]));
+}
+__global__ void __launch_bounds__(128) unpack_reads_kernel(ReadsView rv, const uint8_t* __restrict__ packed,
+                                                           uint32_t uni_rec, const uint32_t* __restrict__ rel,
+                                                           ReadWord* __restrict__ words) {
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rv.n_reads) return;
+  const uint64_t a = rv.seq_off[rv.read0 + r], b = rv.seq_off[rv.read0 + r + 1];
+  const uint32_t L = (uint32_t)(b - a);
+  const uint32_t W = (L + 63) >> 6;
+  const uint32_t woff = (uint32_t)((a - rv.seq_off[rv.read0]) >> 6) + r;
+  const uint8_t* rec = packed + (rel ? (uint64_t)rel[r] : (uint64_t)r * uni_rec);
+  for (uint32_t w = 0; w < W; ++w) words[woff + w] = unpack_word(rec, L, w);
+}
+
 // seed search: one thread per slot.  Each thread owns one dependent chain of sector fetches;
 // ~2048 chains per SM keep the HBM random-access pipeline full.
 __global__ void __launch_bounds__(256) seed_search_kernel(FmView fm, KtabView kt, ReadsView rv, EncView ev, Params p,
@@ -1414,7 +1434,7 @@ static void emit_abort(mtsvgpu_index* h, int rc) {
 // in-flight cap and the caller must split the range (nothing was emitted in that case).
 static int run_sub_batch(mtsvgpu_index* h, Lane& ln, const Params& p, const uint8_t* d_seqs,
                          const uint64_t* d_seq_off, uint64_t read0, uint32_t n_reads,
-                         uint64_t slot_bound, uint64_t sub_bytes, uint64_t* out_total) {
+                         uint64_t slot_bound, uint64_t sub_bytes, uint64_t pack_base, uint64_t* out_total) {
   const uint64_t batch_read0 = 0;
   DeviceIndex& ix = h->ix;
   BatchWorkspace& ws = *ln.ws;  // scratch of this lane
@@ -1475,7 +1495,20 @@ static int run_sub_batch(mtsvgpu_index* h, Lane& ln, const Params& p, const uint
   // all reads of one length: slots are addressed arithmetically, no slot -> query map needed
   const uint32_t uni_spq = (min_len == hc.max_len && nq && n_slots % nq == 0) ? n_slots / nq : 0;
   if (!uni_spq) MTSV_LAUNCH(expand_slots_kernel, qgrid, 256, 0, st, slot_off, nq, ws.slot_q.as<uint32_t>());
-  MTSV_LAUNCH(encode_reads_kernel, (n_reads + 127) / 128, 128, 0, st, rv, ws.enc.as<ReadWord>());
+  if (!h->packed_input) {
+    MTSV_LAUNCH(encode_reads_kernel, (n_reads + 127) / 128, 128, 0, st, rv, ws.enc.as<ReadWord>());
+  } else {
+    // d_seqs holds packed records: the sub-batch's first one at pack_base
+    const uint32_t* rel = nullptr;
+    if (min_len != hc.max_len) {
+      MTSV_TRY(ws.pack_rel.reserve(((size_t)n_reads + 1) * 4));
+      MTSV_LAUNCH(packed_sizes_kernel, (n_reads + 127) / 128, 128, 0, st, rv, ws.pack_rel.as<uint32_t>());
+      MTSV_TRY(exclusive_scan_u32(ws.pack_rel.as<uint32_t>(), ws.pack_rel.as<uint32_t>(), n_reads, ws.scan_tmp, nullptr, st));
+      rel = ws.pack_rel.as<uint32_t>();
+    }
+    MTSV_LAUNCH(unpack_reads_kernel, (n_reads + 127) / 128, 128, 0, st, rv, d_seqs + pack_base,
+                packed_record_bytes(hc.max_len), rel, ws.enc.as<ReadWord>());
+  }
   if (p.ns == 2) {
     const uint32_t w_max = hc.max_len ? (hc.max_len + 63) / 64 : 1;
     const uint64_t threads = (uint64_t)n_reads * w_max;
@@ -1663,6 +1696,8 @@ static int run_range(mtsvgpu_index* h, Lane& ln, const Params& p, const uint8_t*
                      uint64_t off_hi, uint64_t* out_total) {
   if (off_hi < off_lo) return set_error(MTSVGPU_EINVAL, "seq_off is not monotone");
   uint64_t r = read0, off_r = off_lo;
+  // packed input: byte offset of the record of read r (the slice's first record was placed by the uploader)
+  uint64_t pack_r = h->packed_input && ln.slice < h->pack_slice_base.size() ? h->pack_slice_base[ln.slice] : 0;
   const uint64_t r_end = read0 + n_reads;
   while (r < r_end) {
     uint64_t nr = std::min(r_end - r, std::max<uint64_t>(ln.chunk_reads, 1));
@@ -1673,7 +1708,7 @@ static int run_range(mtsvgpu_index* h, Lane& ln, const Params& p, const uint8_t*
     const uint64_t bytes = off_e - off_r;
     const uint64_t slot_bound = (bytes / p.G + nr) * p.ns + 1;
     const bool too_big = slot_bound > 0xfffffff0ull || nr * p.ns > 0x7ffffff0ull;
-    int rc = too_big ? 1 : run_sub_batch(h, ln, p, d_seqs, d_seq_off, r, (uint32_t)nr, slot_bound, bytes, out_total);
+    int rc = too_big ? 1 : run_sub_batch(h, ln, p, d_seqs, d_seq_off, r, (uint32_t)nr, slot_bound, bytes, pack_r, out_total);
     if (rc == 1) {
       if (nr == 1) return set_error(MTSVGPU_ELIMIT, "a single read exceeds the device batch limits");
       ln.chunk_reads = std::max<uint64_t>(1, nr / 2);
@@ -1681,6 +1716,8 @@ static int run_range(mtsvgpu_index* h, Lane& ln, const Params& p, const uint8_t*
     }
     if (rc != 0) return rc;
     ln.stats.n_sub_batches += 1;
+    if (h->packed_input && r + nr < r_end && offs.host)  // (only after a split: a slice is normally one group)
+      for (uint64_t i = r; i < r + nr; ++i) pack_r += packed_record_bytes((uint32_t)(offs.host[i + 1] - offs.host[i]));
     r += nr;
     off_r = off_e;
   }

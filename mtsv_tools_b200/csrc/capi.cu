@@ -181,19 +181,38 @@ static bool uniform_lengths(const uint64_t* o, uint64_t n_reads) {  // o[0 .. n_
 // The uploader: enqueues the slices one after the other on the copy-in stream (runs on its own host thread so
 // that checking a slice's lengths does not hold up the compute lanes; it stays far ahead of the DMA engine).
 static int upload_slices(mtsvgpu_index* ix, const uint8_t* seqs, const uint64_t* offs, uint64_t base, uint64_t bytes,
-                         const std::vector<uint64_t>& rb, bool trace, uint64_t* h2d_bytes) {
+                         const std::vector<uint64_t>& rb, bool trace, bool packed, uint64_t* h2d_bytes) {
   MTSV_CUDA_TRY(cudaSetDevice(ix->ix.device));
   BatchWorkspace& ws = ix->ws;
   cudaStream_t cin = ix->copy_in_stream;
   const uint64_t n_sub = rb.size() - 1;
+  uint64_t pack_at = 0;  // packed input: byte offset of the next slice's first record
   for (uint64_t i = 0; i < n_sub; ++i) {
     uint64_t r0 = rb[i], r1 = rb[i + 1];
     if (r1 < r0 || offs[r1] < offs[r0]) return set_error(MTSVGPU_EINVAL, "seq_off is not monotone");
-    uint64_t b0 = offs[r0], nb = offs[r1] - b0;
-    if (b0 + nb > bytes) return set_error(MTSVGPU_EINVAL, "seq_off exceeds the reads buffer");
+    const uint64_t b0 = offs[r0];
+    uint64_t c0 = b0, cn = offs[r1] - b0;  // what is copied: the slice's bases, or its packed records
+    const bool uniform = uniform_lengths(offs + r0, r1 - r0);
+    if (packed) {
+      // the slice's records: 3 * ceil(L / 8) bytes per read (core.cuh "packed reads")
+      uint64_t pb = 0;
+      if (uniform) {
+        pb = (r1 - r0) * (uint64_t)packed_record_bytes((uint32_t)(offs[r0 + 1] - offs[r0]));
+      } else {
+        for (uint64_t r = r0; r < r1; ++r) {
+          if (offs[r + 1] < offs[r]) return set_error(MTSVGPU_EINVAL, "seq_off is not monotone");
+          pb += 3 * ((offs[r + 1] - offs[r] + 7) >> 3);
+        }
+      }
+      ix->pack_slice_base[i] = pack_at;
+      c0 = pack_at;
+      cn = pb;
+      pack_at += pb;
+    }
+    if (c0 + cn > bytes) return set_error(MTSVGPU_EINVAL, "seq_off exceeds the reads buffer");
     // offsets of the slice (r0 .. r1 inclusive) first, then its bases: sub-batch i can start as soon as
     // its own slice has landed
-    if (uniform_lengths(offs + r0, r1 - r0)) {
+    if (uniform) {
       const uint64_t cnt = r1 - r0 + 1;
       MTSV_LAUNCH(fill_offsets_kernel, (unsigned)((cnt + 255) / 256), 256, 0, cin, ws.d_seq_off.as<uint64_t>() + r0, b0,
                   offs[r0 + 1] - offs[r0], cnt);
@@ -202,9 +221,9 @@ static int upload_slices(mtsvgpu_index* ix, const uint8_t* seqs, const uint64_t*
                                     cudaMemcpyHostToDevice, cin));
       *h2d_bytes += (r1 - r0 + 1) * 8;
     }
-    if (nb)
-      MTSV_CUDA_TRY(cudaMemcpyAsync(ws.d_seqs.as<uint8_t>() + b0, seqs + base + b0, nb, cudaMemcpyHostToDevice, cin));
-    *h2d_bytes += nb;
+    if (cn)
+      MTSV_CUDA_TRY(cudaMemcpyAsync(ws.d_seqs.as<uint8_t>() + c0, seqs + base + c0, cn, cudaMemcpyHostToDevice, cin));
+    *h2d_bytes += cn;
     MTSV_CUDA_TRY(cudaEventRecord(ix->in_events[i], cin));
     if (trace) cudaEventRecord(g_trace_landed[i], cin);
     ix->slices_enqueued.store(i + 1, std::memory_order_release);
@@ -218,7 +237,7 @@ static int upload_slices(mtsvgpu_index* ix, const uint8_t* seqs, const uint64_t*
 // buffers, valid until the next batch call on this handle.
 static int bin_batch_host(mtsvgpu_index* ix, const uint8_t* seqs, const uint64_t* seq_off, uint64_t n_reads,
                           const mtsvgpu_params* params, int pinned_result, mtsvgpu_hit** hits,
-                          uint64_t** hit_off, uint64_t* n_hits_out) {
+                          uint64_t** hit_off, uint64_t* n_hits_out, bool packed = false, uint64_t packed_bytes = 0) {
   if (!ix || !seq_off || !hits || !hit_off) return set_error(MTSVGPU_EINVAL, "null argument");
   *hits = nullptr;
   *hit_off = nullptr;
@@ -229,7 +248,7 @@ static int bin_batch_host(mtsvgpu_index* ix, const uint8_t* seqs, const uint64_t
   const double t_begin = trace ? now() : 0;
   const uint64_t base = seq_off[0];
   if (seq_off[n_reads] < base) return set_error(MTSVGPU_EINVAL, "seq_off is not monotone");
-  const uint64_t bytes = seq_off[n_reads] - base;
+  const uint64_t bytes = packed ? packed_bytes : seq_off[n_reads] - base;
   if (bytes && !seqs) return set_error(MTSVGPU_EINVAL, "seqs is NULL");
   BatchWorkspace& ws = ix->ws;
   MTSV_TRY(ws.d_seqs.reserve(bytes + 16));
@@ -258,11 +277,13 @@ static int bin_batch_host(mtsvgpu_index* ix, const uint8_t* seqs, const uint64_t
   if (trace && n_sub) trace_event(g_trace_landed, n_sub - 1);
   ix->slices_enqueued.store(0);
   ix->upload_rc.store(0);
+  ix->packed_input = packed;
+  ix->pack_slice_base.assign(n_sub + 1, 0);
   uint64_t h2d_bytes = 0;
   std::thread uploader;
   if (n_sub) {
     uploader = std::thread([&] {
-      int urc = upload_slices(ix, seqs, offs, base, bytes, rb, trace, &h2d_bytes);
+      int urc = upload_slices(ix, seqs, offs, packed ? 0 : base, bytes, rb, trace, packed, &h2d_bytes);
       if (urc != 0) {
         ix->upload_msg = last_error_cstr();
         ix->upload_rc.store(urc, std::memory_order_release);
@@ -288,6 +309,7 @@ static int bin_batch_host(mtsvgpu_index* ix, const uint8_t* seqs, const uint64_t
                             &d_hits, &d_hit_off, &n_hits);
   ix->sub_batch_hook = nullptr;
   ix->results_hook = nullptr;
+  ix->packed_input = false;
   if (uploader.joinable()) uploader.join();
   ix->stats.h2d_bytes = h2d_bytes;
   if (rc != 0) {
@@ -366,6 +388,17 @@ int mtsvgpu_bin_batch_pinned(mtsvgpu_index* ix, const uint8_t* seqs, const uint6
   mtsvgpu_hit* h = nullptr;
   uint64_t* o = nullptr;
   int rc = bin_batch_host(ix, seqs, seq_off, n_reads, params, 1, &h, &o, n_hits);
+  if (hits) *hits = h;
+  if (hit_off) *hit_off = o;
+  return rc;
+}
+
+int mtsvgpu_bin_batch_packed(mtsvgpu_index* ix, const uint8_t* packed, uint64_t packed_bytes, const uint64_t* seq_off,
+                             uint64_t n_reads, const mtsvgpu_params* params, const mtsvgpu_hit** hits,
+                             const uint64_t** hit_off, uint64_t* n_hits) {
+  mtsvgpu_hit* h = nullptr;
+  uint64_t* o = nullptr;
+  int rc = bin_batch_host(ix, packed, seq_off, n_reads, params, 1, &h, &o, n_hits, true, packed_bytes);
   if (hits) *hits = h;
   if (hit_off) *hit_off = o;
   return rc;

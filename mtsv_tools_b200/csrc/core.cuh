@@ -371,6 +371,48 @@ MTSV_HD ReadWord encode_rc_word(const ReadWord* fwd, uint32_t L, uint32_t w) {
   return out;
 }
 
+// ---------------------------------------------------------------------------------------------
+// packed reads (mtsvgpu_bin_batch_packed): what a host parser hands over instead of raw bytes.  The record of a
+// read of L bases is three bit planes of ceil(L/8) bytes each — lo, hi (the two bits of the base code, A 0, C 1,
+// G 2, T 3) and nn (1 = not a base after the normalisation of src/binner.rs:88-100; lo = hi = 0 there) — base j
+// at bit j % 8 of byte j / 8.  Records follow each other without padding: 57 bytes for a 150-base read.
+// ---------------------------------------------------------------------------------------------
+MTSV_HD uint32_t packed_plane_bytes(uint32_t L) { return (L + 7) >> 3; }
+MTSV_HD uint32_t packed_record_bytes(uint32_t L) { return 3 * packed_plane_bytes(L); }
+
+// word w (64 bases) of a packed record
+MTSV_HD ReadWord unpack_word(const uint8_t* rec, uint32_t L, uint32_t w) {
+  const uint32_t pb = packed_plane_bytes(L);
+  const uint32_t b0 = w * 8;
+  const uint32_t nb = pb > b0 ? (pb - b0 < 8 ? pb - b0 : 8) : 0;
+  uint64_t v[3] = {0, 0, 0};
+  for (uint32_t pl = 0; pl < 3; ++pl)
+    for (uint32_t i = 0; i < nb; ++i) v[pl] |= (uint64_t)ldg(rec + pl * pb + b0 + i) << (8 * i);
+  const uint32_t bits = L > w * 64 ? (L - w * 64 < 64 ? L - w * 64 : 64) : 0;
+  const uint64_t m = low_mask(bits);
+  ReadWord r;
+  r.nn = v[2] & m;
+  r.lo = v[0] & m & ~r.nn;
+  r.hi = v[1] & m & ~r.nn;
+  return r;
+}
+
+// host side of the format (also what tests/emul compiles): one read
+inline void pack_read(const uint8_t* seq, uint32_t L, uint8_t* rec) {
+  const uint32_t pb = packed_plane_bytes(L);
+  for (uint32_t i = 0; i < 3 * pb; ++i) rec[i] = 0;
+  for (uint32_t j = 0; j < L; ++j) {
+    const uint32_t c = read_code(seq[j]);
+    const uint32_t bit = 1u << (j & 7);
+    if (c < 4) {
+      if (c & 1) rec[j >> 3] |= (uint8_t)bit;
+      if (c & 2) rec[pb + (j >> 3)] |= (uint8_t)bit;
+    } else {
+      rec[2 * pb + (j >> 3)] |= (uint8_t)bit;
+    }
+  }
+}
+
 // where a query's words live: reads are laid out by a closed form of their byte offset, so no scan
 // is needed: woff(r) = floor((seq_off[r] - seq_off[read0]) / 64) + (r - read0); the second strand
 // follows the first at + total_words.

@@ -127,6 +127,7 @@ struct BatchWorkspace {
   DevBuf slot_off, q_nseeds, q_nhits, hit_off, q_ncand, cand_off, q_nout, out_off;
   // per slot
   DevBuf slot_q, slot_lo, slot_cnt, slot_hoff;
+  DevBuf pack_rel;  // packed input with ragged lengths: byte offset of each read's record inside the sub-batch
   // per seed hit
   DevBuf hit_keys, cand_sparse, cand_stage;
   // per candidate (dense)
@@ -189,6 +190,10 @@ struct mtsvgpu_index {
   std::atomic<int> upload_rc{0};
   std::string upload_msg;
   std::vector<cudaEvent_t> in_events;
+  // host API, packed input (mtsvgpu_bin_batch_packed): d_seqs holds packed records; byte offset of each slice's
+  // first record (filled by the uploader before the slice is announced)
+  bool packed_input = false;
+  std::vector<uint64_t> pack_slice_base;
   // called before each slice on the stream that will compute it
   int (*sub_batch_hook)(mtsvgpu_index*, uint64_t, cudaStream_t) = nullptr;
   // called after each sub-batch's results are enqueued on `stream`: (first hit, #hits, first read, #reads, stream)

@@ -50,6 +50,22 @@ def pack_reads(reads):
     return cat, off
 
 
+def pack_reads_planes(reads, threads=0, out=None):
+    """Raw reads -> the packed records mtsvgpu_bin_batch_packed takes (include/mtsv_b200.h): returns
+    (uint8 records, uint64 base offsets).  `out`: a preallocated (e.g. page-locked) uint8 array to fill."""
+    L = _lib.load_library()
+    cat, off = reads if isinstance(reads, tuple) else pack_reads(reads)
+    cat = np.ascontiguousarray(cat, dtype=np.uint8)
+    off = np.ascontiguousarray(off, dtype=np.uint64)
+    n = len(off) - 1
+    if out is None:
+        out = np.empty(int(L.mtsvgpu_packed_size(_ptr(off), n)), dtype=np.uint8)
+    nb = C.c_uint64()
+    check(L.mtsvgpu_pack_reads(_ptr(cat) if len(cat) else None, _ptr(off), n, _ptr(out) if len(out) else None,
+                               len(out), C.byref(nb), threads))
+    return out[: nb.value], off
+
+
 class MGIndex:
     """Device-resident MG-index.  ``MGIndex.from_file`` replaces ``from_file::<MGIndex>``
     (src/io.rs:115-122, called at src/binner.rs:63): the `.index` written by mtsv-build is parsed,
@@ -207,6 +223,22 @@ class MGIndex:
         hp, op, nh = C.c_void_p(), C.c_void_p(), C.c_uint64()
         check(L.mtsvgpu_bin_batch_pinned(self._h, _ptr(cat), _ptr(off), n, C.byref(ps), C.byref(hp),
                                          C.byref(op), C.byref(nh)))
+        offs = np.frombuffer((C.c_uint8 * ((n + 1) * 8)).from_address(op.value), dtype=np.uint64)
+        total = int(nh.value)
+        hits = np.frombuffer((C.c_uint8 * (max(total, 1) * 24)).from_address(hp.value), dtype=HIT_DTYPE)[:total]
+        return hits, offs
+
+    def bin_reads_packed(self, packed, off, params=None, strands=2):
+        """mtsvgpu_bin_batch_packed: reads as packed records (pack_reads_planes) + their base offsets; results as
+        bin_reads_pinned (views of the handle's page-locked buffers)."""
+        L = _lib.load_library()
+        params = params or Params()
+        assert packed.dtype == np.uint8 and off.dtype == np.uint64 and packed.flags.c_contiguous
+        n = len(off) - 1
+        ps = params.c_struct(strands)
+        hp, op, nh = C.c_void_p(), C.c_void_p(), C.c_uint64()
+        check(L.mtsvgpu_bin_batch_packed(self._h, _ptr(packed) if len(packed) else None, len(packed), _ptr(off), n,
+                                         C.byref(ps), C.byref(hp), C.byref(op), C.byref(nh)))
         offs = np.frombuffer((C.c_uint8 * ((n + 1) * 8)).from_address(op.value), dtype=np.uint64)
         total = int(nh.value)
         hits = np.frombuffer((C.c_uint8 * (max(total, 1) * 24)).from_address(hp.value), dtype=HIT_DTYPE)[:total]
