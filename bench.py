@@ -779,6 +779,13 @@ def run_gpu_arm(args, name, cfg, ctx):
             "e2e_value": tot / (e2e_s * 1e-3), "e2e_ms_per_step": e2e_s / args.steps,
             "e2e_packed_value": tot / (pk_ms * 1e-3), "e2e_prepacked_value": tot / (ppk_ms * 1e-3),
             "note": "same index, the step's reads divided among the ranks; compare with the N=1 line's value / e2e"}
+    if world == 1 and name == "cfg2" and not args.only_main or args.mode == "cli":
+        try:
+            line["cli_e2e"] = run_cli(args, w)
+        except SystemExit:
+            raise
+        except Exception as e:
+            line["cli_e2e"] = {"error": repr(e)}
     w.close()
 
     # ---- the other BASELINE configs and a ragged-read batch, shorter runs attached to the same line (N=1) ----
@@ -810,6 +817,81 @@ def run_gpu_arm(args, name, cfg, ctx):
             line["chunk_sharded"] = {"error": repr(e)}
     if ctx.rank == 0:
         print(json.dumps(line), flush=True)
+
+
+def write_fastq(path, reads_np, n, L, gz=False):
+    """Uniform-length reads -> 4-line FASTQ (fixed-width ids), built as one byte matrix."""
+    hdr = np.frombuffer(b"@read_", dtype=np.uint8)
+    width = len(hdr) + 9 + 1 + L + 3 + L + 1
+    rows = np.empty((n, width), dtype=np.uint8)
+    rows[:, :len(hdr)] = hdr
+    idx = np.arange(n)
+    for d in range(9):
+        rows[:, len(hdr) + 8 - d] = 48 + (idx // 10 ** d) % 10
+    c = len(hdr) + 9
+    rows[:, c] = 10
+    rows[:, c + 1:c + 1 + L] = reads_np[:n * L].reshape(n, L)
+    rows[:, c + 1 + L:c + 4 + L] = np.frombuffer(b"\n+\n", dtype=np.uint8)
+    rows[:, c + 4 + L:c + 4 + 2 * L] = ord("I")
+    rows[:, -1] = 10
+    if gz:
+        import gzip
+        with gzip.open(path, "wb", compresslevel=1) as f:
+            f.write(rows.tobytes())
+    else:
+        rows.tofile(path)
+    return ["read_%09d" % i for i in range(n)] if n <= 200000 else None
+
+
+def run_cli(args, w, n_plain=2_000_000, n_gz=500_000, n_check=100_000):
+    """The drop-in binary itself: FASTQ file -> results file through mtsv_tools_b200/bin/mtsv-binner (reader thread,
+    parser pool packing straight into bit planes, mtsvgpu_bin_batch_packed, formatter pool, ordered writer), wall
+    clock of the process and the query time the binary reports (the reference's own timer starts after index
+    deserialisation, src/binner.rs:63,72,143).  Results of the first reads are compared with the oracle's lines."""
+    from oracle import pyoracle
+    exe = os.path.join(ROOT, "mtsv_tools_b200", "bin", "mtsv-binner")
+    cores = len(os.sched_getaffinity(0)) or 1
+    hr, ho = w.host_views(min(w.n_reads, n_plain))
+    n_plain = len(ho) - 1
+    L = w.L
+    out = {}
+    want = None
+    for kind, n, gz in (("fastq", n_plain, False), ("fastq_gz", min(n_gz, n_plain), True)):
+        path = os.path.join(CACHE_DIR, "cli_reads_%d.fq%s" % (n, ".gz" if gz else ""))
+        res = path + ".results"
+        write_fastq(path, hr, n, L, gz)
+        t0 = time.time()
+        pr = subprocess.run([exe, "--fastq", path, "--index", w.path, "--results", res, "--force-overwrite",
+                             "--threads", str(cores)], capture_output=True, text=True)
+        wall = time.time() - t0
+        if pr.returncode != 0:
+            raise SystemExit("bench.py: mtsv-binner failed (%d): %s" % (pr.returncode, pr.stderr[-400:]))
+        took = None
+        for ln in pr.stderr.splitlines():
+            if "Took" in ln:
+                took = float(ln.split("Took")[1].split()[0])
+        lines = open(res).read().splitlines(True)
+        if want is None:
+            nc = min(n_check, n)
+            names = ["read_%09d" % i for i in range(nc)]
+            oh, oo = w.oracle().bin_reads((hr[:nc * L], ho[:nc + 1]), pyoracle.default_params(**w.cfg["flags"]),
+                                          threads=os.cpu_count())
+            want = pyoracle.results_lines(names, oh, oo, False)
+        last = "read_%09d" % (min(n_check, n) - 1)
+        got = [l for l in lines if l.split(":")[0] <= last]
+        ok = got == want
+        if not ok:
+            raise SystemExit("bench.py: mtsv-binner results differ from the oracle's lines (%s)" % kind)
+        out[kind] = {"reads": n, "file_bytes": os.path.getsize(path), "wall_seconds": wall, "query_seconds": took,
+                     "reads_per_s_wall": n / wall, "reads_per_s_query": n / took if took else None,
+                     "result_lines": len(lines), "parity_lines_checked": len(got), "bit_exact": True}
+        os.unlink(path)
+        os.unlink(res)
+    out["threads"] = cores
+    out["note"] = ("wall includes process start, CUDA context and mtsvgpu_index_open of the %.1f GB .index; query_seconds "
+                   "is the binary's own timer (starts after the index is loaded, like the reference's)" %
+                   (os.path.getsize(w.path) / 1e9))
+    return out
 
 
 def run_chunk_arm(args, ctx, as_dict=False):
@@ -1014,8 +1096,9 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--mode", default="reads", choices=["reads", "chunk"],
-                    help="reads: index replicated, reads sharded (default); chunk: one index chunk per GPU")
+    ap.add_argument("--mode", default="reads", choices=["reads", "chunk", "cli"],
+                    help="reads: index replicated, reads sharded (default); chunk: one index chunk per GPU; "
+                         "cli: reads + the mtsv-binner binary on a FASTQ file (also part of the default N=1 run)")
     ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS))
     ap.add_argument("--reads", type=int, default=0, help="reads per GPU per step (default: the config's)")
     ap.add_argument("--sa-rate", type=int, default=0)

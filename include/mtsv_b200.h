@@ -183,6 +183,12 @@ MTSVGPU_API int mtsvgpu_bin_batch_packed(mtsvgpu_index* ix, const uint8_t* packe
 MTSVGPU_API uint64_t mtsvgpu_packed_size(const uint64_t* seq_off, uint64_t n_reads);
 MTSVGPU_API int mtsvgpu_pack_reads(const uint8_t* seqs, const uint64_t* seq_off, uint64_t n_reads, uint8_t* packed,
                        uint64_t packed_cap, uint64_t* packed_bytes, int threads);
+/* One read -> its record (3 * ceil(len / 8) bytes at `record`): what a parser thread calls per sequence. */
+MTSVGPU_API void mtsvgpu_pack_read(const uint8_t* seq, uint32_t len, uint8_t* record);
+/* Page-locked host memory for batch inputs (uploads from pageable memory are staged by the driver and do not
+ * overlap with compute).  NULL on failure. */
+MTSVGPU_API void* mtsvgpu_host_alloc(uint64_t bytes);
+MTSVGPU_API void mtsvgpu_host_free(void* p);
 MTSVGPU_API int mtsvgpu_last_batch_stats(const mtsvgpu_index* ix, mtsvgpu_batch_stats* stats);
 /* Launch on a caller-provided cudaStream_t (e.g. torch's current stream); NULL = the handle's own
  * non-blocking stream.  To use the legacy default stream pass cudaStreamLegacy ((cudaStream_t)0x1).

@@ -431,6 +431,21 @@ int mtsvgpu_bin_batch_chunked(mtsvgpu_index* ix, mtsvgpu_comm* comm, const uint8
                            n_out);
 }
 
+void* mtsvgpu_host_alloc(uint64_t bytes) {
+  void* p = nullptr;
+  cudaError_t e = cudaMallocHost(&p, bytes ? bytes : 1);
+  if (e != cudaSuccess) {
+    (void)cudaGetLastError();
+    set_error(e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver ? MTSVGPU_ENODEVICE : MTSVGPU_ENOMEM,
+              "cudaMallocHost(%llu) failed: %s", (unsigned long long)bytes, cudaGetErrorString(e));
+    return nullptr;
+  }
+  return p;
+}
+void mtsvgpu_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
 void mtsvgpu_device_free(void* d_ptr) {
   if (d_ptr) cudaFree(d_ptr);
 }

@@ -126,6 +126,11 @@ uint64_t mtsvgpu_packed_size(const uint64_t* seq_off, uint64_t n_reads) {
   return total;
 }
 
+void mtsvgpu_pack_read(const uint8_t* seq, uint32_t len, uint8_t* record) {
+  static const PackFn fn = pick();
+  fn(seq, len, record, false);
+}
+
 int mtsvgpu_pack_reads(const uint8_t* seqs, const uint64_t* seq_off, uint64_t n_reads, uint8_t* packed,
                        uint64_t packed_cap, uint64_t* packed_bytes, int threads) {
   if (!seq_off || (!packed && n_reads) || (n_reads && !seqs && seq_off[n_reads] != seq_off[0])) return MTSVGPU_EINVAL;

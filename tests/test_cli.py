@@ -40,6 +40,69 @@ def test_fastx_parsing(tmp_path):
     assert _run("--dump-reads", "--fastq", str(bad)).returncode == 12  # src/binner.rs:81-84
 
 
+def _lens(dump_stdout):
+    return "".join("%s\t%d\n" % (l.split("\t")[0], len(l.rstrip("\n").split("\t")[1]))
+                   for l in dump_stdout.splitlines(True))
+
+
+def test_pipeline_scanner_and_parser_match_the_sequential_reader(tmp_path):
+    """--dump-reads-mt drives the production path (block reader, record scanner, parser pool, ordered writer)
+    without a GPU and prints id<TAB>length; it must agree with the line-by-line reader on awkward files, in
+    particular where 4 MiB block edges cut lines and records."""
+    rng = np.random.default_rng(3)
+
+    def fastq(n, multi=False, crlf=False, final_newline=True):
+        nl = "\r\n" if crlf else "\n"
+        parts = []
+        for i in range(n):
+            L = int(rng.integers(0, 400))
+            s = "".join(rng.choice(list("ACGTN"), size=L))
+            q = "".join(rng.choice(list("@+I#>"), size=L))  # quality lines that look like headers / separators
+            if multi and L > 10:
+                k = int(rng.integers(1, L))
+                s, q = s[:k] + nl + s[k:], q[:k // 2] + nl + q[k // 2:]
+            parts.append("@r%d extra words%s%s%s+%s%s%s" % (i, nl, s, nl, nl, q, nl))
+            if i % 97 == 0:
+                parts.append(nl)  # blank line between records
+        t = "".join(parts)
+        return t if final_newline else t.rstrip("\r\n")
+
+    def fasta(n, crlf=False, final_newline=True):
+        nl = "\r\n" if crlf else "\n"
+        parts = []
+        for i in range(n):
+            L = int(rng.integers(0, 900))
+            s = "".join(rng.choice(list("ACGTNacgtn"), size=L))
+            lines = [s[j:j + 70] for j in range(0, L, 70)] or [""]
+            parts.append(">s%d-%d desc%s%s%s" % (i, i % 7, nl, nl.join(lines), nl))
+        t = "".join(parts)
+        return t if final_newline else t.rstrip("\r\n")
+
+    cases = [("a.fq", fastq(30000), "--fastq"), ("b.fq", fastq(3000, multi=True, crlf=True), "--fastq"),
+             ("c.fq", fastq(2000, final_newline=False), "--fastq"), ("d.fa", fasta(20000), "--fasta"),
+             ("e.fa", fasta(1500, crlf=True, final_newline=False), "--fasta")]
+    for name, text, flag in cases:
+        f = tmp_path / name
+        f.write_text(text, newline="")
+        want = _run("--dump-reads", flag, str(f))
+        assert want.returncode == 0
+        for extra in ([], ["--threads", "3", "--batch-reads", "1000"], ["--read-offset", "1234"]):
+            got = _run("--dump-reads-mt", flag, str(f), *extra)
+            assert got.returncode == 0, (name, extra, got.stderr)
+            w = _lens(want.stdout)
+            if "--read-offset" in extra:
+                w = "".join(w.splitlines(True)[1234:])
+            assert got.stdout == w, (name, extra)
+    gzf = tmp_path / "a.fq.gz"
+    with gzip.open(gzf, "wt", newline="") as f:
+        f.write(cases[0][1])
+    assert _run("--dump-reads-mt", "--fastq", str(gzf)).stdout == _lens(_run("--dump-reads", "--fastq", str(tmp_path / "a.fq")).stdout)
+    # malformed input: quality shorter than the sequence, in the middle of a large file
+    bad = tmp_path / "bad.fq"
+    bad.write_text(cases[0][1][:5_000_000].rsplit("@r", 1)[0] + "@x\nACGT\n+\nII\n" + "@y\nAC\n+\nII\n")
+    assert _run("--dump-reads-mt", "--fastq", str(bad)).returncode == 12
+
+
 def test_exit_codes_without_gpu(tmp_path):
     fa = tmp_path / "t.fa"
     fa.write_text(">r1\nACGT\n")
