@@ -26,7 +26,9 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <fcntl.h>
 #include <sys/stat.h>
+#include <unistd.h>
 #include <zlib.h>
 
 #include <algorithm>
@@ -279,7 +281,7 @@ void usage() {
           "  -t, --threads <n>              parser / formatter threads [default: all cores]\n"
           "      --gpu <id>                 first CUDA device [default: 0]\n"
           "      --gpus <n>                 number of CUDA devices; batches go round-robin [default: 1]\n"
-          "      --batch-reads <n>          reads per library call [default: 4194304]\n");
+          "      --batch-reads <n>          reads per library call [default: 524288]\n");
 }
 
 
@@ -520,7 +522,7 @@ void parse_block(const TextBlock& tb, bool fastq, ParsedBlock* out) {
 int main(int argc, char** argv) {
   const char *fasta = nullptr, *fastq = nullptr, *index = nullptr, *results = nullptr;
   mtsvgpu_params p{0.13, 18, 15, 0.015, 2000, 200, -1, -1, 2, 0};
-  uint64_t read_offset = 0, batch_reads = 4u << 20;
+  uint64_t read_offset = 0, batch_reads = 1u << 19;
   bool long_fmt = false, force = false, dump_reads = false;
   int device = 0, n_gpus = 1, n_threads = 0;
   auto need = [&](int& i) -> const char* {
@@ -624,6 +626,15 @@ int main(int argc, char** argv) {
     return 2;
   }
   gzbuffer(gz, 1 << 20);
+  // an uncompressed file is read with plain read(2): no pass through zlib's copy-through mode
+  int plain_fd = -1;
+  struct stat ist;
+  if (stat(input, &ist) == 0 && S_ISREG(ist.st_mode) && gzdirect(gz)) {
+    plain_fd = open(input, O_RDONLY);
+#ifdef POSIX_FADV_SEQUENTIAL
+    if (plain_fd >= 0) posix_fadvise(plain_fd, 0, 0, POSIX_FADV_SEQUENTIAL);
+#endif
+  }
   std::vector<mtsvgpu_index*> handles((size_t)n_gpus, nullptr);
   if (!dump_mt) {
     logf("INFO", "Deserializing candidate filter ...");
@@ -657,19 +668,30 @@ int main(int argc, char** argv) {
   const size_t kBlockBytes = 4u << 20;
   const uint64_t max_blocks_in_flight = (uint64_t)std::max(8, 4 * n_threads) + batch_reads / 8192;
   std::thread reader([&] {
+    // Each block is read straight into the string that becomes the parser's input; only the cut-off tail (the
+    // beginning of the record the block edge fell into) is copied over to the next block.
     std::string carry;
-    std::vector<char> buf(kBlockBytes);
     uint64_t records_seen = 0;  // complete records cut so far (including skipped ones)
     bool eof = false;
     while (!eof && !sh.failed()) {
-      int got = gzread(gz, buf.data(), (unsigned)buf.size());
-      if (got < 0) {
-        sh.fail(12, "Unable to read from input file");
-        break;
+      const size_t have = carry.size();
+      carry.resize(have + kBlockBytes);
+      size_t filled = 0;
+      while (filled < kBlockBytes) {  // (short reads happen on pipes and at gzip member boundaries)
+        long got = plain_fd >= 0 ? (long)read(plain_fd, &carry[have + filled], kBlockBytes - filled)
+                                 : (long)gzread(gz, &carry[have + filled], (unsigned)(kBlockBytes - filled));
+        if (got < 0) {
+          sh.fail(12, "Unable to read from input file");
+          break;
+        }
+        if (got == 0) {
+          eof = true;
+          break;
+        }
+        filled += (size_t)got;
       }
-      eof = got == 0 || gzeof(gz);
-      carry.append(buf.data(), (size_t)got);
-      if (!eof && carry.size() < kBlockBytes) continue;
+      if (sh.failed()) break;
+      carry.resize(have + filled);
       const char* cut = nullptr;
       const int64_t n = scan_records(carry.data(), carry.data() + carry.size(), is_fastq, eof, &cut);
       if (n < 0) {
@@ -686,8 +708,10 @@ int main(int argc, char** argv) {
       auto tb = std::make_shared<TextBlock>();
       tb->n_records = (uint32_t)n;
       const size_t used = (size_t)(cut - carry.data());
-      tb->text.assign(carry.data(), used);
-      carry.erase(0, used);
+      std::string tail(carry, used);
+      carry.resize(used);
+      tb->text.swap(carry);
+      carry.swap(tail);
       // .skip(read_offset) (src/binner.rs:176,199): whole blocks are dropped, a straddling block is trimmed by the parser
       const uint64_t first = records_seen;
       records_seen += (uint64_t)n;
@@ -872,6 +896,7 @@ int main(int argc, char** argv) {
   }
   writer.join();
   gzclose(gz);
+  if (plain_fd >= 0) close(plain_fd);
   for (auto h : handles) mtsvgpu_index_close(h);
   int code = 0;
   {
