@@ -1158,9 +1158,85 @@ constexpr uint32_t kMaxReadLen = 4096;
 // "TaxID already matched" test scans the accepted list with all lanes.
 constexpr uint32_t kSelectTaxCache = 1024;  // accepted TaxIDs of a heavy strand kept in shared memory
 
+// Strands with up to kSelectTaxCache / 2 candidates: the accepted TaxIDs live in a warp-private hash set in shared
+// memory (open addressing, TaxID + 1 as the key), and the passing candidates of a 32-candidate step are taken
+// together: a lane drops out when its TaxID is in the set or when a lower lane of the step carries the same TaxID
+// (rank order: the lower lane is the earlier candidate), the others are accepted at once.
+__device__ uint32_t select_warp_hashed(const BinsView& bv, const Params& p, const CandRec* __restrict__ cand,
+                                       const uint32_t* __restrict__ edits, uint32_t n_cand, uint32_t k,
+                                       HitRec* __restrict__ out, uint32_t* __restrict__ s_set) {
+  const unsigned lane = threadIdx.x & 31;
+  uint32_t n_out = 0;
+  if (p.max_candidates >= 0 && (uint64_t)n_cand > (uint64_t)p.max_candidates) n_cand = (uint32_t)p.max_candidates;
+  for (uint32_t j = lane; j < kSelectTaxCache; j += 32) s_set[j] = 0;
+  __syncwarp();
+  for (uint32_t t0 = 0; t0 < n_cand; t0 += 32) {
+    const uint32_t c = t0 + lane;
+    const uint32_t e = c < n_cand ? edits[c] : kNoEdit;
+    bool pass = e != kNoEdit && e <= k;
+    CandRec cr{0, 0, 0, 0};
+    uint32_t tax = 0;
+    if (pass) {
+      cr = cand[c];
+      tax = ldg(&bv.tax[cr.bin]);
+      // already accepted?  (the set only changes between steps)
+      const uint32_t key = tax + 1u;  // 0 marks an empty slot; TaxID 0xffffffff wraps to 0 and is handled below
+      if (key != 0) {
+        uint32_t h = (tax * 2654435761u) >> 22;  // 10 bits
+        for (;;) {
+          const uint32_t v = s_set[h];
+          if (v == key) {
+            pass = false;
+            break;
+          }
+          if (v == 0) break;
+          h = (h + 1) & (kSelectTaxCache - 1);
+        }
+      }
+    }
+    const unsigned pm = __ballot_sync(0xffffffffu, pass);
+    if (pm == 0) continue;
+    // one candidate per TaxID within the step: the lowest lane
+    const unsigned peers = __match_any_sync(0xffffffffu, pass ? tax : (0x80000000u | lane) ^ 0x5a5a5a5au) & pm;
+    bool win = pass && (unsigned)(__ffs(peers) - 1) == lane;
+    if (tax == 0xffffffffu && pass) {  // the one key the set cannot hold: fall back to scanning the output
+      bool seen = false;
+      for (uint32_t j = 0; j < n_out; ++j) seen |= out[j].tax_id == tax;
+      win = win && !seen;
+    }
+    unsigned wm = __ballot_sync(0xffffffffu, win);
+    if (p.max_assignments >= 0) {  // :421-425: stop once max_assignments hits are in (tested after a push: >= 1)
+      const uint64_t lim = p.max_assignments > 0 ? (uint64_t)p.max_assignments : 1;
+      const uint64_t room = lim > n_out ? lim - n_out : 0;
+      while ((uint64_t)__popc(wm) > room) wm &= ~(0x80000000u >> __clz(wm));  // drop the highest lanes
+      win = (wm >> lane) & 1u;
+    }
+    if (win) {
+      HitRec hrec;
+      hrec.tax_id = tax;
+      hrec.gi = ldg(&bv.gi[cr.bin]);
+      const uint32_t bs = ldg(&bv.start[cr.bin]);
+      hrec.offset = cr.start >= bs ? cr.start - bs : 0;
+      hrec.edit = e;
+      hrec.reserved = 0;
+      out[n_out + __popc(wm & ((1u << lane) - 1u))] = hrec;
+      const uint32_t key = tax + 1u;
+      if (key != 0) {
+        uint32_t h = (tax * 2654435761u) >> 22;
+        while (atomicCAS(&s_set[h], 0u, key) != 0u) h = (h + 1) & (kSelectTaxCache - 1);
+      }
+    }
+    __syncwarp();
+    n_out += (uint32_t)__popc(wm);
+    if (p.max_assignments >= 0 && (uint64_t)n_out >= (uint64_t)p.max_assignments) return n_out;
+  }
+  return n_out;
+}
+
 __device__ uint32_t select_warp(const BinsView& bv, const Params& p, const CandRec* __restrict__ cand,
                                 const uint32_t* __restrict__ edits, uint32_t n_cand, uint32_t k,
                                 HitRec* __restrict__ out, uint32_t* __restrict__ s_tax) {
+  if (n_cand <= kSelectTaxCache / 2) return select_warp_hashed(bv, p, cand, edits, n_cand, k, out, s_tax);
   const unsigned lane = threadIdx.x & 31;
   uint32_t n_out = 0;
   if (p.max_candidates >= 0 && (uint64_t)n_cand > (uint64_t)p.max_candidates) n_cand = (uint32_t)p.max_candidates;

@@ -178,6 +178,28 @@ def test_pipeline_redundant_reference(oracle):
             _same(h1, o1, h2, o2)
 
 
+def test_pipeline_many_strains_sharing_taxids(oracle):
+    """Heavy strands (hundreds of candidates) where several strains carry the SAME TaxID: only the first passing
+    candidate of a TaxID in rank order may be reported (src/index.rs:393-396), with and without the
+    max-candidates / max-assignments limits (:385-389, :421-425) — the warp-level selection with its hash set of
+    accepted TaxIDs, and the scan fall-back beyond 512 candidates."""
+    for n_strains, per_tax in ((200, 7), (200, 1), (700, 3)):
+        taxids = 500 + (np.arange(n_strains, dtype=np.uint32) // np.uint32(per_tax))
+        rng = np.random.default_rng(n_strains)
+        taxids = taxids[rng.permutation(n_strains)]  # strains of one TaxID are not neighbours in the text
+        ref = synth.make_reference(n_strains, 2000, seed=16, n_frac=0.0, shared_frac=0.95, divergence=0.004, taxids=taxids)
+        ix = oracle.Index.build((ref[0], ref[1]), ref[2], ref[3], 64, 32)
+        reads = synth.make_reads(ref[0], ref[1], 600, 75, seed=17)
+        with _gpu_index(ix) as g:
+            for flags in ({}, dict(max_assignments=3), dict(max_assignments=0), dict(max_candidates=40),
+                          dict(max_candidates=100, max_assignments=33), dict(tune_max_hits=100000, max_hits=100000)):
+                po, pg = _params(oracle, **flags)
+                h1, o1 = ix.bin_reads(reads, po, threads=8)
+                h2, o2 = g.bin_reads(reads, pg)
+                _same(h1, o1, h2, o2)
+            assert int((o1[1:] - o1[:-1]).max()) > 32
+
+
 def test_pipeline_long_reads_high_edit(oracle, small_ref, small_index):
     """BASELINE config 5 in miniature: 250 bp, edit-rate 0.2, --seed-interval 3."""
     reads = synth.make_reads(small_ref[0], small_ref[1], 1000, 250, seed=8, sub=0.10)
