@@ -197,7 +197,8 @@ def test_pipeline_many_strains_sharing_taxids(oracle):
                 h1, o1 = ix.bin_reads(reads, po, threads=8)
                 h2, o2 = g.bin_reads(reads, pg)
                 _same(h1, o1, h2, o2)
-            assert int((o1[1:] - o1[:-1]).max()) > 32
+            # (heavy strands indeed: about n_strains candidates per strand, one hit per TaxID among them)
+            assert int((o1[1:] - o1[:-1]).max()) >= min(100, n_strains // per_tax)
 
 
 def test_pipeline_long_reads_high_edit(oracle, small_ref, small_index):
