@@ -42,7 +42,13 @@ extern "C" {
 #define MTSVGPU_ENODEVICE -4 /* no usable CUDA device */
 #define MTSVGPU_ECUDA -5     /* CUDA runtime error */
 #define MTSVGPU_ENOMEM -6    /* host or device allocation failed */
-#define MTSVGPU_ELIMIT -7    /* input exceeds a documented limit (index >= 2^32 symbols, read too long, hit explosion) */
+#define MTSVGPU_ELIMIT -7    /* input exceeds a documented limit (index >= 2^32 - 64 symbols, exchange slot too small) */
+
+/* Limits that apply PER READ (the batch goes on, the read is reported without hits and counted in
+ * mtsvgpu_batch_stats; the reference has no such limits):
+ *   - reads longer than MTSVGPU_MAX_READ_LEN bases          -> stats.n_reads_over_limit
+ *   - a read strand whose seeds produce more than 2^26 hits -> stats.n_strands_over_hits */
+#define MTSVGPU_MAX_READ_LEN 4096
 
 typedef struct mtsvgpu_index mtsvgpu_index;
 
@@ -118,6 +124,8 @@ typedef struct {
   uint64_t n_sub_batches;  /* device sub-batches the call was processed in (= launches of every stage kernel) */
   uint64_t h2d_bytes;      /* host API: bytes actually uploaded (offsets of equal-length slices are generated
                               on the device instead) */
+  uint64_t n_reads_over_limit;   /* reads longer than MTSVGPU_MAX_READ_LEN: given no hits */
+  uint64_t n_strands_over_hits;  /* read strands with more than 2^26 seed hits: given no hits */
 } mtsvgpu_batch_stats;
 
 /* ---- index lifetime: replaces from_file::<MGIndex> (src/io.rs:115-122, src/binner.rs:63-67) ---- */

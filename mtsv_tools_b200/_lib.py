@@ -52,7 +52,8 @@ class StatsStruct(C.Structure):
     _fields_ = [("ms", C.c_float * N_STAGES), ("launches", C.c_uint64 * N_STAGES),
                 ("n_queries", C.c_uint64), ("n_seed_slots", C.c_uint64), ("n_seed_hits", C.c_uint64),
                 ("n_candidates", C.c_uint64), ("n_hits", C.c_uint64), ("window_bytes", C.c_uint64),
-                ("rank_queries", C.c_uint64), ("n_sub_batches", C.c_uint64), ("h2d_bytes", C.c_uint64)]
+                ("rank_queries", C.c_uint64), ("n_sub_batches", C.c_uint64), ("h2d_bytes", C.c_uint64),
+                ("n_reads_over_limit", C.c_uint64), ("n_strands_over_hits", C.c_uint64)]
 
 
 # every symbol include/mtsv_b200.h declares

@@ -24,7 +24,7 @@ namespace mtsv {
 // ------------------------------------------------------------------------------------------
 // small kernels
 // ------------------------------------------------------------------------------------------
-constexpr uint32_t kMaxReadLenDev = 4096;  // longer reads fail the batch (ELIMIT) before any seed work
+constexpr uint32_t kMaxReadLenDev = MTSVGPU_MAX_READ_LEN;  // longer reads get no seeds, hence no hits; they are counted
 
 // adds `v` of every thread of the CTA into one of 32 counters with a single global atomic per CTA
 __device__ __forceinline__ void cta_accumulate(unsigned long long* counters32, unsigned int v) {
@@ -49,7 +49,11 @@ __global__ void count_slots_kernel(ReadsView rv, Params p, uint32_t nq, uint32_t
     } else {
       L = (uint32_t)(b - a);
     }
-    q_nslots[q] = L <= kMaxReadLenDev ? seed_slots(L, p.S, p.G) : 0;
+    if (L > kMaxReadLenDev) {  // over the documented limit: this read is left out (stats.n_reads_over_limit)
+      if (q % p.ns == 0) atomicAdd(&ctr->n_over_len, 1u);
+      L = 0;
+    }
+    q_nslots[q] = seed_slots(L, p.S, p.G);
   }
   // block max of L -> one atomic per block
   __shared__ unsigned int smax, simin;
@@ -228,9 +232,13 @@ __global__ void seed_select_kernel(ReadsView rv, EncView ev, Params p, const uin
       ns = nh = ovf = 0;
     }
   }
+  if (ovf) {  // more seed hits than a strand may hold: the strand is left out (stats.n_strands_over_hits)
+    for (uint32_t j = b; j < e; ++j) slot_hoff[j] = kUnused;
+    ns = nh = 0;
+    atomicAdd(&ctr->overflow, 1u);
+  }
   q_nseeds[q] = ns;
   q_nhits[q] = nh;
-  if (ovf) atomicExch(&ctr->overflow, 1u);
 }
 
 // locate: one lane per query, walking its seed slots (most slots carry no hit, and with the k-mer table's
@@ -1556,15 +1564,14 @@ static int run_sub_batch(mtsvgpu_index* h, Lane& ln, const Params& p, const uint
   clk.end();
   MTSV_TRY(fetch_counters(ln, d_ctr, &hc, st));
   if (hc.bad_offsets) return set_error(MTSVGPU_EINVAL, "seq_off is not monotone");
-  if (hc.max_len > kMaxReadLen)
-    return set_error(MTSVGPU_ELIMIT, "a read of %u bases exceeds this build's limit of %u", hc.max_len,
-                     kMaxReadLen);
+  ln.stats.n_reads_over_limit += hc.n_over_len;
   if (hc.total_slots > slot_bound)
     return set_error(MTSVGPU_ECUDA, "internal: seed slots %llu exceed bound %llu (reads [%llu,+%u), %llu bytes)",
                      hc.total_slots, (unsigned long long)slot_bound, (unsigned long long)read0, n_reads,
                      (unsigned long long)sub_bytes);
   const uint32_t n_slots = (uint32_t)hc.total_slots;
-  const uint32_t min_len = ~hc.inv_min_len;  // == max_len: every read of the sub-batch has the same length
+  // min_len == max_len: every read of the sub-batch has the same length (never when a read was left out)
+  const uint32_t min_len = hc.n_over_len ? 0u : ~hc.inv_min_len;
   ln.stats.n_seed_slots += n_slots;
   // (only now that the slot count is known to fit the buffers)
   clk.begin(ST_PREP);
@@ -1609,9 +1616,7 @@ static int run_sub_batch(mtsvgpu_index* h, Lane& ln, const Params& p, const uint
                               (uint64_t*)&d_ctr->total_hits, st));
   clk.end();
   MTSV_TRY(fetch_counters(ln, d_ctr, &hc, st));
-  if (hc.overflow)
-    return set_error(MTSVGPU_ELIMIT, "a single read-strand produced more than %u seed hits; lower max_hits",
-                     kMaxQueryHits);
+  ln.stats.n_strands_over_hits += hc.overflow;
   if (hc.total_hits > hit_cap || hc.total_hits > 0xfffffff0ull) {
     if (n_reads == 1)
       return set_error(MTSVGPU_ELIMIT, "one read produced %llu seed hits (cap %llu)", hc.total_hits,
@@ -1907,6 +1912,8 @@ int bin_batch_device(mtsvgpu_index* h, const uint8_t* d_seqs, const uint64_t* d_
     h->stats.window_bytes += ln.stats.window_bytes;
     h->stats.rank_queries += ln.stats.rank_queries;
     h->stats.n_sub_batches += ln.stats.n_sub_batches;
+    h->stats.n_reads_over_limit += ln.stats.n_reads_over_limit;
+    h->stats.n_strands_over_hits += ln.stats.n_strands_over_hits;
   }
   if (h->abort_rc != 0) {
     cudaStreamSynchronize(st);

@@ -522,8 +522,11 @@ MTSV_HD void seed_search_item(const FmView& fm, const KtabView& kt, const ReadWo
   }
   if (rank_steps) *rank_steps = steps;
   if (l < u) {
+    // bit 31 of the count is the direct-hit flag: an interval of 2^31 rows or more (possible beyond 2 Gbp with a
+    // very short seed) is clamped — far above any usable max_hits, and above kMaxQueryHits, so the strand is either
+    // dropped by the max-hits rule or counted as over the hit limit, exactly as with the true count
     *out_lo = l;
-    *out_cnt = u - l;
+    *out_cnt = u - l < kSlotCountMask ? u - l : kSlotCountMask;
   } else {
     *out_lo = 0;
     *out_cnt = 0;

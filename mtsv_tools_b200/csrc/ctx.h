@@ -57,7 +57,7 @@ struct BatchCounters {  // device-side scalars of one sub-batch
   unsigned long long total_slots, total_hits, total_cands, total_out;
   unsigned int max_len, overflow, n_warp, n_medium, n_large, bad_offsets, n_heavy, heavy_cursor, n_monster;
   unsigned int inv_min_len;  // ~(shortest read) so that a zeroed struct means "no read seen"
-  unsigned int n_ssw_full, reserved3;  // candidates of reads >= 254 bases that needed the full SW matrices
+  unsigned int n_ssw_full, n_over_len;  // candidates of reads >= 254 bases that needed the full SW matrices; reads over the length limit
   unsigned long long rank_steps[32], window_bytes[32];  // profiling only; spread to avoid one hot address
 };
 

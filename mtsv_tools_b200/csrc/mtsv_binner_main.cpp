@@ -281,7 +281,9 @@ void usage() {
           "  -t, --threads <n>              parser / formatter threads [default: all cores]\n"
           "      --gpu <id>                 first CUDA device [default: 0]\n"
           "      --gpus <n>                 number of CUDA devices; batches go round-robin [default: 1]\n"
-          "      --batch-reads <n>          reads per library call [default: 524288]\n");
+          "      --batch-reads <n>          reads per library call [default: 524288]\n"
+          "      --strict-limits            exit 2 when a read exceeded a limit of this implementation (reads longer\n"
+          "                                 than 4096 bases get no assignments; default: warn and go on)\n");
 }
 
 
@@ -523,7 +525,7 @@ int main(int argc, char** argv) {
   const char *fasta = nullptr, *fastq = nullptr, *index = nullptr, *results = nullptr;
   mtsvgpu_params p{0.13, 18, 15, 0.015, 2000, 200, -1, -1, 2, 0};
   uint64_t read_offset = 0, batch_reads = 1u << 19;
-  bool long_fmt = false, force = false, dump_reads = false;
+  bool long_fmt = false, force = false, dump_reads = false, strict_limits = false;
   int device = 0, n_gpus = 1, n_threads = 0;
   auto need = [&](int& i) -> const char* {
     if (i + 1 >= argc) {
@@ -553,6 +555,7 @@ int main(int argc, char** argv) {
     else if (a == "-v") g_verbose = true;
     else if (a == "--gpu") device = atoi(need(i));
     else if (a == "--gpus") n_gpus = atoi(need(i));
+    else if (a == "--strict-limits") strict_limits = true;
     else if (a == "--dump-reads") dump_reads = true;  // test hook: parse the input, print "id<TAB>seq", no GPU
     else if (a == "--dump-reads-mt") dump_reads = true, n_threads = n_threads ? n_threads : -1;  // same through the pipeline's scanner + parser
     else if (a == "--batch-reads") batch_reads = strtoull(need(i), nullptr, 10);
@@ -773,7 +776,7 @@ int main(int argc, char** argv) {
   std::condition_variable wcv;
   std::map<uint64_t, std::shared_ptr<Batch>> done;  // formatted (or empty) batches by sequence number
   uint64_t batches_total = ~0ull;                   // known once the input is exhausted
-  std::atomic<uint64_t> total_reads{0}, total_lines{0};
+  std::atomic<uint64_t> total_reads{0}, total_lines{0}, over_len{0}, over_hits{0};
 
   auto take_batch = [&]() -> std::shared_ptr<Batch> {
     std::lock_guard<std::mutex> blk(bmu);
@@ -845,6 +848,11 @@ int main(int argc, char** argv) {
           break;
         }
         ms_call = since(tc0);
+        mtsvgpu_batch_stats bst;
+        if (mtsvgpu_last_batch_stats(ix, &bst) == 0) {
+          over_len += bst.n_reads_over_limit;
+          over_hits += bst.n_strands_over_hits;
+        }
         b->hits.assign(hits, hits + n_hits);  // the handle's buffers are reused by its next batch
         b->hit_off.assign(hit_off, hit_off + b->n_reads + 1);
         logf("DEBUG", "gpu %d batch %llu: %llu reads, %llu hits; waited+gathered %.1f ms, library call %.1f ms, results copied %.1f ms",
@@ -936,6 +944,13 @@ int main(int argc, char** argv) {
     code = 11;
   }
   if (code) return code;
+  if (over_len.load() || over_hits.load()) {
+    // the reference has no such limits: say so loudly (README "Limits"); --strict-limits turns it into a failure
+    logf("WARN", "%llu read(s) longer than %d bases and %llu read strand(s) with more than 2^26 seed hits were reported "
+                 "without assignments (limits of this implementation)",
+         (unsigned long long)over_len.load(), MTSVGPU_MAX_READ_LEN, (unsigned long long)over_hits.load());
+    if (strict_limits) return 2;
+  }
   double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   logf("INFO", "All reads binned: %llu reads, %llu result lines. Took %.3f seconds.",
        (unsigned long long)total_reads.load(), (unsigned long long)total_lines.load(), secs);

@@ -180,7 +180,8 @@ class MGIndex:
         s = StatsStruct()
         check(_lib.load_library().mtsvgpu_last_batch_stats(self._h, C.byref(s)))
         d = {n: int(getattr(s, n)) for n in ("n_queries", "n_seed_slots", "n_seed_hits", "n_candidates",
-                                            "n_hits", "window_bytes", "rank_queries", "n_sub_batches", "h2d_bytes")}
+                                            "n_hits", "window_bytes", "rank_queries", "n_sub_batches", "h2d_bytes",
+                                            "n_reads_over_limit", "n_strands_over_hits")}
         d["ms"] = {name: float(s.ms[i]) for i, name in enumerate(_lib.STAGE_NAMES)}
         return d
 

@@ -240,6 +240,39 @@ def test_pipeline_ragged_and_garbage(oracle, small_ref, small_index):
             assert [tuple(h) for h in got] == want
 
 
+def test_reads_over_the_length_limit_do_not_fail_the_batch(oracle, small_ref, small_index):
+    """A read longer than MTSVGPU_MAX_READ_LEN is reported without hits and counted; every other read of the batch
+    gets exactly the oracle's result (the reference itself has no such limit: README "Limits")."""
+    cat, off, gi, tax = small_ref
+    reads = synth.make_reads(cat, off, 2000, 150, seed=71)
+    lst = [reads[0][int(reads[1][i]):int(reads[1][i + 1])].tobytes() for i in range(2000)]
+    big1, big2 = bytes(cat[100:5100]), bytes(cat[20000:140000])
+    lst.insert(700, big1)
+    lst.insert(1500, big2)
+    lst.append(bytes(cat[5:4101]))  # 4096 bases: the longest read that is still processed
+    po, pg = _params(oracle)
+    keep = [i for i in range(len(lst)) if i not in (700, 1500)]
+    for opts in ({}, {"batch_reads": 300}):
+        with _gpu_index(small_index, **opts) as g:
+            for entry in ("bin_reads", "packed"):
+                if entry == "packed":
+                    from mtsv_tools_b200.index import pack_reads_planes
+                    pk, po_ = pack_reads_planes(lst)
+                    h2, o2 = g.bin_reads_packed(pk, po_, pg)
+                    h2, o2 = h2.copy(), o2.copy()
+                else:
+                    h2, o2 = g.bin_reads(lst, pg)
+                st = g.last_batch_stats()
+                assert st["n_reads_over_limit"] == 2 and st["n_strands_over_hits"] == 0
+                cnt = o2[1:] - o2[:-1]
+                assert cnt[700] == 0 and cnt[1500] == 0
+                h1, o1 = small_index.bin_reads([lst[i] for i in keep], po, threads=8)
+                assert np.array_equal(cnt[keep], o1[1:] - o1[:-1])
+                for f in ("tax_id", "gi", "offset", "edit"):
+                    assert np.array_equal(h2[f], h1[f]), (opts, entry, f)
+                assert (o1[-1] - o1[-2]) >= 1  # the 4096-base read maps
+
+
 def test_pipeline_n_rich_reference(oracle):
     """N runs in the reference and reads sampled across them (see tests/test_emul_parity.py::_n_rich_case)."""
     from tests.test_emul_parity import _n_rich_case
