@@ -123,11 +123,20 @@ __global__ void __launch_bounds__(256) chunk_push_kernel(PeerTable pt, CommLayou
   __threadfence_system();
 }
 
-__global__ void chunk_signal_kernel(PeerTable pt, uint32_t world, uint32_t rank, uint32_t epoch) {
+__global__ void chunk_signal_kernel(PeerTable pt, uint32_t world, uint32_t rank, uint32_t epoch, int variant) {
   const uint32_t d = threadIdx.x;
   if (d >= world) return;
-  __threadfence_system();
-  st_release_sys(&reinterpret_cast<CommHeader*>(pt.base[d])->flags[rank], epoch);
+  uint32_t* flag = &reinterpret_cast<CommHeader*>(pt.base[d])->flags[rank];
+  if (variant == 0) {
+    __threadfence_system();
+    st_release_sys(flag, epoch);
+  } else if (variant == 1) {
+    st_release_sys(flag, epoch);
+  } else {
+    // every pushing thread fenced its own stores at system scope before the push kernel ended, and this kernel
+    // starts after that one has completed: the flag cannot overtake the data
+    asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(epoch) : "memory");
+  }
 }
 
 // status: 0 ok, 1 a rank overflowed its slot, 2 timed out waiting for a peer
@@ -170,6 +179,7 @@ struct mtsvgpu_comm {
   PeerTable peers{};        // peers' buffers as mapped into this process (base[rank] = base)
   bool connected = false;
   uint32_t epoch = 0;
+  long long timeout_cycles = 60000000000ll;  // set from the SM clock at creation (the attribute query is a slow driver call)
   uint32_t* d_status = nullptr;    // [0] wait status, [1] overflow flag
   uint32_t* h_status = nullptr;    // mapped page-locked copy of the wait status
   uint32_t* h_status_dev = nullptr;
@@ -246,6 +256,11 @@ int comm_create(int device, uint32_t rank, uint32_t world, uint64_t max_local_re
   MTSV_CUDA_TRY(cudaMalloc((void**)&c->out, ((uint64_t)world * max_hits_per_source + 1) * sizeof(mtsvgpu_taxhit)));
   MTSV_CUDA_TRY(cudaMalloc((void**)&c->out_off, (max_local_reads + 1) * 8));
   MTSV_CUDA_TRY(cudaDeviceSynchronize());
+  {
+    int clock_khz = 2000000;
+    if (cudaDeviceGetAttribute(&clock_khz, cudaDevAttrClockRate, device) != cudaSuccess) (void)cudaGetLastError();
+    c->timeout_cycles = (long long)clock_khz * 1000ll * 30ll;
+  }
   HandleBlob blob;
   memset(&blob, 0, sizeof blob);
   blob.magic = kCommMagic;
@@ -306,6 +321,7 @@ int bin_batch_chunked(mtsvgpu_index* h, mtsvgpu_comm* c, const uint8_t* d_seqs, 
   cudaStream_t st = h->stream;
   static const bool trace = getenv("MTSV_B200_TRACE") != nullptr;  // phase times on stderr
   cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  static const bool no_host_status = getenv("MTSV_B200_CHUNK_NOHOST") != nullptr;  // experiment knob
   if (trace) {
     for (auto& e : ev) cudaEventCreate(&e);
     cudaEventRecord(ev[0], st);
@@ -323,11 +339,12 @@ int bin_batch_chunked(mtsvgpu_index* h, mtsvgpu_comm* c, const uint8_t* d_seqs, 
                 c->rank, parity, d_overflow);
   }
   if (trace) cudaEventRecord(ev[1], st);
-  MTSV_LAUNCH(chunk_signal_kernel, 1, 32, 0, st, c->peers, c->world, c->rank, epoch);
-  int clock_khz = 1965000;
-  cudaDeviceGetAttribute(&clock_khz, cudaDevAttrClockRate, c->device);
-  const long long timeout_cycles = (long long)clock_khz * 1000ll * 30ll;  // 30 s: a peer that never arrives is an error
-  MTSV_LAUNCH(chunk_wait_kernel, 1, 32, 0, st, c->base, c->world, epoch, timeout_cycles, c->d_status, c->h_status_dev);
+  static const int sig_variant = getenv("MTSV_B200_CHUNK_SIGNAL") ? atoi(getenv("MTSV_B200_CHUNK_SIGNAL")) : 1;
+  MTSV_LAUNCH(chunk_signal_kernel, 1, 32, 0, st, c->peers, c->world, c->rank, epoch, sig_variant);
+  const long long timeout_cycles = c->timeout_cycles;  // 30 s: a peer that never arrives is an error
+  if (trace) cudaEventRecord(ev[4], st);
+  MTSV_LAUNCH(chunk_wait_kernel, 1, 32, 0, st, c->base, c->world, epoch, timeout_cycles, c->d_status,
+              no_host_status ? c->d_status + 2 : c->h_status_dev);
   if (trace) cudaEventRecord(ev[2], st);
   // ---- merge epilogue over the world slots of my range (src/collapse.rs:597-602) ----
   const mtsvgpu_hit* part_hits[kMaxRanks];
@@ -345,12 +362,13 @@ int bin_batch_chunked(mtsvgpu_index* h, mtsvgpu_comm* c, const uint8_t* d_seqs, 
   MTSV_CUDA_TRY(cudaMemcpyAsync(&total, c->d_n_out, 8, cudaMemcpyDeviceToHost, st));
   MTSV_CUDA_TRY(cudaStreamSynchronize(st));  // the batch's one host synchronisation after the local binning
   if (trace) {
-    float a = 0, b = 0, d = 0;
+    float a = 0, b = 0, d = 0, sg = 0;
     cudaEventElapsedTime(&a, ev[0], ev[1]);
-    cudaEventElapsedTime(&b, ev[1], ev[2]);
+    cudaEventElapsedTime(&sg, ev[1], ev[4]);
+    cudaEventElapsedTime(&b, ev[4], ev[2]);
     cudaEventElapsedTime(&d, ev[2], ev[3]);
-    fprintf(stderr, "[mtsv_b200 trace] rank %u chunked batch: %llu hits, push %.3f ms, signal+wait %.3f ms, merge %.3f ms\n",
-            c->rank, (unsigned long long)n_hits, a, b, d);
+    fprintf(stderr, "[mtsv_b200 trace] rank %u chunked batch: %llu hits, push %.3f ms, signal %.3f ms, wait %.3f ms, merge %.3f ms\n",
+            c->rank, (unsigned long long)n_hits, a, sg, b, d);
     for (auto& e : ev) cudaEventDestroy(e);
   }
   const uint32_t status = c->h_status[0];
