@@ -248,6 +248,68 @@ def _chunk_refs(world):
     return refs, cat, off
 
 
+def _hybrid_worker(rank, world, n_chunks, port, n_reads, out):
+    """Hybrid operation: rank r holds chunk r % n_chunks and works on read shard r // n_chunks; each shard's ranks
+    form their own exchange group (a torch.distributed sub-group and a communicator of n_chunks ranks)."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from mtsv_tools_b200 import MGIndex, Params, synth
+        dev = rank % torch.cuda.device_count()
+        torch.cuda.set_device(dev)
+        groups = chunked.hybrid_groups(world, n_chunks)
+        group = None
+        for g in groups:
+            pg = dist.new_group(g)
+            if rank in g:
+                group = pg
+        shard, chunk = rank // n_chunks, rank % n_chunks
+        refs, cat, off = _chunk_refs(n_chunks)
+        r = refs[chunk]
+        with MGIndex.build(r[0], r[1], r[2], r[3], device=dev) as gix:
+            comm = chunked.ChunkComm(dev, max_local_reads=-(-n_reads // n_chunks), max_hits_per_source=200000, group=group)
+            try:
+                reads, roff = synth.make_reads(cat, off, n_reads, 150, seed=80 + shard)
+                first, pairs, offs = comm.bin_reads_tensors(gix, torch.from_numpy(reads).cuda(),
+                                                            torch.from_numpy(roff.astype(np.int64)).cuda(), n_reads, Params())
+                out.put((rank, (first, pairs.cpu().numpy().astype(np.uint32), offs.cpu().numpy().astype(np.uint64))))
+            finally:
+                comm.close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_hybrid_chunk_groups_times_read_shards(oracle):
+    """4 ranks = 2 chunks x 2 read shards: every shard's reads meet both chunks inside their own
+    group; results equal the oracle's merge per shard."""
+    from mtsv_tools_b200 import synth
+    world, n_chunks, n_reads = 4, 2, 2000
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_hybrid_worker, args=(r, world, n_chunks, port, n_reads, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=600) for _ in range(world))
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    refs, cat, off = _chunk_refs(n_chunks)
+    idx = [oracle.Index.build((r[0], r[1]), r[2], r[3], 64, 32) for r in refs]
+    for shard in range(world // n_chunks):
+        reads = synth.make_reads(cat, off, n_reads, 150, seed=80 + shard)
+        want_pairs, want_off = oracle.collapse_taxid([ix.bin_reads(reads, oracle.default_params(), threads=4) for ix in idx])
+        bounds = chunked.read_ranges(n_reads, n_chunks)
+        for c in range(n_chunks):
+            first, pairs, offs = got[shard * n_chunks + c]
+            assert first == bounds[c]
+            a, e = int(want_off[bounds[c]]), int(want_off[bounds[c + 1]])
+            assert np.array_equal(pairs, want_pairs[a:e]) and len(pairs) > 100
+            assert np.array_equal(offs, want_off[bounds[c]:bounds[c + 1] + 1] - want_off[bounds[c]])
+
+
 def _fused_worker(rank, world, port, n_batches, n_reads, cap, out):
     """One rank of the fused chunk-sharded path.  With fewer GPUs than ranks the ranks share device 0: CUDA IPC
     works between processes on one device too, the peer stores are then local stores."""
