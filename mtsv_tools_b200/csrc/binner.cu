@@ -1441,9 +1441,9 @@ int run_segmented_sort(cudaStream_t st, DevBuf& worklist, uint64_t* keys, const 
   MTSV_CUDA_TRY(cudaMemsetAsync(&d_ctr->n_warp, 0, 3 * sizeof(unsigned int), st));
   MTSV_LAUNCH(sort_classify_kernel, (nq + 255) / 256, 256, 0, st, seg_cnt, nq, min_count, lists, lists + nq,
               lists + 2 * (size_t)nq, d_ctr);
-  MTSV_LAUNCH(sort_warp_kernel, 148 * 8, 256, 0, st, keys, seg_off, seg_cnt, lists, d_ctr);
-  MTSV_LAUNCH(sort_medium_kernel, 148 * 4, 512, 0, st, keys, seg_off, seg_cnt, lists + nq, d_ctr);
-  MTSV_LAUNCH(sort_large_kernel, 148, 1024, 0, st, keys, seg_off, seg_cnt, lists + 2 * (size_t)nq, d_ctr);
+  MTSV_LAUNCH(sort_warp_kernel, sm_count() * 8, 256, 0, st, keys, seg_off, seg_cnt, lists, d_ctr);
+  MTSV_LAUNCH(sort_medium_kernel, sm_count() * 4, 512, 0, st, keys, seg_off, seg_cnt, lists + nq, d_ctr);
+  MTSV_LAUNCH(sort_large_kernel, sm_count(), 1024, 0, st, keys, seg_off, seg_cnt, lists + 2 * (size_t)nq, d_ctr);
   MTSV_CUDA_TRY(cudaGetLastError());
   return 0;
 }
@@ -1651,10 +1651,10 @@ static int run_sub_batch(mtsvgpu_index* h, Lane& ln, const Params& p, const uint
                 ws.hit_off.as<uint32_t>(), ws.q_nhits.as<uint32_t>(), ws.q_nseeds.as<uint32_t>(),
                 ws.hit_keys.as<uint64_t>(), ws.cand_sparse.as<CandRec>(), ws.q_ncand.as<uint32_t>(),
                 ws.worklist.as<uint32_t>(), ws.worklist.as<uint32_t>() + nq, d_ctr);
-    MTSV_LAUNCH(coalesce_heavy_kernel, 148 * 16, 128, 0, st, ix.bins_view(), rv, p, ws.hit_off.as<uint32_t>(),
+    MTSV_LAUNCH(coalesce_heavy_kernel, sm_count() * 16, 128, 0, st, ix.bins_view(), rv, p, ws.hit_off.as<uint32_t>(),
                 ws.q_nhits.as<uint32_t>(), ws.q_nseeds.as<uint32_t>(), ws.hit_keys.as<uint64_t>(),
                 ws.cand_sparse.as<CandRec>(), ws.q_ncand.as<uint32_t>(), ws.worklist.as<uint32_t>(), d_ctr);
-    MTSV_LAUNCH(coalesce_monster_kernel, 148, 1024, 0, st, ix.bins_view(), rv, p, ws.hit_off.as<uint32_t>(),
+    MTSV_LAUNCH(coalesce_monster_kernel, sm_count(), 1024, 0, st, ix.bins_view(), rv, p, ws.hit_off.as<uint32_t>(),
                 ws.q_nhits.as<uint32_t>(), ws.q_nseeds.as<uint32_t>(), ws.hit_keys.as<uint64_t>(),
                 ws.cand_sparse.as<CandRec>(), ws.cand_stage.as<CandRec>(), ws.q_ncand.as<uint32_t>(),
                 ws.worklist.as<uint32_t>() + nq, d_ctr);

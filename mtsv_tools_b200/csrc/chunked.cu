@@ -333,7 +333,7 @@ int bin_batch_chunked(mtsvgpu_index* h, mtsvgpu_comm* c, const uint8_t* d_seqs, 
   MTSV_LAUNCH(chunk_check_kernel, 1, 32, 0, st, c->peers, c->lay, d_hit_off, n_reads, step, c->rank, epoch, d_overflow);
   {
     const uint64_t per_dest = std::max<uint64_t>(step, (n_hits / c->world + 1) * 3);
-    unsigned gx = (unsigned)std::min<uint64_t>(148 * 2, (per_dest + 2047) / 2048);
+    unsigned gx = (unsigned)std::min<uint64_t>(sm_count() * 2, (per_dest + 2047) / 2048);
     if (gx == 0) gx = 1;
     MTSV_LAUNCH(chunk_push_kernel, dim3(gx, c->world), 256, 0, st, c->peers, c->lay, d_hits, d_hit_off, n_reads, step,
                 c->rank, parity, d_overflow);

@@ -18,6 +18,7 @@
 namespace mtsv {
 
 int set_error(int code, const char* fmt, ...);
+unsigned sm_count();  // SMs of the current device (cached)
 extern std::atomic<uint64_t> g_launches;
 
 #define MTSV_CUDA_TRY(expr)                                                                  \

@@ -35,7 +35,7 @@ struct RsPlan {
 
 RsPlan rs_plan(uint64_t n) {
   const uint64_t tiles = (n + kRsTile - 1) / kRsTile;
-  uint64_t tpc = tiles / (148 * 16);  // >= 16 chunks per SM when the input is large enough
+  uint64_t tpc = tiles / ((uint64_t)sm_count() * 16);  // >= 16 chunks per SM when the input is large enough
   if (tpc < 1) tpc = 1;
   if (tpc > 64) tpc = 64;
   RsPlan p;

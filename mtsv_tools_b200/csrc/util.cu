@@ -20,6 +20,23 @@ int set_error(int code, const char* fmt, ...) {
 
 const char* last_error_cstr() { return g_last_error.c_str(); }
 
+// SMs of the current device (grids of the worklist-driven kernels are sized in multiples of it); the attribute
+// query is a driver call, so it is made once per device
+unsigned sm_count() {
+  static std::atomic<int> cached[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  int n = cached[dev].load(std::memory_order_relaxed);
+  if (n == 0) {
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) {
+      (void)cudaGetLastError();
+      n = 148;
+    }
+    cached[dev].store(n, std::memory_order_relaxed);
+  }
+  return (unsigned)n;
+}
+
 int DevBuf::reserve(size_t bytes) {
   if (bytes <= cap && p) return 0;
   if (p) {

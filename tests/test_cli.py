@@ -152,3 +152,94 @@ def test_cli_end_to_end(oracle, tmp_path):
     assert r.returncode == 0, r.stderr
     h2, o2 = ix.bin_reads((rc, ro), oracle.default_params(edit_rate=0.05, seed_gap=10, max_candidates=2), threads=4)
     assert res.read_text() == "".join(oracle.results_lines(names, h2, o2, False))
+
+
+# ------------------------------------------------------------------------------------------------
+# mtsv-build (mtsv_tools_b200/csrc/mtsv_build_main.cpp): src/bin/mtsv-build.rs, src/builder.rs, src/io.rs:35-184
+# ------------------------------------------------------------------------------------------------
+BUILD = os.path.join(ROOT, "mtsv_tools_b200", "bin", "mtsv-build")
+
+
+def _build(*args):
+    return subprocess.run([BUILD, *args], capture_output=True, text=True)
+
+
+def test_mtsv_build_input_errors_without_gpu(tmp_path):
+    """Everything that fails before the index is built exits 1 with the reference's messages: header format
+    (src/util.rs:26-55), mapping file rules (src/io.rs:35-112), records missing from the mapping (:153-184)."""
+    fa = tmp_path / "db.fa"
+    fa.write_text(">12-34\nACGT\n>56-78-9\nACGT\n")
+    r = _build("--fasta", str(fa), "--index", str(tmp_path / "x.index"))
+    assert r.returncode == 1 and "Invalid header: 56-78-9" in r.stderr
+    fa.write_text(">12-34\nACGT\n>ab-78\nACGT\n")
+    r = _build("--fasta", str(fa), "--index", str(tmp_path / "x.index"))
+    assert r.returncode == 1 and "Invalid integer: ab" in r.stderr
+    assert _build("--fasta", str(fa)).returncode == 1  # --index is required
+    assert _build("--fasta", str(tmp_path / "nope.fa"), "--index", str(tmp_path / "x.index")).returncode == 1
+    fa.write_text(">foo desc\nACGT\n>bar\nTTTT\n")
+    mp = tmp_path / "map.tsv"
+    mp.write_text("header\ttaxid\n foo\t2\n")
+    r = _build("--fasta", str(fa), "--index", str(tmp_path / "x.index"), "--mapping", str(mp))
+    assert r.returncode == 1 and "Missing 'seqid' column" in r.stderr
+    mp.write_text("Header, TaxID, GI\nfoo, 2, 1\nfoo, 3, 4\n")
+    r = _build("--fasta", str(fa), "--index", str(tmp_path / "x.index"), "--mapping", str(mp))
+    assert r.returncode == 1 and "Duplicate header mapping for foo" in r.stderr
+    mp.write_text("header taxid seqid\nfoo 2 1\n")
+    r = _build("--fasta", str(fa), "--index", str(tmp_path / "x.index"), "--mapping", str(mp))
+    assert r.returncode == 1 and "Missing mapping for header bar" in r.stderr
+    mp.write_text("header taxid seqid\nfoo x 1\n")
+    r = _build("--fasta", str(fa), "--index", str(tmp_path / "x.index"), "--mapping", str(mp))
+    assert r.returncode == 1 and "Invalid integer: x" in r.stderr
+
+
+@pytest.mark.gpu
+def test_mtsv_build_writes_the_oracles_index_and_feeds_the_binner(oracle, tmp_path):
+    from mtsv_tools_b200 import synth
+    cat, off, gi, tax = synth.make_reference(9, 15000, seed=3, n_frac=0.002, shared_frac=0.1)
+    tax = np.array([7, 3, 9, 3, 5, 7, 1, 9, 2], dtype=np.uint32)
+    fa = tmp_path / "db.fa.gz"
+    with gzip.open(fa, "wt") as f:
+        for i in range(9):
+            s = bytes(cat[int(off[i]):int(off[i + 1])]).decode()
+            s = s[:5000].lower() + s[5000:]  # lower case is folded (src/index.rs:543-553)
+            f.write(">%d-%d some text\n" % (gi[i], tax[i]))
+            for j in range(0, len(s), 60):
+                f.write(s[j:j + 60] + "\n")
+    ix = oracle.Index.build((cat, off), gi, tax, 64, 32)
+    want = tmp_path / "oracle.index"
+    ix.write(str(want))
+    out = tmp_path / "gpu.index"
+    r = _build("--fasta", str(fa), "--index", str(out))
+    assert r.returncode == 0, r.stderr
+    assert out.read_bytes() == want.read_bytes()
+    # other intervals; mapping file instead of ACCESSION-TAXID headers, one record skipped
+    ix2 = oracle.Index.build((cat[:int(off[8])], off[:9]), gi[:8], tax[:8], 128, 16)
+    ix2.write(str(want))
+    fa2 = tmp_path / "db2.fa"
+    mp = tmp_path / "map.csv"
+    with open(fa2, "w") as f, open(mp, "w") as m:
+        m.write("seqid,header,taxid\n")
+        for i in range(9):
+            f.write(">seq_%d\n%s\n" % (i, bytes(cat[int(off[i]):int(off[i + 1])]).decode()))
+            if i < 8:
+                m.write("%d,seq_%d,%d\n" % (gi[i], i, tax[i]))
+    r = _build("--fasta", str(fa2), "--index", str(out), "--mapping", str(mp), "--skip-missing",
+               "--sample-interval", "128", "--sa-sample", "16")
+    assert r.returncode == 0 and "Missing mapping for header seq_8, skipping" in r.stderr, r.stderr
+    assert out.read_bytes() == want.read_bytes()
+    r = _build("--fasta", str(fa2), "--index", str(out), "--mapping", str(mp))
+    assert r.returncode == 1
+    # the index the GPU builder wrote drives the binner binary to the oracle's result lines
+    r = _build("--fasta", str(fa), "--index", str(out))
+    assert r.returncode == 0
+    rc, ro = synth.make_reads(cat, off, 1000, 150, seed=4)
+    names = ["r%d" % i for i in range(1000)]
+    fq = tmp_path / "reads.fa"
+    with open(fq, "w") as f:
+        for i, n in enumerate(names):
+            f.write(">%s\n%s\n" % (n, bytes(rc[int(ro[i]):int(ro[i + 1])]).decode()))
+    res = tmp_path / "res.txt"
+    r = _run("--fasta", str(fq), "--index", str(out), "--results", str(res))
+    assert r.returncode == 0, r.stderr
+    hits, offs = ix.bin_reads((rc, ro), oracle.default_params(), threads=4)
+    assert res.read_text() == "".join(oracle.results_lines(names, hits, offs, False))
