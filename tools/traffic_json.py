@@ -13,6 +13,8 @@ WANT = {
     "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active": "fma_pipe_pct_of_peak",
     "smsp__issue_active.avg.pct_of_peak_sustained_active": "issue_active_pct",
     "sm__warps_active.avg.pct_of_peak_sustained_active": "warps_active_pct",
+    "smsp__inst_executed_pipe_alu.sum": "alu_inst", "smsp__inst_executed.sum": "inst",
+    "launch__grid_size": "grid", "launch__block_size": "block",
 }
 UNIT = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "ms": 1e-3, "us": 1e-6, "ns": 1e-9, "s": 1.0,
         "usecond": 1e-6, "msecond": 1e-3, "nsecond": 1e-9, "second": 1.0}
@@ -43,4 +45,11 @@ for path in sys.argv[1:]:
                  "alu_pipe_pct_of_peak": avg("alu_pipe_pct_of_peak"), "fma_pipe_pct_of_peak": avg("fma_pipe_pct_of_peak"),
                  "issue_active_pct": avg("issue_active_pct"), "warps_active_pct": avg("warps_active_pct"),
                  "launches_captured": n, "source": path}
+    threads = sum(l.get("grid", 0.0) * l.get("block", 0.0) for l in launches)
+    if threads and any("alu_inst" in l for l in launches):
+        # thread-per-work-item kernels: ALU-pipe warp instructions per work item (grid x block threads, the last
+        # block padded), summed over the captured launches (one step)
+        out[name]["alu_warp_inst_per_launch"] = sum(l.get("alu_inst", 0.0) for l in launches) / n
+        out[name]["warp_inst_per_launch"] = sum(l.get("inst", 0.0) for l in launches) / n
+        out[name]["alu_warp_inst_per_candidate"] = sum(l.get("alu_inst", 0.0) for l in launches) / threads
 print(json.dumps(out, indent=1))
