@@ -37,6 +37,11 @@ CONFIGS = {
     "cfg4": dict(n_seqs=500, seq_len=2_000_000, shared=0.0, div=0.0, strains=dict(base_len=2_000_000, div=0.003),
                  reads=2_000_000, read_len=75, flags={},
                  label="cfg4: 500 strains x 2 Mbp at 0.3 % divergence, 75 bp reads, default flags"),
+    # config 4 with the strains filed under 50 species TaxIDs (ten genomes each), the way reference databases carry
+    # many assemblies per TaxID: the reference stops a TaxID at its first passing window (src/index.rs:393-396)
+    "cfg4b": dict(n_seqs=500, seq_len=2_000_000, shared=0.0, div=0.0, strains=dict(base_len=2_000_000, div=0.003),
+                  per_taxid=10, reads=2_000_000, read_len=75, flags={},
+                  label="cfg4b: 500 strains x 2 Mbp at 0.3 % divergence under 50 TaxIDs, 75 bp reads, default flags"),
     # config 5: 250 bp reads at edit-rate 0.2 with dense seeding: verifier stress
     "cfg5": dict(n_seqs=40, seq_len=5_000_000, shared=0.10, div=0.01, reads=2_000_000, read_len=250,
                  flags=dict(edit_rate=0.2, seed_gap=3), read_sub=0.12,
@@ -99,7 +104,7 @@ def make_reference_torch(cfg, seed, device):
         cat[idx[m]] = ord("N")
     off = np.arange(n_seqs + 1, dtype=np.uint64) * np.uint64(seq_len)
     gi = np.arange(1, n_seqs + 1, dtype=np.uint32)
-    tax = (1000 + np.arange(n_seqs)).astype(np.uint32)
+    tax = (1000 + np.arange(n_seqs) // cfg.get("per_taxid", 1)).astype(np.uint32)
     return cat, off, gi, tax
 
 
@@ -797,7 +802,7 @@ def run_gpu_arm(args, name, cfg, ctx):
         rw_m.pop("cpu_baseline", None)
         others["cfg2_ragged"] = dict(strip(rw_m), note="cfg2 with every read trimmed to 100-150 bases: per-slot offsets, "
                                      "non-uniform verifier, seq_off uploaded")
-        for oname in ("cfg1", "cfg4", "cfg5"):
+        for oname in ("cfg1", "cfg4", "cfg4b", "cfg5"):
             try:
                 om, ow = measure(args, oname, CONFIGS[oname], ctx, max(2, args.steps // 2), 3, cpu_seconds=args.other_cpu_seconds)
                 ow.close()

@@ -876,7 +876,13 @@ struct BinnerJobs {
   const uint32_t* cand_off;
   const uint32_t* order;
   const uint8_t* text;
-  uint32_t n;
+  uint32_t n;             // upper bound on the jobs (sizes the grid)
+  const uint32_t* n_dev;  // when set: the actual number of jobs, known only on the device (compacted lists)
+  __device__ __forceinline__ uint32_t count() const {
+    if (!n_dev) return n;
+    const uint32_t m = __ldg(n_dev);
+    return m < n ? m : n;
+  }
   __device__ __forceinline__ VerifyJob get(uint32_t i) const {
     VerifyJob j;
     uint32_t ci = order[i];
@@ -903,6 +909,7 @@ struct PairJobs {
   const uint8_t* texts;
   const uint64_t* text_off;
   uint32_t n;
+  __device__ __forceinline__ uint32_t count() const { return n; }
   __device__ __forceinline__ VerifyJob get(uint32_t i) const {
     VerifyJob j;
     j.enc = ev.words + query_word_off(pv, ev, 1, i);
@@ -922,7 +929,7 @@ __global__ void __launch_bounds__(kVerifyThreads) verify_kernel(Jobs jobs, uint3
                                                                 BatchCounters* __restrict__ ctr) {
   extern __shared__ uint64_t peq[];  // [NCLS][W][kVerifyThreads] when SMEM_PEQ
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= jobs.n) return;
+  if (i >= jobs.count()) return;
   VerifyJob job = jobs.get(i);
   if (job.skip) {
     out[job.out] = kNoEdit;
@@ -1029,12 +1036,14 @@ __global__ void __launch_bounds__(kVerifyThreads) verify_warp_kernel(BinnerJobs 
   job.out = 0;
   job.enc = nullptr;
   uint32_t start = 0;
-  if (i < jobs.n) {
+  const uint32_t n_jobs = jobs.count();
+  if (blockIdx.x * blockDim.x >= n_jobs) return;  // (grids are sized by the upper bound)
+  if (i < n_jobs) {
     job = jobs.get(i);
     start = (uint32_t)(job.txt - jobs.text);
   }
-  bool live = i < jobs.n && !job.skip && job.L != 0;
-  if (i < jobs.n && !live) out[job.out] = job.skip ? kNoEdit : 0u;  // L == 0: src/align.rs test_empty
+  bool live = i < n_jobs && !job.skip && job.L != 0;
+  if (i < n_jobs && !live) out[job.out] = job.skip ? kNoEdit : 0u;  // L == 0: src/align.rs test_empty
   const uint32_t L = job.L;
   const int nb = live ? (int)((L - 1) >> 6) : -1;
 #pragma unroll
@@ -1083,7 +1092,7 @@ __global__ void __launch_bounds__(128) ssw_band_kernel(BinnerJobs jobs, const ui
                                                        const uint32_t* __restrict__ cand_edit,
                                                        uint32_t* __restrict__ list, unsigned int* __restrict__ n_list) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= jobs.n) return;
+  if (i >= jobs.count()) return;
   VerifyJob job = jobs.get(i);
   if (job.skip || job.L < 254) return;
   const uint32_t edit = cand_edit[job.out];
@@ -1369,6 +1378,115 @@ __global__ void cand_order_kernel(const CandRec* __restrict__ cand, const uint32
   uint32_t mb = multi_before[i], n_multi = multi_before[n];
   uint32_t pos = cand[i].num_seeds > 1 ? mb : n_multi + (i - mb);
   order[pos] = i;
+}
+
+// ------------------------------------------------------------------------------------------
+// Verification in two rounds (strands with several candidates per TaxID).  The reference walks a strand's ranked
+// candidates and skips every candidate whose TaxID has already matched (src/index.rs:393-396): the later windows
+// of a TaxID are only ever aligned when the earlier ones fail.  Here: the first candidate of every
+// (strand, TaxID) group — its leader — is verified in round one; the other members only in round two, and only
+// when their leader did not pass.  A member that is never verified keeps "no edit distance", which is what the
+// selection does with it anyway (its TaxID has matched).  lead[c] = index of c's leader (c itself for leaders).
+// ------------------------------------------------------------------------------------------
+constexpr uint32_t kLeaderSlots = 1024;  // per-warp hash map TaxID -> leader, for strands of up to 512 candidates
+
+__global__ void __launch_bounds__(128) cand_leader_kernel(BinsView bv, uint32_t nq, const uint32_t* __restrict__ cand_off,
+                                                          const CandRec* __restrict__ cand, uint32_t* __restrict__ lead) {
+  __shared__ uint32_t s_key[4][kLeaderSlots];
+  __shared__ uint32_t s_val[4][kLeaderSlots];
+  const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t b = 0, nc = 0;
+  if (q < nq) {
+    b = cand_off[q];
+    nc = cand_off[q + 1] - b;
+  }
+  if (nc && nc <= kLightItems) {
+    for (uint32_t i = 0; i < nc; ++i) {
+      const uint32_t tax = ldg(&bv.tax[cand[b + i].bin]);
+      uint32_t l = b + i;
+      for (uint32_t j = 0; j < i; ++j)
+        if (ldg(&bv.tax[cand[b + j].bin]) == tax) {
+          l = b + j;
+          break;
+        }
+      lead[b + i] = l;
+    }
+  }
+  unsigned heavy = __ballot_sync(0xffffffffu, nc > kLightItems);
+  while (heavy) {
+    const int sl = __ffs(heavy) - 1;
+    heavy &= heavy - 1;
+    const uint32_t nc_s = __shfl_sync(0xffffffffu, nc, sl), b_s = __shfl_sync(0xffffffffu, b, sl);
+    if (nc_s > kLeaderSlots / 2) {  // too many for the map: every candidate is its own leader (all are verified)
+      for (uint32_t i = lane; i < nc_s; i += 32) lead[b_s + i] = b_s + i;
+      continue;
+    }
+    uint32_t* key = s_key[warp];
+    uint32_t* val = s_val[warp];
+    for (uint32_t j = lane; j < kLeaderSlots; j += 32) key[j] = 0;
+    __syncwarp();
+    for (uint32_t t0 = 0; t0 < nc_s; t0 += 32) {
+      const uint32_t c = t0 + lane;
+      const bool in = c < nc_s;
+      uint32_t tax = 0, l = b_s + c;
+      bool fresh = in;
+      if (in) {
+        tax = ldg(&bv.tax[cand[b_s + c].bin]);
+        const uint32_t k2 = tax + 1u;
+        if (k2 != 0) {
+          uint32_t h = (tax * 2654435761u) >> 22;
+          for (;;) {
+            const uint32_t v = key[h];
+            if (v == k2) {
+              l = val[h];
+              fresh = false;
+              break;
+            }
+            if (v == 0) break;
+            h = (h + 1) & (kLeaderSlots - 1);
+          }
+        }
+      }
+      const unsigned fm = __ballot_sync(0xffffffffu, fresh);
+      const unsigned peers = __match_any_sync(0xffffffffu, fresh ? tax : ~lane) & fm;
+      if (fresh) {
+        const unsigned first = (unsigned)(__ffs(peers) - 1);
+        if (first != lane) {
+          l = b_s + t0 + first;  // an earlier candidate of this step carries the TaxID
+        } else if (tax + 1u != 0) {
+          uint32_t h = (tax * 2654435761u) >> 22;
+          while (atomicCAS(&key[h], 0u, tax + 1u) != 0u) h = (h + 1) & (kLeaderSlots - 1);
+          val[h] = l;
+        }
+      }
+      if (in) lead[b_s + c] = l;
+      __syncwarp();
+    }
+  }
+}
+
+// round 1: positions of `order` whose candidate is a leader; round 2: members whose leader did not pass
+__global__ void cand_round_flags_kernel(const uint32_t* __restrict__ order, const uint32_t* __restrict__ lead,
+                                        const uint32_t* __restrict__ edit, uint32_t n, int round,
+                                        uint32_t* __restrict__ flag) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t c = order[i], l = lead[c];
+  flag[i] = round == 1 ? (l == c ? 1u : 0u) : ((l != c && edit[l] == kNoEdit) ? 1u : 0u);
+}
+
+__global__ void cand_compact_order_kernel(const uint32_t* __restrict__ order, const uint32_t* __restrict__ idx, uint32_t n,
+                                          const CandRec* __restrict__ cand, uint32_t* __restrict__ out,
+                                          BatchCounters* __restrict__ ctr) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t wbytes = 0;
+  if (i < n && idx[i + 1] != idx[i]) {
+    const uint32_t c = order[i];
+    out[idx[i]] = c;
+    wbytes = cand[c].end - cand[c].start;
+  }
+  if (ctr) cta_accumulate(ctr->window_bytes, wbytes);  // profiling: reference columns of the candidates verified
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1663,8 +1781,8 @@ static int run_sub_batch(mtsvgpu_index* h, Lane& ln, const Params& p, const uint
     clk.end();
     MTSV_TRY(fetch_counters(ln, d_ctr, &hc, st));
     n_cand = (uint32_t)hc.total_cands;
-    ln.stats.n_candidates += n_cand;
   }
+  bool grouped = false;
   if (n_cand) {
     MTSV_TRY(ws.cand_dense.reserve((size_t)n_cand * sizeof(CandRec)));
     MTSV_TRY(ws.cand_q.reserve((size_t)n_cand * 4));
@@ -1680,16 +1798,40 @@ static int run_sub_batch(mtsvgpu_index* h, Lane& ln, const Params& p, const uint
     clk.begin(ST_VERIFY);
     MTSV_TRY(ws.cand_flag.reserve(((size_t)n_cand + 1) * 4));
     MTSV_TRY(ws.cand_order.reserve((size_t)n_cand * 4));
+    const bool need_ssw = hc.max_len >= 254;  // reads the SW pre-filter is not implied for
+    // several candidates per strand on average: verify TaxID group leaders first (see cand_leader_kernel)
+    {
+      const char* ge = getenv("MTSV_B200_GROUP_VERIFY");
+      grouped = !need_ssw && !legacy_verifier() && (ge ? ge[0] != '0' : n_cand > nq);
+    }
     MTSV_LAUNCH(cand_class_kernel, (n_cand + 255) / 256, 256, 0, st, ws.cand_dense.as<CandRec>(), n_cand,
-                ws.cand_flag.as<uint32_t>(), h->profiling ? d_ctr : nullptr);
+                ws.cand_flag.as<uint32_t>(), (h->profiling && !grouped) ? d_ctr : nullptr);
     MTSV_TRY(exclusive_scan_u32(ws.cand_flag.as<uint32_t>(), ws.cand_flag.as<uint32_t>(), n_cand, ws.scan_tmp,
                                 nullptr, st));
     MTSV_LAUNCH(cand_order_kernel, (n_cand + 255) / 256, 256, 0, st, ws.cand_dense.as<CandRec>(),
                 ws.cand_flag.as<uint32_t>(), n_cand, ws.cand_order.as<uint32_t>());
     BinnerJobs jobs{rv, ev, p, ws.cand_dense.as<CandRec>(), ws.cand_q.as<uint32_t>(),
-                    ws.cand_off.as<uint32_t>(), ws.cand_order.as<uint32_t>(), ix.text, n_cand};
-    const bool need_ssw = hc.max_len >= 254;  // reads the SW pre-filter is not implied for
-    if (!need_ssw && !legacy_verifier()) {
+                    ws.cand_off.as<uint32_t>(), ws.cand_order.as<uint32_t>(), ix.text, n_cand, nullptr};
+    if (grouped) {
+      MTSV_TRY(ws.cand_lead.reserve((size_t)n_cand * 4));
+      MTSV_TRY(ws.cand_order2.reserve((size_t)n_cand * 4));
+      MTSV_CUDA_TRY(cudaMemsetAsync(ws.cand_edit.p, 0xff, (size_t)n_cand * 4, st));  // kNoEdit until verified
+      MTSV_LAUNCH(cand_leader_kernel, (nq + 127) / 128, 128, 0, st, ix.bins_view(), nq, ws.cand_off.as<uint32_t>(),
+                  ws.cand_dense.as<CandRec>(), ws.cand_lead.as<uint32_t>());
+      for (int round = 1; round <= 2; ++round) {
+        uint32_t* flag = ws.cand_flag.as<uint32_t>();
+        MTSV_LAUNCH(cand_round_flags_kernel, (n_cand + 255) / 256, 256, 0, st, ws.cand_order.as<uint32_t>(),
+                    ws.cand_lead.as<uint32_t>(), ws.cand_edit.as<uint32_t>(), n_cand, round, flag);
+        MTSV_TRY(exclusive_scan_u32(flag, flag, n_cand, ws.scan_tmp, (uint64_t*)&d_ctr->verified[round - 1], st));
+        MTSV_LAUNCH(cand_compact_order_kernel, (n_cand + 255) / 256, 256, 0, st, ws.cand_order.as<uint32_t>(), flag,
+                    n_cand, ws.cand_dense.as<CandRec>(), ws.cand_order2.as<uint32_t>(), h->profiling ? d_ctr : nullptr);
+        BinnerJobs round_jobs = jobs;
+        round_jobs.order = ws.cand_order2.as<uint32_t>();
+        round_jobs.n_dev = flag + n_cand;  // the scan's total: how many positions the compacted list holds
+        MTSV_TRY(launch_verify_warp(round_jobs, ix, std::max(hc.max_len, 1u), min_len == hc.max_len,
+                                    ws.cand_edit.as<uint32_t>(), st));
+      }
+    } else if (!need_ssw && !legacy_verifier()) {
       MTSV_TRY(launch_verify_warp(jobs, ix, std::max(hc.max_len, 1u), min_len == hc.max_len,
                                   ws.cand_edit.as<uint32_t>(), st));
     } else {
@@ -1725,6 +1867,7 @@ static int run_sub_batch(mtsvgpu_index* h, Lane& ln, const Params& p, const uint
     clk.end();
     MTSV_TRY(fetch_counters(ln, d_ctr, &hc, st));
     sub_out = hc.total_out;
+    ln.stats.n_candidates += grouped ? hc.verified[0] + hc.verified[1] : n_cand;
     for (int i = 0; i < 32; ++i) ln.stats.window_bytes += hc.window_bytes[i];
   } else {
     MTSV_CUDA_TRY(cudaMemsetAsync(ws.out_off.p, 0, qn * 4, st));

@@ -59,6 +59,7 @@ struct BatchCounters {  // device-side scalars of one sub-batch
   unsigned int max_len, overflow, n_warp, n_medium, n_large, bad_offsets, n_heavy, heavy_cursor, n_monster;
   unsigned int inv_min_len;  // ~(shortest read) so that a zeroed struct means "no read seen"
   unsigned int n_ssw_full, n_over_len;  // candidates of reads >= 254 bases that needed the full SW matrices; reads over the length limit
+  unsigned long long verified[2];  // two-round verification: candidates verified in round 1 / round 2
   unsigned long long rank_steps[32], window_bytes[32];  // profiling only; spread to avoid one hot address
 };
 
@@ -133,6 +134,7 @@ struct BatchWorkspace {
   DevBuf hit_keys, cand_sparse, cand_stage;
   // per candidate (dense)
   DevBuf cand_dense, cand_q, cand_edit, hit_tmp, cand_flag, cand_order, cand_end, ssw_list, ssw_scratch;
+  DevBuf cand_lead, cand_order2;  // two-round verification: leader of each candidate, compacted visiting order
   // bit-plane encoded reads of the sub-batch
   DevBuf enc;
   // scan scratch, counters, worklists

@@ -201,6 +201,34 @@ def test_pipeline_many_strains_sharing_taxids(oracle):
             assert int((o1[1:] - o1[:-1]).max()) >= min(100, n_strains // per_tax)
 
 
+def test_two_round_verification_is_result_preserving(oracle, small_ref, small_index, monkeypatch):
+    """Verifying the leaders of the (strand, TaxID) groups first and the other members only when their leader
+    failed (binner.cu, cand_leader_kernel) must give the results of verifying everything: forced on and forced off,
+    on strands with one, a few and hundreds of candidates."""
+    cat, off, gi, tax = small_ref
+    reads_small = synth.make_reads(cat, off, 3000, 150, seed=41)
+    taxids = 500 + (np.arange(150, dtype=np.uint32) // np.uint32(6))
+    ref = synth.make_reference(150, 2000, seed=26, n_frac=0.0, shared_frac=0.95, divergence=0.01, taxids=taxids)
+    heavy_ix = oracle.Index.build((ref[0], ref[1]), ref[2], ref[3], 64, 32)
+    reads_heavy = synth.make_reads(ref[0], ref[1], 800, 75, seed=27, sub=0.06)  # some leaders fail, members pass
+    for ix, reads, flags in ((small_index, reads_small, {}), (small_index, reads_small, dict(seed_gap=3, edit_rate=0.2)),
+                             (heavy_ix, reads_heavy, {}), (heavy_ix, reads_heavy, dict(edit_rate=0.08)),
+                             (heavy_ix, reads_heavy, dict(max_candidates=60, max_assignments=4))):
+        po, pg = _params(oracle, **flags)
+        h1, o1 = ix.bin_reads(reads, po, threads=8)
+        with _gpu_index(ix) as g:
+            verified = {}
+            for mode in ("1", "0"):
+                monkeypatch.setenv("MTSV_B200_GROUP_VERIFY", mode)
+                h2, o2 = g.bin_reads(reads, pg)
+                _same(h1, o1, h2, o2)
+                verified[mode] = g.last_batch_stats()["n_candidates"]
+            assert verified["1"] <= verified["0"]
+            if ix is heavy_ix and not flags:
+                assert verified["1"] < 0.5 * verified["0"]  # six strains per TaxID: most members are never aligned
+    monkeypatch.delenv("MTSV_B200_GROUP_VERIFY")
+
+
 def test_pipeline_long_reads_high_edit(oracle, small_ref, small_index):
     """BASELINE config 5 in miniature: 250 bp, edit-rate 0.2, --seed-interval 3."""
     reads = synth.make_reads(small_ref[0], small_ref[1], 1000, 250, seed=8, sub=0.10)
