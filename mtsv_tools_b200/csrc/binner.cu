@@ -876,13 +876,8 @@ struct BinnerJobs {
   const uint32_t* cand_off;
   const uint32_t* order;
   const uint8_t* text;
-  uint32_t n;             // upper bound on the jobs (sizes the grid)
-  const uint32_t* n_dev;  // when set: the actual number of jobs, known only on the device (compacted lists)
-  __device__ __forceinline__ uint32_t count() const {
-    if (!n_dev) return n;
-    const uint32_t m = __ldg(n_dev);
-    return m < n ? m : n;
-  }
+  uint32_t n;
+  __device__ __forceinline__ uint32_t count() const { return n; }
   __device__ __forceinline__ VerifyJob get(uint32_t i) const {
     VerifyJob j;
     uint32_t ci = order[i];
@@ -1037,7 +1032,6 @@ __global__ void __launch_bounds__(kVerifyThreads) verify_warp_kernel(BinnerJobs 
   job.enc = nullptr;
   uint32_t start = 0;
   const uint32_t n_jobs = jobs.count();
-  if (blockIdx.x * blockDim.x >= n_jobs) return;  // (grids are sized by the upper bound)
   if (i < n_jobs) {
     job = jobs.get(i);
     start = (uint32_t)(job.txt - jobs.text);
@@ -1360,12 +1354,12 @@ __global__ void __launch_bounds__(256) gather_hits_kernel(uint32_t nq, uint32_t 
 
 // verification order: multi-seed candidates first, single-seed ones after (stable within each class)
 __global__ void cand_class_kernel(const CandRec* __restrict__ cand, uint32_t n, uint32_t* __restrict__ flag,
-                                  BatchCounters* __restrict__ ctr) {
+                                  BatchCounters* __restrict__ ctr, int write_flags) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   uint32_t wbytes = 0;
   if (i < n) {
     CandRec c = cand[i];
-    flag[i] = c.num_seeds > 1 ? 1u : 0u;
+    if (write_flags) flag[i] = c.num_seeds > 1 ? 1u : 0u;
     wbytes = c.end - c.start;
   }
   if (ctr) cta_accumulate(ctr->window_bytes, wbytes);  // profiling: reference bytes the verifier reads
@@ -1805,32 +1799,60 @@ static int run_sub_batch(mtsvgpu_index* h, Lane& ln, const Params& p, const uint
       grouped = !need_ssw && !legacy_verifier() && (ge ? ge[0] != '0' : n_cand > nq);
     }
     MTSV_LAUNCH(cand_class_kernel, (n_cand + 255) / 256, 256, 0, st, ws.cand_dense.as<CandRec>(), n_cand,
-                ws.cand_flag.as<uint32_t>(), (h->profiling && !grouped) ? d_ctr : nullptr);
+                ws.cand_flag.as<uint32_t>(), (h->profiling && !grouped) ? d_ctr : nullptr, 1);
     MTSV_TRY(exclusive_scan_u32(ws.cand_flag.as<uint32_t>(), ws.cand_flag.as<uint32_t>(), n_cand, ws.scan_tmp,
                                 nullptr, st));
     MTSV_LAUNCH(cand_order_kernel, (n_cand + 255) / 256, 256, 0, st, ws.cand_dense.as<CandRec>(),
                 ws.cand_flag.as<uint32_t>(), n_cand, ws.cand_order.as<uint32_t>());
     BinnerJobs jobs{rv, ev, p, ws.cand_dense.as<CandRec>(), ws.cand_q.as<uint32_t>(),
-                    ws.cand_off.as<uint32_t>(), ws.cand_order.as<uint32_t>(), ix.text, n_cand, nullptr};
+                    ws.cand_off.as<uint32_t>(), ws.cand_order.as<uint32_t>(), ix.text, n_cand};
+    uint64_t n_verified = n_cand;
     if (grouped) {
+      // round 1: the leaders.  The list lengths come back to the host (two short synchronisations per sub-batch,
+      // only on this path): an all-leaders sub-batch falls through to the plain launch, and the launches are sized
+      // exactly — a grid sized for every candidate costs more in empty blocks than the round saves.
       MTSV_TRY(ws.cand_lead.reserve((size_t)n_cand * 4));
       MTSV_TRY(ws.cand_order2.reserve((size_t)n_cand * 4));
-      MTSV_CUDA_TRY(cudaMemsetAsync(ws.cand_edit.p, 0xff, (size_t)n_cand * 4, st));  // kNoEdit until verified
+      uint32_t* flag = ws.cand_flag.as<uint32_t>();
       MTSV_LAUNCH(cand_leader_kernel, (nq + 127) / 128, 128, 0, st, ix.bins_view(), nq, ws.cand_off.as<uint32_t>(),
                   ws.cand_dense.as<CandRec>(), ws.cand_lead.as<uint32_t>());
-      for (int round = 1; round <= 2; ++round) {
-        uint32_t* flag = ws.cand_flag.as<uint32_t>();
-        MTSV_LAUNCH(cand_round_flags_kernel, (n_cand + 255) / 256, 256, 0, st, ws.cand_order.as<uint32_t>(),
-                    ws.cand_lead.as<uint32_t>(), ws.cand_edit.as<uint32_t>(), n_cand, round, flag);
-        MTSV_TRY(exclusive_scan_u32(flag, flag, n_cand, ws.scan_tmp, (uint64_t*)&d_ctr->verified[round - 1], st));
-        MTSV_LAUNCH(cand_compact_order_kernel, (n_cand + 255) / 256, 256, 0, st, ws.cand_order.as<uint32_t>(), flag,
-                    n_cand, ws.cand_dense.as<CandRec>(), ws.cand_order2.as<uint32_t>(), h->profiling ? d_ctr : nullptr);
+      MTSV_LAUNCH(cand_round_flags_kernel, (n_cand + 255) / 256, 256, 0, st, ws.cand_order.as<uint32_t>(),
+                  ws.cand_lead.as<uint32_t>(), ws.cand_edit.as<uint32_t>(), n_cand, 1, flag);
+      MTSV_TRY(exclusive_scan_u32(flag, flag, n_cand, ws.scan_tmp, (uint64_t*)&d_ctr->verified[0], st));
+      MTSV_TRY(fetch_counters(ln, d_ctr, &hc, st));
+      const uint32_t n1 = (uint32_t)hc.verified[0];
+      if (n1 == n_cand) {
+        grouped = false;  // one candidate per (strand, TaxID) everywhere: nothing to hold back
+        if (h->profiling)
+          MTSV_LAUNCH(cand_class_kernel, (n_cand + 255) / 256, 256, 0, st, ws.cand_dense.as<CandRec>(), n_cand,
+                      (uint32_t*)nullptr, d_ctr, 0);
+      } else {
+        MTSV_CUDA_TRY(cudaMemsetAsync(ws.cand_edit.p, 0xff, (size_t)n_cand * 4, st));  // kNoEdit until verified
         BinnerJobs round_jobs = jobs;
         round_jobs.order = ws.cand_order2.as<uint32_t>();
-        round_jobs.n_dev = flag + n_cand;  // the scan's total: how many positions the compacted list holds
+        MTSV_LAUNCH(cand_compact_order_kernel, (n_cand + 255) / 256, 256, 0, st, ws.cand_order.as<uint32_t>(), flag,
+                    n_cand, ws.cand_dense.as<CandRec>(), ws.cand_order2.as<uint32_t>(), h->profiling ? d_ctr : nullptr);
+        round_jobs.n = n1;
         MTSV_TRY(launch_verify_warp(round_jobs, ix, std::max(hc.max_len, 1u), min_len == hc.max_len,
                                     ws.cand_edit.as<uint32_t>(), st));
+        // round 2: members whose leader did not pass
+        MTSV_LAUNCH(cand_round_flags_kernel, (n_cand + 255) / 256, 256, 0, st, ws.cand_order.as<uint32_t>(),
+                    ws.cand_lead.as<uint32_t>(), ws.cand_edit.as<uint32_t>(), n_cand, 2, flag);
+        MTSV_TRY(exclusive_scan_u32(flag, flag, n_cand, ws.scan_tmp, (uint64_t*)&d_ctr->verified[1], st));
+        MTSV_TRY(fetch_counters(ln, d_ctr, &hc, st));
+        const uint32_t n2 = (uint32_t)hc.verified[1];
+        if (n2) {
+          MTSV_LAUNCH(cand_compact_order_kernel, (n_cand + 255) / 256, 256, 0, st, ws.cand_order.as<uint32_t>(), flag,
+                      n_cand, ws.cand_dense.as<CandRec>(), ws.cand_order2.as<uint32_t>(), h->profiling ? d_ctr : nullptr);
+          round_jobs.n = n2;
+          MTSV_TRY(launch_verify_warp(round_jobs, ix, std::max(hc.max_len, 1u), min_len == hc.max_len,
+                                      ws.cand_edit.as<uint32_t>(), st));
+        }
+        n_verified = (uint64_t)n1 + n2;
       }
+    }
+    if (grouped) {
+      // (both rounds launched above)
     } else if (!need_ssw && !legacy_verifier()) {
       MTSV_TRY(launch_verify_warp(jobs, ix, std::max(hc.max_len, 1u), min_len == hc.max_len,
                                   ws.cand_edit.as<uint32_t>(), st));
@@ -1867,7 +1889,7 @@ static int run_sub_batch(mtsvgpu_index* h, Lane& ln, const Params& p, const uint
     clk.end();
     MTSV_TRY(fetch_counters(ln, d_ctr, &hc, st));
     sub_out = hc.total_out;
-    ln.stats.n_candidates += grouped ? hc.verified[0] + hc.verified[1] : n_cand;
+    ln.stats.n_candidates += n_verified;
     for (int i = 0; i < 32; ++i) ln.stats.window_bytes += hc.window_bytes[i];
   } else {
     MTSV_CUDA_TRY(cudaMemsetAsync(ws.out_off.p, 0, qn * 4, st));
