@@ -1796,7 +1796,9 @@ static int run_sub_batch(mtsvgpu_index* h, Lane& ln, const Params& p, const uint
     // several candidates per strand on average: verify TaxID group leaders first (see cand_leader_kernel)
     {
       const char* ge = getenv("MTSV_B200_GROUP_VERIFY");
-      grouped = !need_ssw && !legacy_verifier() && (ge ? ge[0] != '0' : n_cand > nq);
+      // (worth trying only where some TaxID has several sequences — otherwise two candidates of one TaxID would have
+      // to be two windows of the same sequence — and the sub-batch has more candidates than strands)
+      grouped = !need_ssw && !legacy_verifier() && (ge ? ge[0] != '0' : (n_cand > nq && ix.n_bins > ix.n_taxids));
     }
     MTSV_LAUNCH(cand_class_kernel, (n_cand + 255) / 256, 256, 0, st, ws.cand_dense.as<CandRec>(), n_cand,
                 ws.cand_flag.as<uint32_t>(), (h->profiling && !grouped) ? d_ctr : nullptr, 1);
@@ -1821,8 +1823,8 @@ static int run_sub_batch(mtsvgpu_index* h, Lane& ln, const Params& p, const uint
       MTSV_TRY(exclusive_scan_u32(flag, flag, n_cand, ws.scan_tmp, (uint64_t*)&d_ctr->verified[0], st));
       MTSV_TRY(fetch_counters(ln, d_ctr, &hc, st));
       const uint32_t n1 = (uint32_t)hc.verified[0];
-      if (n1 == n_cand) {
-        grouped = false;  // one candidate per (strand, TaxID) everywhere: nothing to hold back
+      if ((uint64_t)n1 * 10 > (uint64_t)n_cand * 9 && !(getenv("MTSV_B200_GROUP_VERIFY") && n1 < n_cand)) {
+        grouped = false;  // (nearly) one candidate per (strand, TaxID): holding the few others back does not pay
         if (h->profiling)
           MTSV_LAUNCH(cand_class_kernel, (n_cand + 255) / 256, 256, 0, st, ws.cand_dense.as<CandRec>(), n_cand,
                       (uint32_t*)nullptr, d_ctr, 0);

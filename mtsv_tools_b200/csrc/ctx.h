@@ -91,6 +91,7 @@ struct DeviceIndex {
   uint64_t text4_words = 0;
   uint32_t *bin_start = nullptr, *bin_end = nullptr, *bin_tax = nullptr, *bin_gi = nullptr;
   uint64_t n_bins = 0;
+  uint64_t n_taxids = 0;  // distinct TaxIDs among the bins (== n_bins: no TaxID has a second sequence)
   uint64_t device_bytes = 0;
   double load_seconds = 0, relayout_seconds = 0, build_seconds = 0;
 

@@ -410,6 +410,11 @@ int index_assemble(const IndexParts& parts, int device, const mtsvgpu_index_opts
       bt[i] = bins[i].tax_id;
       bg[i] = bins[i].gi;
     }
+    {
+      std::vector<uint32_t> t = bt;
+      std::sort(t.begin(), t.end());
+      d.n_taxids = (uint64_t)(std::unique(t.begin(), t.end()) - t.begin());
+    }
     MTSV_TRY(dev_alloc(&d.bin_start, n_bins, &d.device_bytes));
     MTSV_TRY(dev_alloc(&d.bin_end, n_bins, &d.device_bytes));
     MTSV_TRY(dev_alloc(&d.bin_tax, n_bins, &d.device_bytes));
