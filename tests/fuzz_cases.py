@@ -107,3 +107,35 @@ def long_case(rng):
                           tune_max_hits=rng.choice([2, 200]), max_candidates=rng.choice([-1, -1, 2]),
                           max_assignments=rng.choice([-1, -1, 1]))
     return ix, reads, p
+
+
+def heavy_case(rng):
+    """Many near-identical strains under few TaxIDs: strands with dozens to hundreds of candidates — the warp-level
+    selection with its hash set, the (strand, TaxID) group leaders of the two-round verification, both limits."""
+    n_strains = rng.choice([20, 40, 80, 160, 300, 600])
+    base_len = rng.randint(200, 900)
+    base = bytes(rng.choice(b"ACGT") for _ in range(base_len))
+    per_tax = rng.choice([1, 2, 5, 13])
+    seqs, tax = [], []
+    for i in range(n_strains):
+        seqs.append(mutate(rng, base, rng.randint(0, max(1, base_len // 60))))
+        tax.append(100 + (i // per_tax if rng.random() < 0.9 else rng.randint(0, n_strains)))
+    order = list(range(n_strains))
+    rng.shuffle(order)  # strains of one TaxID are not neighbours (the builder re-orders bins by TaxID anyway)
+    seqs = [seqs[i] for i in order]
+    tax = [tax[i] for i in order]
+    ix = po.Index.build(seqs, list(range(1000, 1000 + n_strains)), tax, 64, rng.choice([4, 32]))
+    L0 = rng.choice([40, 64, 75, 100, 150])
+    rate = rng.choice([0.05, 0.13, 0.2])
+    reads = []
+    for _ in range(rng.randint(1, 12)):
+        st = rng.randrange(0, max(1, base_len - L0))
+        s = mutate(rng, base[st:st + L0 + 6], int(rng.random() * 1.5 * rate * L0))[:L0]
+        if rng.random() < 0.5:
+            s = bytes({65: 84, 67: 71, 71: 67, 84: 65}.get(c, c) for c in reversed(s))
+        reads.append(s)
+    p = po.default_params(edit_rate=rate, seed_size=rng.choice([12, 18]), seed_gap=rng.choice([5, 15]),
+                          min_seed=rng.choice([0.015, 0.5]), max_hits=rng.choice([50, 2000, 100000]),
+                          tune_max_hits=rng.choice([10, 200, 100000]), max_candidates=rng.choice([-1, -1, 0, 7, 40, 500]),
+                          max_assignments=rng.choice([-1, -1, 0, 1, 9, 64]))
+    return ix, reads, p
