@@ -263,7 +263,8 @@ MTSVGPU_API void mtsvgpu_comm_destroy(mtsvgpu_comm* comm);
  * chunk's index.  On return this rank holds, for the reads [*first_read, *first_read + *n_local_reads) (the rank-th
  * of `world` contiguous ranges), what mtsv-collapse leaves of the per-chunk results (src/collapse.rs:597-602,
  * :278-279): each TaxID once with its minimum edit, by ascending TaxID, CSR by read.  The device pointers are owned
- * by the communicator and stay valid until its next batch. */
+ * by the communicator and stay valid until its next batch.  Every rank of the communicator must make the call: a
+ * rank that fails before the exchange (or never calls) makes its peers give up after 30 s with MTSVGPU_ECUDA. */
 MTSVGPU_API int mtsvgpu_bin_batch_chunked(mtsvgpu_index* ix, mtsvgpu_comm* comm, const uint8_t* d_seqs,
                               const uint64_t* d_seq_off, uint64_t n_reads, const mtsvgpu_params* params,
                               uint64_t* first_read, uint64_t* n_local_reads, const mtsvgpu_taxhit** d_out,

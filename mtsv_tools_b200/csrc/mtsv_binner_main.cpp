@@ -677,6 +677,11 @@ int main(int argc, char** argv) {
   auto t0 = std::chrono::steady_clock::now();
 
   Shared sh;
+  // a failure anywhere in the pipeline is raised through `sh`, not through every stage's condition variable: waits
+  // re-check it at short intervals
+  auto wait_on = [](std::condition_variable& cv, std::unique_lock<std::mutex>& lk, auto pred) {
+    while (!pred()) cv.wait_for(lk, std::chrono::milliseconds(50));
+  };
   Pool pool(n_threads);
   // ---- reader -> parsed blocks (ordered by block sequence number) ----
   std::mutex pmu;
@@ -739,7 +744,7 @@ int main(int argc, char** argv) {
       uint64_t seq;
       {
         std::unique_lock<std::mutex> lk(pmu);
-        pcv.wait(lk, [&] { return blocks_issued - blocks_taken < max_blocks_in_flight || sh.failed(); });
+        wait_on(pcv, lk, [&] { return blocks_issued - blocks_taken < max_blocks_in_flight || sh.failed(); });
         seq = blocks_issued++;
       }
       tb->seq = seq;
@@ -783,7 +788,7 @@ int main(int argc, char** argv) {
     auto b = std::make_shared<Batch>();
     std::unique_lock<std::mutex> lk(pmu);
     for (;;) {
-      pcv.wait(lk, [&] { return parsed.count(blocks_taken) || (reader_done && blocks_taken == blocks_issued) || sh.failed(); });
+      wait_on(pcv, lk, [&] { return parsed.count(blocks_taken) || (reader_done && blocks_taken == blocks_issued) || sh.failed(); });
       if (sh.failed()) return nullptr;
       if (!parsed.count(blocks_taken)) break;  // input exhausted
       auto it = parsed.find(blocks_taken);
@@ -906,7 +911,7 @@ int main(int argc, char** argv) {
       std::shared_ptr<Batch> b;
       {
         std::unique_lock<std::mutex> lk(wmu);
-        wcv.wait(lk, [&] { return done.count(next) || next == batches_total || sh.failed(); });
+        wait_on(wcv, lk, [&] { return done.count(next) || next == batches_total || sh.failed(); });
         if (!done.count(next)) return;
         b = done[next];
         done.erase(next);
