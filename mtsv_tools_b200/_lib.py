@@ -4,7 +4,8 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmtsv_b200.so")
+# (MTSV_B200_LIB: an alternative build of the same library, for A/B measurements of compile-time knobs)
+LIB_PATH = os.environ.get("MTSV_B200_LIB") or os.path.join(_HERE, "libmtsv_b200.so")
 _LIB = None
 
 E_NAMES = {0: "OK", -1: "EINVAL", -2: "EIO", -3: "EFORMAT", -4: "ENODEVICE", -5: "ECUDA", -6: "ENOMEM",

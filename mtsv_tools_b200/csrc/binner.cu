@@ -19,6 +19,15 @@
 
 #include "ctx.h"
 
+#ifndef MTSV_COALESCE_UNROLL
+#define MTSV_COALESCE_UNROLL 4
+#endif
+#ifndef MTSV_COALESCE_TILES
+#define MTSV_COALESCE_TILES 4
+#endif
+constexpr int kCoalesceTiles = MTSV_COALESCE_TILES;    // tiles of 32 hits fetched together by coalesce_warp
+constexpr int kCoalesceUnroll = MTSV_COALESCE_UNROLL;  // replay loop of coalesce_warp (code size vs shuffle look-ahead)
+
 namespace mtsv {
 
 // ------------------------------------------------------------------------------------------
@@ -501,7 +510,7 @@ __device__ uint32_t coalesce_warp(const BinsView& bv, const uint64_t* __restrict
   // The automaton itself is cheap; what a long strand waits for is memory (keys, bins).  Four tiles of
   // 32 hits are therefore fetched together — the four key loads and the four branch-free binary searches
   // over the bin ends proceed in lock step, i.e. with four loads in flight — and then replayed in order.
-  constexpr int U = 4;
+  constexpr int U = kCoalesceTiles;
   uint32_t top = 1;
   while (top < bv.n) top <<= 1;
   for (uint32_t g0 = 0; g0 < n_hits; g0 += 32 * U) {
@@ -576,10 +585,11 @@ __device__ uint32_t coalesce_warp(const BinsView& bv, const uint64_t* __restrict
         cur = CandRec{__shfl_sync(0xffffffffu, ws[u], cnt - 1), __shfl_sync(0xffffffffu, we[u], cnt - 1), last_b, 1};
         continue;
       }
-      // (fully unrolled so that the shuffles, which do not depend on the automaton's state, are issued
-      //  ahead of the short dependent chain through cur / have)
+      // (unrolled by 8 so that the shuffles, which do not depend on the automaton's state, are issued ahead of
+      //  the short dependent chain through cur / have; the full 32-way unroll of round 1 made four copies of a
+      //  2 700-instruction body — ncu: warps stalled on instruction fetch, `no_instruction` 10.8 per issue)
       const uint32_t sb = (b[u] << 1) | (some[u] ? 1u : 0u);
-#pragma unroll
+#pragma unroll(kCoalesceUnroll)
       for (uint32_t i = 0; i < 32; ++i) {
         uint32_t ws_i = __shfl_sync(0xffffffffu, ws[u], i), we_i = __shfl_sync(0xffffffffu, we[u], i);
         uint32_t sb_i = __shfl_sync(0xffffffffu, sb, i);
