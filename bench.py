@@ -163,7 +163,7 @@ class ClockSampler:
         self.p = None
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q,
-                                       "--format=csv,noheader,nounits", "-lms", "200"], stdout=self.f,
+                                       "--format=csv,noheader,nounits", "-lms", "50"], stdout=self.f,
                                       stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
@@ -686,12 +686,14 @@ def measure(args, name, cfg, ctx, steps, warmup, ragged=False, n_reads=None, cpu
     w = Workload(args, name, cfg, ctx, ragged=ragged, n_reads=n_reads)
     parity = parity_gate(args, w) if (ctx.rank == 0 and not args.no_parity) else None
     ctx.barrier()
+    # clocks and throttle reasons are sampled from before the warm-up steps of the device-resident leg to the end of
+    # the end-to-end leg (both timed regions and the identical load around them; the legs themselves last ~0.1-0.2 s)
     clocks = ClockSampler(ctx.local_rank) if full else None
     ms, stats, per_step, launches = time_device(w, steps, max(3, warmup), profile=not args.no_profile)
-    clk = clocks.stop() if clocks else None
     if args.no_profile:
         _, stats, per_step, _ = time_device(w, 1, 0, profile=True)
     e2e_ms, h2d, d2h = time_e2e(w, steps)
+    clk = clocks.stop() if clocks else None
     pk = time_e2e_packed(w, steps) if full else None
     ms, e2e_ms = ctx.max_over_ranks([ms, e2e_ms])
     total = w.n_reads * ctx.world * steps
@@ -1056,14 +1058,14 @@ def run_chunk_arm(args, ctx, as_dict=False):
         ctx.barrier()
         return e0.elapsed_time(e1), r
 
+    clocks = ClockSampler(ctx.local_rank)  # (from the warm-up steps on: the timed legs are ~0.1 s each)
     for _ in range(max(3, args.warmup)):
         step()
     launches0 = lib.mtsvgpu_launch_count()
-    clocks = ClockSampler(ctx.local_rank)
     ms, last = timed(step, args.steps)
-    clk = clocks.stop()
     launches = lib.mtsvgpu_launch_count() - launches0
     ms_local, _ = timed(step_local, args.steps)
+    clk = clocks.stop()
     n_pairs = float(last[4])
     ms, ms_local = ctx.max_over_ranks([ms, ms_local])
     if world > 1:
