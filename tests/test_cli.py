@@ -243,3 +243,32 @@ def test_mtsv_build_writes_the_oracles_index_and_feeds_the_binner(oracle, tmp_pa
     assert r.returncode == 0, r.stderr
     hits, offs = ix.bin_reads((rc, ro), oracle.default_params(), threads=4)
     assert res.read_text() == "".join(oracle.results_lines(names, hits, offs, False))
+
+
+@pytest.mark.gpu
+def test_cli_two_gpus_give_the_same_file(oracle, tmp_path):
+    """--gpus 2: batches go to the devices round-robin, the ordered writer makes the results file identical to the
+    one-GPU run (and to the oracle's lines)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from mtsv_tools_b200 import synth
+    cat, off, gi, tax = synth.make_reference(8, 20000, seed=1, n_frac=0.002, shared_frac=0.1, seqs_per_taxid=2)
+    ix = oracle.Index.build((cat, off), gi, tax, 64, 32)
+    index_path = str(tmp_path / "ref.index")
+    ix.write(index_path)
+    rc, ro = synth.make_reads(cat, off, 20000, 150, seed=2)
+    names = ["read_%d" % i for i in range(20000)]
+    fq = tmp_path / "reads.fq"
+    with open(fq, "w") as f:
+        for i, n in enumerate(names):
+            s = bytes(rc[int(ro[i]):int(ro[i + 1])]).decode()
+            f.write("@%s\n%s\n+\n%s\n" % (n, s, "I" * len(s)))
+    hits, offs = ix.bin_reads((rc, ro), oracle.default_params(), threads=4)
+    want = "".join(oracle.results_lines(names, hits, offs, False))
+    for gpus in ("1", "2"):
+        res = tmp_path / ("res_%s.txt" % gpus)
+        r = _run("--fastq", str(fq), "--index", index_path, "--results", str(res), "--gpus", gpus,
+                 "--batch-reads", "1500", "--threads", "6")
+        assert r.returncode == 0, r.stderr
+        assert res.read_text() == want, gpus
