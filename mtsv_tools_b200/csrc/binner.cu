@@ -2003,26 +2003,36 @@ int bin_batch_device(mtsvgpu_index* h, const uint8_t* d_seqs, const uint64_t* d_
   }
   // sub-batch boundaries of seq_off: one strided gather instead of copying 8 B per read
   // the host API (sub_batch_hook set) uploads slice by slice: short first slices fill the pipeline
-  const std::vector<uint64_t> rb = sub_batch_bounds(n_reads, step, host_path);
+  // ---- lanes: the slices of a batch alternate between two lanes (own stream, scratch and host thread each): the
+  // synchronisation bubbles and kernel tails of one slice are filled by the other — ~10 % on the small slices of
+  // the host API, 4 % on the large ones of device-resident input.  One lane when per-stage timing is on, so that
+  // the event timers measure kernels that run alone.  MTSV_B200_LANES=1|2 overrides. ----
+  const char* lanes_env = getenv("MTSV_B200_LANES");
+  int want_lanes = (host_path || !h->profiling) ? 2 : 1;
+  if (lanes_env && (atoi(lanes_env) == 1 || atoi(lanes_env) == 2)) want_lanes = atoi(lanes_env);
+  std::vector<uint64_t> rb;
+  uint64_t stride = step;  // device-resident input: slices of equal size
+  if (host_path) {
+    rb = sub_batch_bounds(n_reads, step, true);
+  } else {
+    uint64_t k = (n_reads + step - 1) / step;
+    if (want_lanes == 2 && k >= 2 && (k & 1)) ++k;  // an even number of slices: both lanes get the same share
+    stride = k ? (n_reads + k - 1) / k : step;
+    rb.push_back(0);
+    for (uint64_t i = 1; i <= k; ++i) rb.push_back(std::min(n_reads, i * stride));
+  }
   const uint64_t n_sub = rb.size() - 1;
   std::vector<uint64_t> bounds(n_sub + 1, 0);
   if (n_reads) {
     if (h_seq_off_or_null) {
       for (uint64_t i = 0; i <= n_sub; ++i) bounds[i] = h_seq_off_or_null[rb[i]];
     } else {
-      // (no ramp without the host API: boundaries are multiples of step)
-      MTSV_CUDA_TRY(cudaMemcpy2DAsync(bounds.data(), 8, d_seq_off, step * 8, 8, n_sub, cudaMemcpyDeviceToHost, st));
+      // (boundaries are multiples of the stride: one strided gather)
+      MTSV_CUDA_TRY(cudaMemcpy2DAsync(bounds.data(), 8, d_seq_off, stride * 8, 8, n_sub, cudaMemcpyDeviceToHost, st));
       MTSV_CUDA_TRY(cudaMemcpyAsync(&bounds[n_sub], d_seq_off + n_reads, 8, cudaMemcpyDeviceToHost, st));
       MTSV_CUDA_TRY(cudaStreamSynchronize(st));
     }
   }
-  // ---- lanes: with host input the slices alternate between two lanes (the sync bubbles and kernel tails of
-  // one slice are filled by the other: ~10 % on small slices, which is what keeps the compute ahead of the
-  // upload); device-resident input uses large slices on one lane, so that the per-stage event timers of the
-  // profiling mode measure kernels that run alone.  MTSV_B200_LANES=1|2 overrides. ----
-  const char* lanes_env = getenv("MTSV_B200_LANES");
-  int want_lanes = host_path ? 2 : 1;
-  if (lanes_env && (atoi(lanes_env) == 1 || atoi(lanes_env) == 2)) want_lanes = atoi(lanes_env);
   const int n_lanes = n_sub >= 2 ? want_lanes : 1;
   h->lanes[0].stream = st;
   h->lanes[0].ws = &h->ws;
