@@ -455,9 +455,9 @@ def time_device(w, steps, warmup, n=None, profile=True):
     def step():
         return w.gix.bin_reads_device(w.d_reads.data_ptr(), w.d_off.data_ptr(), n, w.params)
 
+    w.gix.set_profiling(profile)  # (before the warm-up: the profiled mode runs other slice sizes on one lane)
     for _ in range(warmup):
         step()
-    w.gix.set_profiling(profile)
     launches0 = lib.mtsvgpu_launch_count()
     torch.cuda.synchronize()
     w.ctx.barrier()
@@ -693,7 +693,7 @@ def measure(args, name, cfg, ctx, steps, warmup, ragged=False, n_reads=None, cpu
     # A second, identical leg with the per-stage CUDA-event timers on (one lane, so that kernels are timed alone)
     # gives the stage times and the roofline's kernel durations; its own step time is reported beside them.
     ms, _, _, launches = time_device(w, steps, max(3, warmup), profile=False)
-    ms_prof, stats, per_step, _ = time_device(w, 1 if args.no_profile else steps, 1, profile=True)
+    ms_prof, stats, per_step, _ = time_device(w, 1 if args.no_profile else steps, 2, profile=True)
     prof_steps = 1 if args.no_profile else steps
     e2e_ms, h2d, d2h = time_e2e(w, steps)
     clk = clocks.stop() if clocks else None
