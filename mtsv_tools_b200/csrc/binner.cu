@@ -2016,7 +2016,10 @@ int bin_batch_device(mtsvgpu_index* h, const uint8_t* d_seqs, const uint64_t* d_
     rb = sub_batch_bounds(n_reads, step, true);
   } else {
     uint64_t k = (n_reads + step - 1) / step;
-    if (want_lanes == 2 && k >= 2 && (k & 1)) ++k;  // an even number of slices: both lanes get the same share
+    // an even number of slices, so that both lanes get the same share; a batch that fits one slice is still cut in
+    // two when it is large enough for the halves to keep the device busy (MTSV_B200_SPLIT_MIN reads, default 2^19)
+    static const uint64_t split_min = getenv("MTSV_B200_SPLIT_MIN") ? strtoull(getenv("MTSV_B200_SPLIT_MIN"), nullptr, 10) : (1ull << 19);
+    if (want_lanes == 2 && ((k >= 2 && (k & 1)) || (k == 1 && n_reads >= split_min))) ++k;
     stride = k ? (n_reads + k - 1) / k : step;
     rb.push_back(0);
     for (uint64_t i = 1; i <= k; ++i) rb.push_back(std::min(n_reads, i * stride));
