@@ -2017,8 +2017,9 @@ int bin_batch_device(mtsvgpu_index* h, const uint8_t* d_seqs, const uint64_t* d_
   } else {
     uint64_t k = (n_reads + step - 1) / step;
     // an even number of slices, so that both lanes get the same share; a batch that fits one slice is still cut in
-    // two when it is large enough for the halves to keep the device busy (MTSV_B200_SPLIT_MIN reads, default 2^19)
-    static const uint64_t split_min = getenv("MTSV_B200_SPLIT_MIN") ? strtoull(getenv("MTSV_B200_SPLIT_MIN"), nullptr, 10) : (1ull << 19);
+    // two when it is large enough (MTSV_B200_SPLIT_MIN reads, default 2^21: +3 % at 2.5 M reads; at 1.25 M reads the
+    // halves gain 3 % on an idle host and lose as much with eight ranks' threads competing for it)
+    static const uint64_t split_min = getenv("MTSV_B200_SPLIT_MIN") ? strtoull(getenv("MTSV_B200_SPLIT_MIN"), nullptr, 10) : (1ull << 21);
     if (want_lanes == 2 && ((k >= 2 && (k & 1)) || (k == 1 && n_reads >= split_min))) ++k;
     stride = k ? (n_reads + k - 1) / k : step;
     rb.push_back(0);
