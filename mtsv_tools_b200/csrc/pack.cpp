@@ -133,7 +133,7 @@ void mtsvgpu_pack_read(const uint8_t* seq, uint32_t len, uint8_t* record) {
 
 int mtsvgpu_pack_reads(const uint8_t* seqs, const uint64_t* seq_off, uint64_t n_reads, uint8_t* packed,
                        uint64_t packed_cap, uint64_t* packed_bytes, int threads) {
-  if (!seq_off || (!packed && n_reads) || (n_reads && !seqs && seq_off[n_reads] != seq_off[0])) return MTSVGPU_EINVAL;
+  if (!seq_off || (n_reads && !seqs && seq_off[n_reads] != seq_off[0])) return MTSVGPU_EINVAL;
   for (uint64_t i = 0; i < n_reads; ++i)
     if (seq_off[i + 1] < seq_off[i] || seq_off[i + 1] - seq_off[i] > 0xffffffffull) return MTSVGPU_EINVAL;
   static const PackFn fn = pick();
@@ -156,6 +156,8 @@ int mtsvgpu_pack_reads(const uint8_t* seqs, const uint64_t* seq_off, uint64_t n_
   }
   if (packed_bytes) *packed_bytes = at[T];
   if (at[T] > packed_cap) return MTSVGPU_ELIMIT;
+  if (at[T] == 0) return 0;  // only empty reads: nothing to write
+  if (!packed) return MTSVGPU_EINVAL;
   auto work = [&](int t) {
     uint8_t* out = packed + at[t];
     const uint64_t end_of_bytes = seq_off[n_reads];

@@ -449,6 +449,23 @@ uint32_t emul_sub_batch_bounds(uint64_t n_reads, uint64_t step, int ramp, uint64
   return (uint32_t)b.size();
 }
 
+// packed reads: the device's unpacker (core.cuh::unpack_word) applied to a record, next to the planes the device
+// computes from the raw bytes (encode_fwd_word).  out: W words of {lo, hi, nn} for each of the two routes.
+// `from_record`: a record made elsewhere (the product's AVX2 / SWAR packer); NULL = core.cuh::pack_read.
+uint32_t emul_packed_words(const uint8_t* seq, uint32_t L, const uint8_t* from_record, uint64_t* unpacked,
+                           uint64_t* encoded) {
+  std::vector<uint8_t> rec(packed_record_bytes(L) + 1);
+  if (from_record) memcpy(rec.data(), from_record, packed_record_bytes(L));
+  else pack_read(seq, L, rec.data());
+  const uint32_t W = (L + 63) >> 6;
+  for (uint32_t w = 0; w < W; ++w) {
+    ReadWord a = unpack_word(rec.data(), L, w), b = encode_fwd_word(seq, L, w, false);
+    unpacked[3 * w] = a.lo, unpacked[3 * w + 1] = a.hi, unpacked[3 * w + 2] = a.nn;
+    encoded[3 * w] = b.lo, encoded[3 * w + 1] = b.hi, encoded[3 * w + 2] = b.nn;
+  }
+  return W;
+}
+
 void emul_free(void* p) { free(p); }
 
 void emul_myers_counters(unsigned long long* blocks, unsigned long long* cols, int reset) {

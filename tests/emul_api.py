@@ -72,6 +72,8 @@ def lib():
                                    C.c_uint32, C.c_int]
     L.emul_bin_reads.argtypes = [vp, vp, vp, C.c_uint64, C.POINTER(Params), C.POINTER(vp), C.POINTER(vp)]
     L.emul_free.argtypes = [vp]
+    L.emul_packed_words.restype = C.c_uint32
+    L.emul_packed_words.argtypes = [C.c_char_p, C.c_uint32, vp, vp, vp]
     _LIB = L
     return L
 
@@ -171,3 +173,19 @@ def sub_batch_bounds(n_reads, step, ramp):
     buf = (C.c_uint64 * 4096)()
     n = lib().emul_sub_batch_bounds(n_reads, step, int(ramp), buf, 4096)
     return [int(buf[i]) for i in range(min(n, 4096))]
+
+
+def packed_words(seq, record=None):
+    """(planes unpacked from the read's packed record, planes encoded from its raw bytes): two uint64 arrays of
+    3 words per 64 bases.  record: bytes of a record made by another packer (None: core.cuh::pack_read)."""
+    import numpy as np
+    seq = bytes(seq)
+    W = (len(seq) + 63) // 64
+    a = np.zeros(3 * max(W, 1), np.uint64)
+    b = np.zeros(3 * max(W, 1), np.uint64)
+    rec = None
+    if record is not None:
+        rec = np.frombuffer(bytes(record), dtype=np.uint8).copy()
+    lib().emul_packed_words(seq, len(seq), rec.ctypes.data if rec is not None and len(rec) else None,
+                            a.ctypes.data, b.ctypes.data)
+    return a[:3 * W], b[:3 * W]

@@ -52,9 +52,34 @@ def test_packer_matches_the_format():
     got, _ = pack_reads_planes((cat, off), threads=4)
     assert len(got) == 20000 * 57
     assert np.array_equal(got, _pack_numpy(cat, off))
-    # empty batch
+    # empty batch, a batch of empty reads, an empty read among others
     got, _ = pack_reads_planes((np.zeros(0, np.uint8), np.zeros(1, np.uint64)))
     assert len(got) == 0
+    got, off = pack_reads_planes([b"", b""])
+    assert len(got) == 0 and off.tolist() == [0, 0, 0]
+    got, off = pack_reads_planes([b"", b"ACGTN", b""])
+    assert got.tolist() == [0b01010, 0b01100, 0b10000]
+
+
+def test_device_unpacker_gives_the_encoders_planes(emul):
+    """core.cuh::unpack_word (what unpack_reads_kernel runs per read) on a packed record == the bit planes the device
+    encodes from the raw bytes (encode_fwd_word), for records from core.cuh::pack_read and from the product's
+    AVX2 / SWAR packer; garbage in a record's padding bits and lo/hi bits under an N are ignored."""
+    import numpy as np
+    for seed in range(2):
+        for s in _odd_reads(seed + 20, 300):
+            a, b = emul.packed_words(s)
+            assert np.array_equal(a, b), (seed, len(s))
+            rec, _ = pack_reads_planes([s])
+            a2, b2 = emul.packed_words(s, rec)
+            assert np.array_equal(a2, b2), (seed, len(s))
+            if len(s) % 8 and len(rec):
+                dirty = bytearray(rec.tobytes())
+                pb = (len(s) + 7) // 8
+                for pl in range(3):
+                    dirty[pl * pb + pb - 1] |= (0xFF << (len(s) % 8)) & 0xFF  # set every padding bit
+                a3, b3 = emul.packed_words(s, bytes(dirty))
+                assert np.array_equal(a3, b3)
 
 
 @pytest.mark.gpu
