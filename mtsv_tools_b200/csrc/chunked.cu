@@ -123,20 +123,12 @@ __global__ void __launch_bounds__(256) chunk_push_kernel(PeerTable pt, CommLayou
   __threadfence_system();
 }
 
-__global__ void chunk_signal_kernel(PeerTable pt, uint32_t world, uint32_t rank, uint32_t epoch, int variant) {
+// every pushing thread fenced its own stores at system scope before the push kernel ended, and this kernel starts
+// after that one has completed; the flag itself is a system-scope release store
+__global__ void chunk_signal_kernel(PeerTable pt, uint32_t world, uint32_t rank, uint32_t epoch) {
   const uint32_t d = threadIdx.x;
   if (d >= world) return;
-  uint32_t* flag = &reinterpret_cast<CommHeader*>(pt.base[d])->flags[rank];
-  if (variant == 0) {
-    __threadfence_system();
-    st_release_sys(flag, epoch);
-  } else if (variant == 1) {
-    st_release_sys(flag, epoch);
-  } else {
-    // every pushing thread fenced its own stores at system scope before the push kernel ended, and this kernel
-    // starts after that one has completed: the flag cannot overtake the data
-    asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(epoch) : "memory");
-  }
+  st_release_sys(&reinterpret_cast<CommHeader*>(pt.base[d])->flags[rank], epoch);
 }
 
 // status: 0 ok, 1 a rank overflowed its slot, 2 timed out waiting for a peer
@@ -321,7 +313,6 @@ int bin_batch_chunked(mtsvgpu_index* h, mtsvgpu_comm* c, const uint8_t* d_seqs, 
   cudaStream_t st = h->stream;
   static const bool trace = getenv("MTSV_B200_TRACE") != nullptr;  // phase times on stderr
   cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
-  static const bool no_host_status = getenv("MTSV_B200_CHUNK_NOHOST") != nullptr;  // experiment knob
   if (trace) {
     for (auto& e : ev) cudaEventCreate(&e);
     cudaEventRecord(ev[0], st);
@@ -339,12 +330,10 @@ int bin_batch_chunked(mtsvgpu_index* h, mtsvgpu_comm* c, const uint8_t* d_seqs, 
                 c->rank, parity, d_overflow);
   }
   if (trace) cudaEventRecord(ev[1], st);
-  static const int sig_variant = getenv("MTSV_B200_CHUNK_SIGNAL") ? atoi(getenv("MTSV_B200_CHUNK_SIGNAL")) : 1;
-  MTSV_LAUNCH(chunk_signal_kernel, 1, 32, 0, st, c->peers, c->world, c->rank, epoch, sig_variant);
+  MTSV_LAUNCH(chunk_signal_kernel, 1, 32, 0, st, c->peers, c->world, c->rank, epoch);
   const long long timeout_cycles = c->timeout_cycles;  // 30 s: a peer that never arrives is an error
   if (trace) cudaEventRecord(ev[4], st);
-  MTSV_LAUNCH(chunk_wait_kernel, 1, 32, 0, st, c->base, c->world, epoch, timeout_cycles, c->d_status,
-              no_host_status ? c->d_status + 2 : c->h_status_dev);
+  MTSV_LAUNCH(chunk_wait_kernel, 1, 32, 0, st, c->base, c->world, epoch, timeout_cycles, c->d_status, c->h_status_dev);
   if (trace) cudaEventRecord(ev[2], st);
   // ---- merge epilogue over the world slots of my range (src/collapse.rs:597-602) ----
   const mtsvgpu_hit* part_hits[kMaxRanks];
