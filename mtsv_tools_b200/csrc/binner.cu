@@ -1470,142 +1470,6 @@ __global__ void __launch_bounds__(128) cand_leader_kernel(BinsView bv, uint32_t 
   }
 }
 
-// ------------------------------------------------------------------------------------------
-// Duplicate windows (redundant references: most candidate windows of a strand are byte-identical copies in
-// near-identical strains).  The edit distance is a function of the read and the window's symbols, so one alignment
-// per distinct window is enough: cand_dedup_kernel hashes every window, makes the first candidate of a strand with a
-// given hash the representative and compares every other member with it symbol for symbol (a hash collision just
-// leaves the member on its own); only representatives are verified, the members copy the result
-// (cand_propagate_kernel).
-// ------------------------------------------------------------------------------------------
-// 16 symbols (4 bits each) of the text starting at symbol position `pos`
-__device__ __forceinline__ uint64_t text4_chunk(const uint64_t* __restrict__ t4, uint64_t last_word, uint32_t pos) {
-  const uint64_t w = pos >> 4;
-  const uint32_t sh = (pos & 15u) * 4u;
-  const uint64_t a = __ldg(t4 + (w < last_word ? w : last_word));
-  if (sh == 0) return a;
-  const uint64_t b = __ldg(t4 + (w + 1 < last_word ? w + 1 : last_word));
-  return (a >> sh) | (b << (64 - sh));
-}
-
-__device__ __forceinline__ uint32_t window_hash(const CandRec& c, const uint64_t* __restrict__ t4, uint64_t last_word) {
-  const uint32_t T = c.end - c.start;
-  uint64_t h = 0x9E3779B97F4A7C15ull ^ T;
-  for (uint32_t j = 0; j < T; j += 16) {
-    uint64_t v = text4_chunk(t4, last_word, c.start + j);
-    if (T - j < 16) v &= (1ull << (4 * (T - j))) - 1;
-    h = (h ^ v) * 0xFF51AFD7ED558CCDull;
-    h ^= h >> 32;
-  }
-  return (uint32_t)(h ^ (h >> 31)) & 0x7fffffffu;
-}
-
-__device__ __forceinline__ bool windows_equal(const CandRec& c, const CandRec& r, const uint64_t* __restrict__ t4,
-                                              uint64_t last_word) {
-  const uint32_t T = c.end - c.start;
-  if (r.end - r.start != T) return false;
-  for (uint32_t j = 0; j < T; j += 16) {
-    uint64_t a = text4_chunk(t4, last_word, c.start + j), b = text4_chunk(t4, last_word, r.start + j);
-    if (T - j < 16) {
-      const uint64_t m = (1ull << (4 * (T - j))) - 1;
-      a &= m;
-      b &= m;
-    }
-    if (a != b) return false;
-  }
-  return true;
-}
-
-// lead[c] = the first candidate of c's strand whose window holds the same symbols (c itself when there is none, when
-// the strand has more candidates than the warp's map takes, or when a hash collision gets in the way).  One pass:
-// a lane reads its candidate's window once for the hash, and once more (from L1) against the representative's.
-__global__ void __launch_bounds__(128) cand_dedup_kernel(uint32_t nq, const uint32_t* __restrict__ cand_off,
-                                                         const CandRec* __restrict__ cand, const uint64_t* __restrict__ t4,
-                                                         uint64_t last_word, uint32_t* __restrict__ lead) {
-  __shared__ uint32_t s_key[4][kLeaderSlots];
-  __shared__ uint32_t s_val[4][kLeaderSlots];
-  const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
-  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  uint32_t b = 0, nc = 0;
-  if (q < nq) {
-    b = cand_off[q];
-    nc = cand_off[q + 1] - b;
-  }
-  if (nc && nc <= kLightItems) {
-    uint32_t hk[kLightItems];
-    for (uint32_t i = 0; i < nc; ++i) hk[i] = window_hash(cand[b + i], t4, last_word);
-    for (uint32_t i = 0; i < nc; ++i) {
-      uint32_t l = b + i;
-      for (uint32_t j = 0; j < i; ++j)
-        if (hk[j] == hk[i] && lead[b + j] == b + j && windows_equal(cand[b + i], cand[b + j], t4, last_word)) {
-          l = b + j;
-          break;
-        }
-      lead[b + i] = l;
-    }
-  }
-  unsigned heavy = __ballot_sync(0xffffffffu, nc > kLightItems);
-  while (heavy) {
-    const int sl = __ffs(heavy) - 1;
-    heavy &= heavy - 1;
-    const uint32_t nc_s = __shfl_sync(0xffffffffu, nc, sl), b_s = __shfl_sync(0xffffffffu, b, sl);
-    if (nc_s > kLeaderSlots / 2) {
-      for (uint32_t i = lane; i < nc_s; i += 32) lead[b_s + i] = b_s + i;
-      continue;
-    }
-    uint32_t* key = s_key[warp];
-    uint32_t* val = s_val[warp];
-    for (uint32_t j = lane; j < kLeaderSlots; j += 32) key[j] = 0;
-    __syncwarp();
-    for (uint32_t t0 = 0; t0 < nc_s; t0 += 32) {
-      const uint32_t c = t0 + lane;
-      const bool in = c < nc_s;
-      CandRec me{0, 0, 0, 0};
-      uint32_t hk = 0, l = b_s + c;
-      bool fresh = in;  // no representative with this hash yet
-      if (in) {
-        me = cand[b_s + c];
-        hk = window_hash(me, t4, last_word);
-        uint32_t h = (hk * 2654435761u) >> 22;
-        for (;;) {
-          const uint32_t v = key[h];
-          if (v == hk + 1u) {
-            const uint32_t r = val[h];
-            fresh = false;
-            if (windows_equal(me, cand[r], t4, last_word)) l = r;  // (a collision leaves the candidate on its own)
-            break;
-          }
-          if (v == 0) break;
-          h = (h + 1) & (kLeaderSlots - 1);
-        }
-      }
-      const unsigned fm = __ballot_sync(0xffffffffu, fresh);
-      const unsigned peers = __match_any_sync(0xffffffffu, fresh ? hk : (0x80000000u | lane)) & fm;
-      if (fresh) {
-        const unsigned first = (unsigned)(__ffs(peers) - 1);
-        if (first != lane) {
-          const uint32_t r = b_s + t0 + first;  // the step's first candidate with this hash becomes the representative
-          if (windows_equal(me, cand[r], t4, last_word)) l = r;
-        } else {
-          uint32_t h = (hk * 2654435761u) >> 22;
-          while (atomicCAS(&key[h], 0u, hk + 1u) != 0u) h = (h + 1) & (kLeaderSlots - 1);
-          val[h] = l;
-        }
-      }
-      if (in) lead[b_s + c] = l;
-      __syncwarp();
-    }
-  }
-}
-
-__global__ void __launch_bounds__(256) cand_propagate_kernel(const uint32_t* __restrict__ lead, uint32_t n,
-                                                             uint32_t* __restrict__ edit) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const uint32_t l = lead[i];
-  if (l != i) edit[i] = edit[l];
-}
-
 // round 1: positions of `order` whose candidate is a leader; round 2: members whose leader did not pass
 __global__ void cand_round_flags_kernel(const uint32_t* __restrict__ order, const uint32_t* __restrict__ lead,
                                         const uint32_t* __restrict__ edit, uint32_t n, int round,
@@ -1946,14 +1810,8 @@ static int run_sub_batch(mtsvgpu_index* h, Lane& ln, const Params& p, const uint
       // to be two windows of the same sequence — and the sub-batch has more candidates than strands)
       grouped = !need_ssw && !legacy_verifier() && (ge ? ge[0] != '0' : (n_cand > nq && ix.n_bins > ix.n_taxids));
     }
-    // duplicate-window pass (below): heavy sub-batches, eight or more candidates per strand on average
-    const char* dedup_env = getenv("MTSV_B200_DEDUP");
-    const bool maybe_dedup = !need_ssw && !legacy_verifier() && (dedup_env ? dedup_env[0] != '0' : (uint64_t)n_cand >= 8ull * nq);
-    // profiling: the reference columns walked by the verifier are counted once, by whichever pass decides what is verified
-    const bool count_all_windows = h->profiling && !grouped && !maybe_dedup;
-    bool windows_counted = count_all_windows;
     MTSV_LAUNCH(cand_class_kernel, (n_cand + 255) / 256, 256, 0, st, ws.cand_dense.as<CandRec>(), n_cand,
-                ws.cand_flag.as<uint32_t>(), count_all_windows ? d_ctr : nullptr, 1);
+                ws.cand_flag.as<uint32_t>(), (h->profiling && !grouped) ? d_ctr : nullptr, 1);
     MTSV_TRY(exclusive_scan_u32(ws.cand_flag.as<uint32_t>(), ws.cand_flag.as<uint32_t>(), n_cand, ws.scan_tmp,
                                 nullptr, st));
     MTSV_LAUNCH(cand_order_kernel, (n_cand + 255) / 256, 256, 0, st, ws.cand_dense.as<CandRec>(),
@@ -1977,11 +1835,9 @@ static int run_sub_batch(mtsvgpu_index* h, Lane& ln, const Params& p, const uint
       const uint32_t n1 = (uint32_t)hc.verified[0];
       if ((uint64_t)n1 * 10 > (uint64_t)n_cand * 9 && !(getenv("MTSV_B200_GROUP_VERIFY") && n1 < n_cand)) {
         grouped = false;  // (nearly) one candidate per (strand, TaxID): holding the few others back does not pay
-        if (h->profiling && !maybe_dedup) {
+        if (h->profiling)
           MTSV_LAUNCH(cand_class_kernel, (n_cand + 255) / 256, 256, 0, st, ws.cand_dense.as<CandRec>(), n_cand,
                       (uint32_t*)nullptr, d_ctr, 0);
-          windows_counted = true;
-        }
       } else {
         MTSV_CUDA_TRY(cudaMemsetAsync(ws.cand_edit.p, 0xff, (size_t)n_cand * 4, st));  // kNoEdit until verified
         BinnerJobs round_jobs = jobs;
@@ -2005,44 +1861,10 @@ static int run_sub_batch(mtsvgpu_index* h, Lane& ln, const Params& p, const uint
                                       ws.cand_edit.as<uint32_t>(), st));
         }
         n_verified = (uint64_t)n1 + n2;
-        windows_counted = true;
       }
     }
-    // duplicate windows: heavy sub-batches (eight or more candidates per strand on average) that the TaxID rounds
-    // did not take.  MTSV_B200_DEDUP=0|1 overrides.
-    bool dedup = !grouped && maybe_dedup;
-    if (dedup) {
-      MTSV_TRY(ws.cand_lead.reserve((size_t)n_cand * 4));
-      MTSV_TRY(ws.cand_order2.reserve((size_t)n_cand * 4));
-      uint32_t* flag = ws.cand_flag.as<uint32_t>();
-      MTSV_LAUNCH(cand_dedup_kernel, (nq + 127) / 128, 128, 0, st, nq, ws.cand_off.as<uint32_t>(),
-                  ws.cand_dense.as<CandRec>(), ix.text4, ix.text4_words - 1, ws.cand_lead.as<uint32_t>());
-      MTSV_LAUNCH(cand_round_flags_kernel, (n_cand + 255) / 256, 256, 0, st, ws.cand_order.as<uint32_t>(),
-                  ws.cand_lead.as<uint32_t>(), ws.cand_edit.as<uint32_t>(), n_cand, 1, flag);
-      MTSV_TRY(exclusive_scan_u32(flag, flag, n_cand, ws.scan_tmp, (uint64_t*)&d_ctr->verified[0], st));
-      MTSV_TRY(fetch_counters(ln, d_ctr, &hc, st));
-      const uint32_t n1 = (uint32_t)hc.verified[0];
-      if ((uint64_t)n1 * 10 > (uint64_t)n_cand * 9 && !(dedup_env && n1 < n_cand)) {
-        dedup = false;  // hardly any duplicates: the plain launch below
-        if (h->profiling && !windows_counted)
-          MTSV_LAUNCH(cand_class_kernel, (n_cand + 255) / 256, 256, 0, st, ws.cand_dense.as<CandRec>(), n_cand,
-                      (uint32_t*)nullptr, d_ctr, 0);
-      } else {
-        BinnerJobs rep_jobs = jobs;
-        rep_jobs.order = ws.cand_order2.as<uint32_t>();
-        rep_jobs.n = n1;
-        MTSV_LAUNCH(cand_compact_order_kernel, (n_cand + 255) / 256, 256, 0, st, ws.cand_order.as<uint32_t>(), flag,
-                    n_cand, ws.cand_dense.as<CandRec>(), ws.cand_order2.as<uint32_t>(),
-                    (h->profiling && !windows_counted) ? d_ctr : nullptr);
-        MTSV_TRY(launch_verify_warp(rep_jobs, ix, std::max(hc.max_len, 1u), min_len == hc.max_len,
-                                    ws.cand_edit.as<uint32_t>(), st));
-        MTSV_LAUNCH(cand_propagate_kernel, (n_cand + 255) / 256, 256, 0, st, ws.cand_lead.as<uint32_t>(), n_cand,
-                    ws.cand_edit.as<uint32_t>());
-        n_verified = n1;
-      }
-    }
-    if (grouped || dedup) {
-      // (launched above)
+    if (grouped) {
+      // (both rounds launched above)
     } else if (!need_ssw && !legacy_verifier()) {
       MTSV_TRY(launch_verify_warp(jobs, ix, std::max(hc.max_len, 1u), min_len == hc.max_len,
                                   ws.cand_edit.as<uint32_t>(), st));

@@ -135,7 +135,7 @@ struct BatchWorkspace {
   DevBuf hit_keys, cand_sparse, cand_stage;
   // per candidate (dense)
   DevBuf cand_dense, cand_q, cand_edit, hit_tmp, cand_flag, cand_order, cand_end, ssw_list, ssw_scratch;
-  DevBuf cand_lead, cand_order2;  // grouped verification: leader of each candidate, compacted visiting order
+  DevBuf cand_lead, cand_order2;  // two-round verification: leader of each candidate, compacted visiting order
   // bit-plane encoded reads of the sub-batch
   DevBuf enc;
   // scan scratch, counters, worklists

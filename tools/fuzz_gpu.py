@@ -39,11 +39,6 @@ def main():
             os.environ.pop("MTSV_B200_GROUP_VERIFY", None)
         else:
             os.environ["MTSV_B200_GROUP_VERIFY"] = gv
-        dd = crng.choice([None, "1", "0"])  # duplicate-window pass: own rule, forced on, forced off
-        if dd is None:
-            os.environ.pop("MTSV_B200_DEDUP", None)
-        else:
-            os.environ["MTSV_B200_DEDUP"] = dd
         h1, o1 = ix.bin_reads(reads, p)
         pg = Params(edit_rate=p.edit_rate, seed_size=p.seed_size, seed_gap=p.seed_gap, min_seed=p.min_seed,
                     max_hits=p.max_hits, tune_max_hits=p.tune_max_hits,
